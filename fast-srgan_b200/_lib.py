@@ -1,0 +1,89 @@
+"""ctypes binding of libfsr_b200.so (include/fsr_b200.h).  No CPU fallback: a missing library or a
+non-zero return code raises - the product path must fail loudly (never route through oracle/)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfsr_b200.so")
+FSR_MAX_LAYERS = 32
+FSR_F16, FSR_BF16 = 0, 1
+EPI_RAW_STATS, EPI_BIAS_ACT, EPI_PS_PRELU, EPI_HEAD_TANH = 0, 1, 2, 3
+ACT_NONE, ACT_RELU, ACT_LRELU, ACT_PRELU = 0, 1, 2, 3
+K_NONE, K_NECK, K_CONV_RES, K_IN_APPLY, K_CONV_UP, K_CONV_HEAD, K_CONV_BIAS_ACT = -1, 0, 1, 2, 3, 4, 5
+
+_vp, _fp, _i, _f, _sz = C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_size_t
+
+
+class FsrGeneratorParams(C.Structure):
+    _fields_ = [
+        ("n_filters", _i), ("n_layers", _i), ("dtype", _i), ("reserved", _i),
+        ("neck_w", _vp), ("neck_b", _vp), ("neck_alpha", _vp),
+        ("stem_w1", _vp * FSR_MAX_LAYERS), ("stem_alpha", _vp * FSR_MAX_LAYERS), ("stem_w2", _vp * FSR_MAX_LAYERS),
+        ("bott_w", _vp),
+        ("up_w", _vp * 2), ("up_b", _vp * 2), ("up_alpha", _vp * 2),
+        ("head_w", _vp), ("head_b", _vp),
+    ]
+
+
+_SIGS = {
+    "fsr_abi_version": (_i, []),
+    "fsr_error_string": (C.c_char_p, [_i]),
+    "fsr_pack_conv3x3_weight": (_i, [_fp, _fp, _vp, _fp, _i, _i, _i, _i, _i, _vp]),
+    "fsr_conv3x3_c64": (_i, [_vp, _vp, _vp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _f, _i, _i, _vp]),
+    "fsr_neck_conv3x3": (_i, [_vp, _fp, _fp, _fp, _vp, _i, _i, _i, _i, _i, _f, _i, _i, _i, _vp]),
+    "fsr_instnorm_apply": (_i, [_vp, _fp, _vp, _vp, _fp, _i, _i, _i, _i, _f, _f, _i, _vp]),
+    "fsr_pixel_shuffle2": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "fsr_nchw_f32_to_nhwc": (_i, [_fp, _vp, _i, _i, _i, _i, _vp]),
+    "fsr_nhwc_to_nchw_f32": (_i, [_vp, _fp, _i, _i, _i, _i, _vp]),
+    "fsr_profile_enable": (_i, [_i]),
+    "fsr_profile_read": (_i, [_vp, _i]),
+    "fsr_launch_count": (C.c_ulonglong, []),
+    "fsr_generator_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "fsr_generator_forward": (_i, [C.POINTER(FsrGeneratorParams), _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _i, _vp]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGS)
+_lib = None
+
+
+def load() -> C.CDLL:
+    """dlopen the in-tree library and set prototypes.  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing - build it with `python fast-srgan_b200/build.py` "
+                "(there is no CPU / PyTorch fallback for the hot path)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str = "fsr call"):
+    if rc != 0:
+        msg = load().fsr_error_string(rc).decode()
+        raise RuntimeError(f"{what} failed: {msg} (code {rc})")
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr(device=None):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def dtype_code(dt: torch.dtype) -> int:
+    if dt == torch.float16:
+        return FSR_F16
+    if dt == torch.bfloat16:
+        return FSR_BF16
+    raise ValueError(f"compute dtype must be float16 or bfloat16, got {dt}")

@@ -1,0 +1,278 @@
+// elementwise.cuh - HBM-bound kernels of the Fast-SRGAN hot path (CUDA cores, vectorised 16-B access).
+//   neck_conv3x3_kernel   : Conv2d(3->F,k3,p1)+bias+PReLU|LeakyReLU   (reference model.py:75-78, 143-146)
+//   instnorm_apply_kernel : InstanceNorm2d normalise (+PReLU|LeakyReLU) (+residual add)
+//                           (reference model.py:55-56, 65+69, 94+115, 132-133)
+//   pixel_shuffle2_kernel : torch.nn.PixelShuffle(2) on NHWC          (reference model.py:36)
+//   layout kernels        : NCHW fp32 <-> NHWC fp16/bf16 at the module boundary
+#pragma once
+#include "fsr_common.cuh"
+#include "conv3x3_tc.cuh"   // ActMode / apply_act
+
+namespace fsr {
+
+// ------------------------------------------------------------------ neck: direct 3->COUT conv
+// One thread = one output pixel x 64 output channels (blockIdx.y selects the 64-channel group).
+// Weights [27][64] fp32 in smem, read as broadcast float4.  Input: fp32 NCHW or uint8 NHWC
+// (uint8 path folds reference inference.py:50  x/127.5 - 1).  VGG mode folds model.py:21-22
+// ((x+1)/2 - mean)/std applied to in-image pixels only (zero padding comes AFTER the renorm).
+struct NeckParams {
+  const void* x;
+  const float* w;      // [COUT,3,3,3] OIHW fp32
+  const float* bias;   // [COUT]
+  const float* alpha;  // PReLU slope pointer (ACT_PRELU)
+  void* out;           // NHWC T [N,H,W,COUT]
+  int N, H, W, cout;
+  int act;
+  float slope;
+  int in_u8;
+  int vgg_norm;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(128) neck_conv3x3_kernel(const NeckParams p) {
+  __shared__ __align__(16) float sw[27 * 64];
+  __shared__ float sb[64];
+  const int cg = blockIdx.y;   // 64-channel group
+  for (int i = threadIdx.x; i < 27 * 64; i += blockDim.x) {
+    const int tap_ci = i / 64, co = i % 64;          // tap_ci = ci*9 + r*3 + s  (OIHW inner order)
+    sw[i] = p.w[(size_t)(cg * 64 + co) * 27 + tap_ci];
+  }
+  if (threadIdx.x < 64) sb[threadIdx.x] = p.bias ? p.bias[cg * 64 + threadIdx.x] : 0.f;
+  __syncthreads();
+  const float slope = (p.act == ACT_PRELU) ? __ldg(p.alpha) : p.slope;
+  const size_t total = (size_t)p.N * p.H * p.W;
+  const size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= total) return;
+  const int x = (int)(pix % p.W);
+  const int y = (int)((pix / p.W) % p.H);
+  const int n = (int)(pix / ((size_t)p.W * p.H));
+
+  float in[27];
+  const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
+#pragma unroll
+  for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int yy = y + r - 1, xx = x + s - 1;
+        float v = 0.f;
+        if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) {
+          if (p.in_u8) {
+            v = (float)reinterpret_cast<const uint8_t*>(p.x)[((size_t)(n * p.H + yy) * p.W + xx) * 3 + ci] / 127.5f - 1.0f;
+          } else {
+            v = reinterpret_cast<const float*>(p.x)[((size_t)(n * 3 + ci) * p.H + yy) * p.W + xx];
+          }
+          if (p.vgg_norm) v = ((v + 1.0f) / 2.0f - mean[ci]) / stdv[ci];
+        }
+        in[ci * 9 + r * 3 + s] = v;
+      }
+
+  float acc[64];
+#pragma unroll
+  for (int c = 0; c < 64; ++c) acc[c] = sb[c];
+#pragma unroll
+  for (int t = 0; t < 27; ++t) {
+    const float4* wr = reinterpret_cast<const float4*>(sw + t * 64);
+#pragma unroll
+    for (int c4 = 0; c4 < 16; ++c4) {
+      const float4 w4 = wr[c4];
+      acc[4 * c4 + 0] = fmaf(in[t], w4.x, acc[4 * c4 + 0]);
+      acc[4 * c4 + 1] = fmaf(in[t], w4.y, acc[4 * c4 + 1]);
+      acc[4 * c4 + 2] = fmaf(in[t], w4.z, acc[4 * c4 + 2]);
+      acc[4 * c4 + 3] = fmaf(in[t], w4.w, acc[4 * c4 + 3]);
+    }
+  }
+  T* o = reinterpret_cast<T*>(p.out) + pix * p.cout + cg * 64;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    uint4 pk;
+    pk.x = Cvt<T>::pack2(apply_act(acc[8 * k + 0], p.act, slope), apply_act(acc[8 * k + 1], p.act, slope));
+    pk.y = Cvt<T>::pack2(apply_act(acc[8 * k + 2], p.act, slope), apply_act(acc[8 * k + 3], p.act, slope));
+    pk.z = Cvt<T>::pack2(apply_act(acc[8 * k + 4], p.act, slope), apply_act(acc[8 * k + 5], p.act, slope));
+    pk.w = Cvt<T>::pack2(apply_act(acc[8 * k + 6], p.act, slope), apply_act(acc[8 * k + 7], p.act, slope));
+    reinterpret_cast<uint4*>(o)[k] = pk;
+  }
+}
+
+// ------------------------------------------------------------------ InstanceNorm apply
+// out = act((raw - mean[n,c]) * rstd[n,c]) (+ residual);  stats = [N][C][2] (sum, sumsq) fp32
+// accumulated by the producing conv's epilogue.  grid = (blocks_per_image, N).
+struct InApplyParams {
+  const void* raw;
+  const float* stats;
+  const void* residual;  // nullable
+  void* out;
+  const float* alpha;    // PReLU slope pointer
+  float slope;
+  int act;
+  int HW, C;
+  float eps;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) instnorm_apply_kernel(const InApplyParams p) {
+  extern __shared__ float s_ms[];  // mean[C], rstd[C]
+  float* s_mean = s_ms;
+  float* s_rstd = s_ms + p.C;
+  const int n = blockIdx.y;
+  const float inv_hw = 1.0f / (float)p.HW;
+  for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+    const float sum = p.stats[((size_t)n * p.C + c) * 2 + 0];
+    const float sq = p.stats[((size_t)n * p.C + c) * 2 + 1];
+    const float m = sum * inv_hw;
+    const float var = fmaxf(sq * inv_hw - m * m, 0.f);   // biased variance (InstanceNorm2d)
+    s_mean[c] = m;
+    s_rstd[c] = rsqrtf(var + p.eps);
+  }
+  __syncthreads();
+  const float slope = (p.act == ACT_PRELU) ? __ldg(p.alpha) : p.slope;
+  const int vec_per_pix = p.C / 8;
+  const size_t nvec = (size_t)p.HW * vec_per_pix;
+  const uint4* raw = reinterpret_cast<const uint4*>(p.raw) + (size_t)n * nvec;
+  const uint4* res = p.residual ? reinterpret_cast<const uint4*>(p.residual) + (size_t)n * nvec : nullptr;
+  uint4* out = reinterpret_cast<uint4*>(p.out) + (size_t)n * nvec;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % vec_per_pix) * 8;
+    const uint4 r = raw[i];
+    uint4 rs = make_uint4(0, 0, 0, 0);
+    if (res) rs = res[i];
+    const uint32_t ru[4] = {r.x, r.y, r.z, r.w};
+    const uint32_t su[4] = {rs.x, rs.y, rs.z, rs.w};
+    uint32_t ou[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = Cvt<T>::unpack2(ru[k]);
+      float a = (f.x - s_mean[c0 + 2 * k]) * s_rstd[c0 + 2 * k];
+      float b = (f.y - s_mean[c0 + 2 * k + 1]) * s_rstd[c0 + 2 * k + 1];
+      a = apply_act(a, p.act, slope);
+      b = apply_act(b, p.act, slope);
+      if (res) {
+        const float2 g = Cvt<T>::unpack2(su[k]);
+        a += g.x;
+        b += g.y;
+      }
+      ou[k] = Cvt<T>::pack2(a, b);
+    }
+    out[i] = make_uint4(ou[0], ou[1], ou[2], ou[3]);
+  }
+}
+
+// ------------------------------------------------------------------ standalone PixelShuffle(2), NHWC
+// out[n, 2y+i, 2x+j, c] = in[n, y, x, 4c + 2i + j]   (reference channel order, model.py:36)
+// One thread: one input pixel x 8 output channels -> reads 32 consecutive input channels (64 B),
+// writes one 16-B vector to each of the 4 output pixels.
+template <typename T>
+__global__ void __launch_bounds__(256) pixel_shuffle2_kernel(const T* __restrict__ in, T* __restrict__ out, int N,
+                                                             int H, int W, int C /*output channels*/) {
+  const int groups = C / 8;
+  const size_t total = (size_t)N * H * W * groups;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % groups);
+    const size_t pix = idx / groups;
+    const int x = (int)(pix % W);
+    const int y = (int)((pix / W) % H);
+    const int n = (int)(pix / ((size_t)W * H));
+    const uint4* src = reinterpret_cast<const uint4*>(in + pix * (size_t)(4 * C) + (size_t)g * 32);
+    uint32_t w[16];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint4 v = src[k];
+      w[4 * k + 0] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
+    }
+    // w[] holds 32 halfs: element e = 4*cl + 2i + j  (cl = local out channel 0..7)
+    const uint16_t* h = reinterpret_cast<const uint16_t*>(w);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {   // q = 2i + j
+      uint32_t o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        o[k] = (uint32_t)h[4 * (2 * k) + q] | ((uint32_t)h[4 * (2 * k + 1) + q] << 16);
+      const int oy = 2 * y + (q >> 1), ox = 2 * x + (q & 1);
+      uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)(n * 2 * H + oy) * (2 * W) + ox) * C + (size_t)g * 8);
+      *dst = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ layout conversion
+template <typename T>
+__global__ void __launch_bounds__(256) nchw_f32_to_nhwc_kernel(const float* __restrict__ in, T* __restrict__ out, int N,
+                                                               int C, int HW) {
+  // tile transpose through smem: 32 pixels x 32 channels
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int j = ty; j < 32; j += 8) {
+    const int c = c0 + j, pp = p0 + tx;
+    tile[j][tx] = (c < C && pp < HW) ? in[((size_t)n * C + c) * HW + pp] : 0.f;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int pp = p0 + j, c = c0 + tx;
+    if (pp < HW && c < C) out[((size_t)n * HW + pp) * C + c] = Cvt<T>::from_f(tile[tx][j]);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) nhwc_to_nchw_f32_kernel(const T* __restrict__ in, float* __restrict__ out, int N,
+                                                               int C, int HW) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int j = ty; j < 32; j += 8) {
+    const int pp = p0 + j, c = c0 + tx;
+    tile[j][tx] = (pp < HW && c < C) ? Cvt<T>::to_f(in[((size_t)n * HW + pp) * C + c]) : 0.f;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int c = c0 + j, pp = p0 + tx;
+    if (c < C && pp < HW) out[((size_t)n * C + c) * HW + pp] = tile[tx][j];
+  }
+}
+
+// ------------------------------------------------------------------ weight packing
+// OIHW fp32 [Cout, Cin, 3, 3]  ->  [9][cout_pad][Cin] T  (tap-major, each row = Cin contiguous = K-major B operand)
+// ps_perm != 0: GEMM row n' = (2i+j)*(Cout/4) + c  holds reference output channel oc = 4c + 2i + j, so that
+// the PixelShuffle(2) of model.py:36 becomes a contiguous 64-channel store per (i,j).
+template <typename T>
+__global__ void pack_conv3x3_weight_kernel(const float* __restrict__ w, T* __restrict__ out, int cout, int cin,
+                                           int cout_pad, int ps_perm) {
+  const size_t total = (size_t)9 * cout_pad * cin;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int ci = (int)(idx % cin);
+    const int row = (int)((idx / cin) % cout_pad);
+    const int tap = (int)(idx / ((size_t)cin * cout_pad));
+    float v = 0.f;
+    if (row < cout) {
+      int oc = row;
+      if (ps_perm) {
+        const int cq = cout / 4;
+        const int q = row / cq, c = row % cq;
+        oc = 4 * c + q;
+      }
+      v = w[((size_t)oc * cin + ci) * 9 + tap];
+    }
+    out[idx] = Cvt<T>::from_f(v);
+  }
+}
+
+__global__ void permute_bias_ps_kernel(const float* __restrict__ b, float* __restrict__ out, int cout, int cout_pad,
+                                       int ps_perm) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= cout_pad) return;
+  float v = 0.f;
+  if (row < cout) {
+    int oc = row;
+    if (ps_perm) {
+      const int cq = cout / 4;
+      oc = 4 * (row % cq) + row / cq;
+    }
+    v = b[oc];
+  }
+  out[row] = v;
+}
+
+}  // namespace fsr

@@ -1,0 +1,225 @@
+"""Drop-in mirror of the reference's model.py surface on the B200 kernels.
+
+`Generator(config)`, `Discriminator(config)`, `VGG19()` keep the reference constructor
+signatures (model.py:73, :140, :6), forward(x: fp32 NCHW) -> fp32 NCHW, and IDENTICAL
+state_dict keys/shapes, so reference checkpoints load unchanged
+(including the `_orig_mod.` prefix handled like inference.py:31-32).
+
+The arithmetic never touches torch.nn.functional: parameters live in small holder modules and
+forward() drives libfsr_b200.so (hand-written sm_100a kernels) through ctypes.  There is no
+CPU fallback - a non-CUDA input or a missing library raises.
+"""
+from __future__ import annotations
+
+import math
+import os
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib as L
+
+
+def _default_dtype() -> torch.dtype:
+    return torch.bfloat16 if os.environ.get("FSR_DTYPE", "fp16").lower() in ("bf16", "bfloat16") else torch.float16
+
+
+class _Conv(torch.nn.Module):
+    """Parameter holder with torch.nn.Conv2d's names, shapes and default init (kaiming_uniform a=sqrt(5))."""
+
+    def __init__(self, cin: int, cout: int, k: int = 3, bias: bool = True):
+        super().__init__()
+        self.weight = torch.nn.Parameter(torch.empty(cout, cin, k, k))
+        torch.nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
+        if bias:
+            bound = 1.0 / math.sqrt(cin * k * k)
+            self.bias = torch.nn.Parameter(torch.empty(cout).uniform_(-bound, bound))
+        else:
+            self.register_parameter("bias", None)
+
+
+class _Slope(torch.nn.Module):
+    """torch.nn.PReLU() holder: one shared slope, init 0.25 (model.py:37,56,77)."""
+
+    def __init__(self):
+        super().__init__()
+        self.weight = torch.nn.Parameter(torch.full((1,), 0.25))
+
+
+class _Empty(torch.nn.Module):
+    """Parameter-less placeholder keeping Sequential indices aligned with the reference."""
+
+
+class ResidualBlock(torch.nn.Module):
+    """model.py:43-69 - conv1, bn1(IN), relu1(PReLU), conv2, bn2(IN), + x."""
+
+    def __init__(self, in_channels: int, out_channels: int):
+        super().__init__()
+        self.conv1 = _Conv(in_channels, out_channels, bias=False)
+        self.bn1 = _Empty()
+        self.relu1 = _Slope()
+        self.conv2 = _Conv(in_channels, out_channels, bias=False)
+        self.bn2 = _Empty()
+
+
+class UpSamplingBlock(torch.nn.Module):
+    """model.py:26-40 - conv(F->4F), PixelShuffle(2), PReLU."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.conv = _Conv(config.n_filters, config.n_filters * 4, bias=True)
+        self.phase_shift = _Empty()
+        self.relu = _Slope()
+
+
+class SimpleBlock(torch.nn.Module):
+    """model.py:120-136 - conv(stride s, no bias), IN, LeakyReLU(0.01)."""
+
+    def __init__(self, in_channels: int, out_channels: int, stride: int):
+        super().__init__()
+        self.stride = stride
+        self.conv = _Conv(in_channels, out_channels, bias=False)
+        self.bn = _Empty()
+        self.act = _Empty()
+
+
+def _strip_prefix(state_dict):
+    return {k.replace("_orig_mod.", ""): v for k, v in state_dict.items()}
+
+
+class Generator(torch.nn.Module):
+    """Reference model.py:72-117 on B200 kernels.
+
+    forward(x) : fp32 NCHW [N,3,H,W] in [-1,1] -> fp32 NCHW [N,3,4H,4W]   (model.py:112-117)
+    super_resolve_u8(img) : uint8 NHWC -> uint8 NHWC, the inference.py:48-56 pipeline fused into
+    the neck load and the head store.
+    """
+
+    def __init__(self, config, compute_dtype: Optional[torch.dtype] = None):
+        super().__init__()
+        self.n_filters = int(config.n_filters)
+        self.n_layers = int(config.n_layers)
+        F_ = self.n_filters
+        self.neck = torch.nn.Sequential(_Conv(3, F_, bias=True), _Slope())
+        self.stem = torch.nn.Sequential(*[ResidualBlock(F_, F_) for _ in range(self.n_layers)])
+        self.bottleneck = torch.nn.Sequential(_Conv(F_, F_, bias=False), _Empty())
+        self.upsampling = torch.nn.Sequential(UpSamplingBlock(config), UpSamplingBlock(config))
+        self.head = torch.nn.Sequential(_Conv(F_, 3, bias=True), _Empty())
+        self.compute_dtype = compute_dtype or _default_dtype()
+        self.l2_group = int(os.environ.get("FSR_L2_GROUP", "0"))   # images per L2-resident group (0 = all)
+        self._packed: Dict[str, torch.Tensor] = {}
+        self._packed_key = None
+        self._ws = None
+
+    # -- checkpoints saved from torch.compile'd modules carry `_orig_mod.` (inference.py:30-33)
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        return super().load_state_dict(_strip_prefix(state_dict), strict=strict, assign=assign)
+
+    # ------------------------------------------------------------------ weight packing
+    def _conv_list(self):
+        convs = [("neck", self.neck[0])]
+        for i, blk in enumerate(self.stem):
+            convs += [(f"s{i}a", blk.conv1), (f"s{i}b", blk.conv2)]
+        convs += [("bott", self.bottleneck[0]), ("up0", self.upsampling[0].conv), ("up1", self.upsampling[1].conv),
+                  ("head", self.head[0])]
+        return convs
+
+    def _pack(self):
+        """(Re)pack OIHW fp32 parameters into the kernel layout when they changed."""
+        dev = self.neck[0].weight.device
+        key = (str(dev), self.compute_dtype) + tuple((c.weight._version, c.weight.data_ptr()) for _, c in self._conv_list())
+        if key == self._packed_key:
+            return
+        if self.n_filters != 64:
+            raise RuntimeError("this build of libfsr_b200 supports generator.n_filters == 64 only")
+        lib, dt = L.load(), L.dtype_code(self.compute_dtype)
+        st = L.stream_ptr(dev)
+        pk: Dict[str, torch.Tensor] = {}
+
+        def pack(name, conv, cout_pad, ps):
+            cout, cin = conv.weight.shape[0], conv.weight.shape[1]
+            w = conv.weight.detach().float().contiguous()
+            b = conv.bias.detach().float().contiguous() if conv.bias is not None else None
+            wp = torch.empty(9 * cout_pad * cin, dtype=self.compute_dtype, device=dev)
+            bp = torch.empty(cout_pad, dtype=torch.float32, device=dev) if b is not None else None
+            L.check(lib.fsr_pack_conv3x3_weight(L.ptr(w), L.ptr(b), L.ptr(wp), L.ptr(bp), cout, cin, cout_pad, ps, dt, st),
+                    f"pack {name}")
+            pk[name + ".w"] = wp
+            if bp is not None:
+                pk[name + ".b"] = bp
+
+        for name, conv in self._conv_list():
+            if name == "neck":
+                pk["neck.w"] = conv.weight.detach().float().contiguous()
+                pk["neck.b"] = conv.bias.detach().float().contiguous()
+            elif name.startswith("up"):
+                pack(name, conv, 256, 1)
+            elif name == "head":
+                pack(name, conv, 16, 0)
+            else:
+                pack(name, conv, 64, 0)
+        self._packed, self._packed_key = pk, key
+
+    def _params_struct(self) -> "L.FsrGeneratorParams":
+        self._pack()
+        pk = self._packed
+        P = L.FsrGeneratorParams()
+        P.n_filters, P.n_layers, P.dtype = self.n_filters, self.n_layers, L.dtype_code(self.compute_dtype)
+        P.neck_w, P.neck_b = pk["neck.w"].data_ptr(), pk["neck.b"].data_ptr()
+        P.neck_alpha = self.neck[1].weight.data_ptr()
+        for i, blk in enumerate(self.stem):
+            P.stem_w1[i] = pk[f"s{i}a.w"].data_ptr()
+            P.stem_alpha[i] = blk.relu1.weight.data_ptr()
+            P.stem_w2[i] = pk[f"s{i}b.w"].data_ptr()
+        P.bott_w = pk["bott.w"].data_ptr()
+        for i in range(2):
+            P.up_w[i] = pk[f"up{i}.w"].data_ptr()
+            P.up_b[i] = pk[f"up{i}.b"].data_ptr()
+            P.up_alpha[i] = self.upsampling[i].relu.weight.data_ptr()
+        P.head_w, P.head_b = pk["head.w"].data_ptr(), pk["head.b"].data_ptr()
+        return P
+
+    def _workspace(self, N, H, W, dev):
+        need = L.load().fsr_generator_workspace_bytes(N, H, W, self.n_filters, self.n_layers)
+        if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        return self._ws, need
+
+    def _run(self, x: torch.Tensor, out: torch.Tensor, N, H, W, in_u8, out_u8):
+        if self.n_layers > L.FSR_MAX_LAYERS:
+            raise RuntimeError(f"n_layers > {L.FSR_MAX_LAYERS} not supported")
+        P = self._params_struct()
+        ws, need = self._workspace(N, H, W, x.device)
+        rc = L.load().fsr_generator_forward(P, x.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel(), N, H, W,
+                                            in_u8, out_u8, self.l2_group, L.stream_ptr(x.device))
+        L.check(rc, "fsr_generator_forward")
+        return out
+
+    @staticmethod
+    def _require_cuda(x):
+        if not x.is_cuda:
+            raise RuntimeError("fast_srgan_b200.Generator runs on CUDA (sm_100a) tensors only - no CPU fallback")
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        self._require_cuda(x)
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            from .autograd import generator_forward_train   # training path (hand-written backward kernels)
+            return generator_forward_train(self, x)
+        x = x.contiguous().float()
+        N, C, H, W = x.shape
+        if C != 3:
+            raise RuntimeError(f"expected 3 input channels, got {C}")
+        out = torch.empty((N, 3, 4 * H, 4 * W), dtype=torch.float32, device=x.device)
+        return self._run(x, out, N, H, W, 0, 0)
+
+    @torch.no_grad()
+    def super_resolve_u8(self, img: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """uint8 NHWC [N,H,W,3] -> uint8 NHWC [N,4H,4W,3]; fuses inference.py:48-51 and :54-56."""
+        self._require_cuda(img)
+        if img.dtype != torch.uint8 or img.dim() != 4 or img.shape[-1] != 3:
+            raise RuntimeError("expected uint8 NHWC [N,H,W,3]")
+        img = img.contiguous()
+        N, H, W, _ = img.shape
+        if out is None:
+            out = torch.empty((N, 4 * H, 4 * W, 3), dtype=torch.uint8, device=img.device)
+        return self._run(img, out, N, H, W, 1, 1)

@@ -1,0 +1,129 @@
+/* fsr_b200.h - C ABI of libfsr_b200.so: B200 (sm_100a) kernels for the Fast-SRGAN hot path.
+ *
+ * The reference (HasnainRaz/Fast-SRGAN) has NO native/FFI interface: its hot path is the Python
+ * class surface of model.py / trainer.py executed by ATen.  Each entry point below therefore cites
+ * the reference torch.nn call site(s) (file:line) whose arithmetic it replaces.  The Python mirror
+ * (fast-srgan_b200/model.py, trainer.py) binds these with ctypes - see INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers + sizes, no torch types.  All pointers are DEVICE pointers unless noted.
+ *   - the caller owns every buffer (activations, packed weights, workspace); nothing is allocated
+ *     or freed here.  Launches go on `stream` (a cudaStream_t passed as void*); calls are
+ *     asynchronous and re-entrant per stream.
+ *   - return 0 on success; <0 on error (fsr_error_string()).  -(1000+e) wraps cudaError_t e.
+ *   - activations between kernels are NHWC, `dtype` FSR_F16 or FSR_BF16 (fp32 accumulation
+ *     everywhere); the module boundary (neck input / head output) is the reference's fp32 NCHW
+ *     (model.py:112-117) or inference.py's uint8 HWC (inference.py:48-56).
+ */
+#ifndef FSR_B200_H_
+#define FSR_B200_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FSR_ABI_VERSION 1
+#define FSR_MAX_LAYERS 32
+
+enum { FSR_F16 = 0, FSR_BF16 = 1 };
+/* conv epilogues (fused neighbours of the conv in the reference graph) */
+enum {
+  FSR_EPI_RAW_STATS = 0, /* raw conv out + InstanceNorm sum/sumsq   (model.py:54-55,64-65,93-94,131-132) */
+  FSR_EPI_BIAS_ACT = 1,  /* act(conv + bias)                         (VGG conv+ReLU, model.py:8)         */
+  FSR_EPI_PS_PRELU = 2,  /* bias + PixelShuffle(2) + PReLU           (model.py:39-40)                    */
+  FSR_EPI_HEAD_TANH = 3  /* bias + tanh -> fp32 NCHW | uint8 NHWC    (model.py:102-110, inference.py:54-56) */
+};
+enum { FSR_ACT_NONE = 0, FSR_ACT_RELU = 1, FSR_ACT_LRELU = 2, FSR_ACT_PRELU = 3 };
+
+int fsr_abi_version(void);
+const char* fsr_error_string(int code);
+
+/* Pack torch OIHW fp32 conv weights [cout,cin,3,3] into the kernel layout [9][cout_pad][cin] (dtype).
+ * ps_perm=1 additionally permutes output channels so that PixelShuffle(2) (model.py:36) becomes a
+ * contiguous store: packed row (2i+j)*(cout/4)+c <- reference channel 4c+2i+j.  bias (nullable) is
+ * permuted/padded the same way into bias_packed[cout_pad] (fp32). */
+int fsr_pack_conv3x3_weight(const float* w_oihw, const float* bias, void* w_packed, float* bias_packed, int cout,
+                            int cin, int cout_pad, int ps_perm, int dtype, void* stream);
+
+/* 3x3 / stride 1 / pad 1 convolution, Cin = 64, on tcgen05 tensor cores (implicit GEMM, TMA-fed).
+ * Replaces torch.nn.Conv2d at model.py:30-35 (UpSamplingBlock.conv), :47-54/:57-64 (ResidualBlock
+ * conv1/conv2), :87-93 (bottleneck), :103-108 (head).
+ *   x        [N,H,W,64] NHWC dtype        w_packed  from fsr_pack_conv3x3_weight
+ *   epilogue FSR_EPI_*:
+ *     RAW_STATS : out [N,H,W,cout] dtype, stats [N,cout,2] fp32 += (sum, sumsq)   (caller zeroes stats)
+ *     BIAS_ACT  : out [N,H,W,cout] dtype = act(conv + bias)
+ *     PS_PRELU  : cout = 256: out [N,2H,2W,64] dtype = PReLU(PixelShuffle2(conv + bias)); alpha = device ptr
+ *     HEAD_TANH : cout_pad = 16 (3 real): out fp32 [N,3,H,W] (out_u8=0) or uint8 [N,H,W,3] (out_u8=1)
+ */
+int fsr_conv3x3_c64(const void* x, const void* w_packed, void* out, const float* bias, float* stats,
+                    const float* alpha, int N, int H, int W, int cout, int epilogue, int act, float slope,
+                    int out_u8, int dtype, void* stream);
+
+/* Conv2d(3 -> cout, k3, p1) + bias + activation, direct (HBM-bound; K = 27 is no tensor-core shape).
+ * Replaces model.py:75-78 (Generator.neck, PReLU) and :143-146 (Discriminator.neck, LeakyReLU 0.2);
+ * vgg_norm=1 also folds VGG19.forward's renormalisation model.py:21-22 into the load (VGG conv1_1).
+ *   x: fp32 NCHW [N,3,H,W] (in_u8=0) or uint8 NHWC [N,H,W,3] (in_u8=1: x/127.5-1, inference.py:50)
+ *   w: fp32 OIHW [cout,3,3,3], bias fp32 [cout]; out NHWC dtype [N,H,W,cout]; cout % 64 == 0 */
+int fsr_neck_conv3x3(const void* x, const float* w, const float* bias, const float* alpha, void* out, int N, int H,
+                     int W, int cout, int act, float slope, int in_u8, int vgg_norm, int dtype, void* stream);
+
+/* InstanceNorm2d(affine=False, eps) normalise from conv-epilogue statistics, fused with the following
+ * activation and residual add: out = act((raw-mean)*rstd) (+ residual).
+ * Replaces model.py:55-56 (bn1+relu1), :65+:69 (bn2 + skip), :94+:115 (bottleneck IN + long skip),
+ * :132-133 (SimpleBlock bn + LeakyReLU).  raw/out/residual NHWC dtype [N,HW,C]; stats [N,C,2] fp32. */
+int fsr_instnorm_apply(const void* raw, const float* stats, const void* residual, void* out, const float* alpha,
+                       int N, int HW, int C, int act, float slope, float eps, int dtype, void* stream);
+
+/* torch.nn.PixelShuffle(2) (model.py:36) on NHWC: in [N,H,W,4C] (reference channel order) -> out [N,2H,2W,C]. */
+int fsr_pixel_shuffle2(const void* in, void* out, int N, int H, int W, int C, int dtype, void* stream);
+
+/* Module-boundary layout conversion (the reference is NCHW fp32 everywhere, inference.py:50-51). */
+int fsr_nchw_f32_to_nhwc(const float* in, void* out, int N, int C, int HW, int dtype, void* stream);
+int fsr_nhwc_to_nchw_f32(const void* in, float* out, int N, int C, int HW, int dtype, void* stream);
+
+/* ---- whole Generator.forward (model.py:112-117) as one call: neck -> n_layers residual blocks ->
+ * bottleneck + long skip -> 2 x (conv + pixel-shuffle + PReLU) -> head + tanh. */
+typedef struct FsrGeneratorParams {
+  int n_filters; /* 64 in this build */
+  int n_layers;  /* <= FSR_MAX_LAYERS */
+  int dtype;     /* FSR_F16 | FSR_BF16 */
+  int reserved;
+  const float* neck_w;     /* [64,3,3,3] fp32 OIHW      model.py:76 */
+  const float* neck_b;     /* [64]                                   */
+  const float* neck_alpha; /* [1]                       model.py:77 */
+  const void* stem_w1[FSR_MAX_LAYERS];     /* packed [9][64][64]   model.py:47 */
+  const float* stem_alpha[FSR_MAX_LAYERS]; /* [1]                  model.py:56 */
+  const void* stem_w2[FSR_MAX_LAYERS];     /* packed               model.py:57 */
+  const void* bott_w;                      /* packed               model.py:87 */
+  const void* up_w[2];      /* packed ps_perm [9][256][64]          model.py:30 */
+  const float* up_b[2];     /* permuted [256]                                  */
+  const float* up_alpha[2]; /* [1]                                  model.py:37 */
+  const void* head_w;       /* packed [9][16][64] (3 real rows)     model.py:103 */
+  const float* head_b;      /* padded [16]                                      */
+} FsrGeneratorParams;
+
+size_t fsr_generator_workspace_bytes(int N, int H, int W, int n_filters, int n_layers);
+/* x: fp32 NCHW [N,3,H,W] or uint8 NHWC [N,H,W,3]; y: fp32 NCHW [N,3,4H,4W] or uint8 NHWC [N,4H,4W,3].
+ * group > 0 runs neck..bottleneck over `group` images at a time so the residual-chain working set
+ * stays inside the 126 MB L2 (0 = whole batch at once). */
+int fsr_generator_forward(const FsrGeneratorParams* prm, const void* x, void* y, void* workspace, size_t ws_bytes,
+                          int N, int H, int W, int in_u8, int out_u8, int group, void* stream);
+
+/* ---- measurement hooks (bench.py): device-time single kernels INSIDE a running forward.
+ * fsr_profile_enable(kernel_id) makes every later launch of that kernel (FSR_K_*) be bracketed by a
+ * cudaEvent pair on its launch stream (at most FSR_PROFILE_MAX pairs are kept);
+ * fsr_profile_read() synchronises those events, writes the elapsed milliseconds and clears the list.
+ * fsr_launch_count() = number of kernels this library has launched so far in this process. */
+enum { FSR_K_NONE = -1, FSR_K_NECK = 0, FSR_K_CONV_RES = 1, FSR_K_IN_APPLY = 2, FSR_K_CONV_UP = 3,
+       FSR_K_CONV_HEAD = 4, FSR_K_CONV_BIAS_ACT = 5 };
+#define FSR_PROFILE_MAX 4096
+int fsr_profile_enable(int kernel_id);
+int fsr_profile_read(float* ms_out, int capacity);
+unsigned long long fsr_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FSR_B200_H_ */
