@@ -5,6 +5,7 @@
 
 #include <cudaTypedefs.h>
 #include <atomic>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -98,14 +99,32 @@ int num_sms() {
   return sms;
 }
 
-template <int NS, int EPI, typename T>
-int launch_conv(const CUtensorMap& tmx, const CUtensorMap& tmw, const ConvParams& p, cudaStream_t st) {
-  auto kern = conv3x3_c64_kernel<NS, EPI, T>;
+int g_halo1 = -1;   // A-operand staging: 0 = 3 column-shifted halo tiles, 1 = single halo tile (see conv3x3_tc.cuh)
+int halo_mode() {
+  if (g_halo1 < 0) {
+    const char* e = getenv("FSR_HALO1");
+    g_halo1 = (e && e[0] == '0') ? 0 : 1;   // default: single halo tile
+  }
+  return g_halo1;
+}
+
+template <int NS, int EPI, typename T, bool HALO1>
+int launch_conv(const void* x, const void* w_packed, int w_rows, ConvParams p, int dtype, cudaStream_t st) {
+  using Cfg = ConvCfg<NS, HALO1>;
+  using Geo = ConvGeo<HALO1>;
+  auto kern = conv3x3_c64_kernel<NS, EPI, T, HALO1>;
   static bool attr_done = false;   // per template instantiation
   if (!attr_done) {
-    FSR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<NS>::kSmemBytes));
+    FSR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_done = true;
   }
+  p.tiles_x = (p.W + Geo::TW - 1) / Geo::TW;
+  p.tiles_y = (p.H + Geo::TH - 1) / Geo::TH;
+  p.num_tiles = p.N * p.tiles_x * p.tiles_y;
+  CUtensorMap tmx, tmw;
+  int rc = make_act_map(&tmx, x, p.N, p.H, p.W, 64, Geo::kBoxW, Geo::kBoxH, dtype);
+  if (rc) return rc;
+  if ((rc = make_w_map(&tmw, w_packed, w_rows, NS, dtype))) return rc;
   int ctas_per_slice = num_sms() / p.num_slices;
   if (ctas_per_slice < 1) ctas_per_slice = 1;
   if (ctas_per_slice > p.num_tiles) ctas_per_slice = p.num_tiles;
@@ -114,9 +133,15 @@ int launch_conv(const CUtensorMap& tmx, const CUtensorMap& tmw, const ConvParams
                     : EPI == EPI_HEAD_TANH ? FSR_K_CONV_HEAD : FSR_K_CONV_BIAS_ACT;
   {
     LaunchScope scope(kid, st);
-    kern<<<grid, kConvThreads, ConvCfg<NS>::kSmemBytes, st>>>(tmx, tmw, p);
+    kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tmx, tmw, p);
   }
   return cuda_rc(cudaGetLastError());
+}
+
+template <int NS, int EPI, typename T>
+int launch_conv_mode(const void* x, const void* w_packed, int w_rows, const ConvParams& p, int dtype, cudaStream_t st) {
+  if (halo_mode()) return launch_conv<NS, EPI, T, true>(x, w_packed, w_rows, p, dtype, st);
+  return launch_conv<NS, EPI, T, false>(x, w_packed, w_rows, p, dtype, st);
 }
 
 template <typename T>
@@ -126,38 +151,28 @@ int conv_dispatch(const void* x, const void* w_packed, void* out, const float* b
   if (N <= 0 || H <= 0 || W <= 0) return FSR_ERR_BAD_SHAPE;
   ConvParams p{};
   p.N = N; p.H = H; p.W = W;
-  p.tiles_x = (W + kTileW - 1) / kTileW;
-  p.tiles_y = (H + kTileH - 1) / kTileH;
-  p.num_tiles = N * p.tiles_x * p.tiles_y;
   p.out = out; p.bias = bias; p.stats = stats; p.alpha = alpha; p.slope = slope; p.act = act; p.out_u8 = out_u8;
-  CUtensorMap tmx, tmw;
-  int rc = make_act_map(&tmx, x, N, H, W, 64, kTileW, kTileH + 2, dtype);
-  if (rc) return rc;
   switch (epilogue) {
     case FSR_EPI_RAW_STATS: {
       if (cout % 64 || !stats) return FSR_ERR_BAD_ARG;
       p.cout_total = cout; p.num_slices = cout / 64;
-      if ((rc = make_w_map(&tmw, w_packed, 9 * cout, 64, dtype))) return rc;
-      return launch_conv<64, EPI_RAW_STATS, T>(tmx, tmw, p, st);
+      return launch_conv_mode<64, EPI_RAW_STATS, T>(x, w_packed, 9 * cout, p, dtype, st);
     }
     case FSR_EPI_BIAS_ACT: {
       if (cout % 64) return FSR_ERR_BAD_ARG;
       if (act == FSR_ACT_PRELU && !alpha) return FSR_ERR_BAD_ARG;
       p.cout_total = cout; p.num_slices = cout / 64;
-      if ((rc = make_w_map(&tmw, w_packed, 9 * cout, 64, dtype))) return rc;
-      return launch_conv<64, EPI_BIAS_ACT, T>(tmx, tmw, p, st);
+      return launch_conv_mode<64, EPI_BIAS_ACT, T>(x, w_packed, 9 * cout, p, dtype, st);
     }
     case FSR_EPI_PS_PRELU: {
       if (cout != 256 || !alpha) return FSR_ERR_BAD_ARG;
       p.cout_total = 256; p.num_slices = 2;
-      if ((rc = make_w_map(&tmw, w_packed, 9 * 256, 128, dtype))) return rc;
-      return launch_conv<128, EPI_PS_PRELU, T>(tmx, tmw, p, st);
+      return launch_conv_mode<128, EPI_PS_PRELU, T>(x, w_packed, 9 * 256, p, dtype, st);
     }
     case FSR_EPI_HEAD_TANH: {
       if (cout != 16) return FSR_ERR_BAD_ARG;   // padded head: 3 real + 13 zero rows
       p.cout_total = 16; p.num_slices = 1;
-      if ((rc = make_w_map(&tmw, w_packed, 9 * 16, 16, dtype))) return rc;
-      return launch_conv<16, EPI_HEAD_TANH, T>(tmx, tmw, p, st);
+      return launch_conv_mode<16, EPI_HEAD_TANH, T>(x, w_packed, 9 * 16, p, dtype, st);
     }
   }
   return FSR_ERR_BAD_ARG;
@@ -297,6 +312,11 @@ int fsr_profile_read(float* ms_out, int capacity) {
 }
 
 unsigned long long fsr_launch_count(void) { return g_launches.load(); }
+
+int fsr_set_halo_mode(int single_halo_tile) {
+  g_halo1 = single_halo_tile ? 1 : 0;
+  return FSR_OK;
+}
 
 // ------------------------------------------------------------------ Generator.forward (model.py:112-117)
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }

@@ -6,16 +6,21 @@
 //
 // Layout: activations NHWC, 64 input channels = one 128-byte row per pixel (fp16 or bf16).
 // GEMM view: D[pixels, Cout] = sum over 9 taps of  A_tap[pixels, 64] * W_tap[64, Cout].
-//   * M tile  = 8 x 16 output pixels (128 rows = one UMMA M),
-//   * A       = TMA 4-D box {64ch, 16, 8+2, 1} of the input at (x0+s-1, y0-1): a halo tile per
-//               COLUMN shift s (zero fill outside the image = the conv padding).  The three ROW
-//               shifts r reuse the same smem tile through a descriptor offset of r*16 rows
-//               (2048 B, a multiple of the 1024-B swizzle atom) -> 3 smem fills per tile, not 9.
+//   * M tile  = 128 output pixels = one UMMA M.  Two geometries (template HALO1):
+//       HALO1 = false: 8 x 16 pixels; A = one TMA 4-D box {64ch, 16, 8+2, 1} per COLUMN shift s
+//               (3 smem fills per tile); the 3 ROW shifts r are descriptor offsets of r*16 rows
+//               (2048 B = multiple of the 1024-B swizzle atom).
+//       HALO1 = true : 16 x 8 pixels; A = ONE TMA box {64ch, 8+2, 16+2, 1} (the halo tile, 180 rows);
+//               tap (r,s) = descriptor start at halo row r*10+s with stride-byte-offset 1280 B
+//               (one 8-pixel tile row per 8-row core group; groups are 10 halo pixels apart).
+//               1 smem fill per tile (2.6x less L2->SM traffic).
+//     Zero fill outside the image (TMA OOB) = the conv padding in both cases.
 //   * B       = the Cout-slice of the weights, resident in smem for the whole persistent CTA
 //               (9 taps x NS rows x 128 B, K-major, 128B swizzle).
 //   * D       = fp32 accumulators in TMEM, double buffered (2 x NS columns).
-// Warp roles (192 threads): warp0 = TMA producer, warp1 = MMA issuer (+TMEM alloc),
-// warps2-5 = epilogue (TMEM -> registers -> fused epilogue -> coalesced global stores).
+// Warp roles: warp0 = TMA producer, warp1 = MMA issuer (+TMEM alloc), then 4 or 8 epilogue warps
+// (TMEM -> registers -> fused epilogue -> swizzled smem transpose -> coalesced global stores); with 8,
+// the two groups of 4 alternate tiles (group g owns accumulator buffer g).
 #pragma once
 #include "fsr_common.cuh"
 #include <type_traits>
@@ -35,7 +40,7 @@ struct ConvParams {
   int N, H, W;              // conv input == output spatial size (stride 1, pad 1)
   int cout_total;           // GEMM N over all slices (multiple of NS)
   int num_slices;           // cout_total / NS
-  int tiles_x, tiles_y;     // ceil(W/16), ceil(H/8)
+  int tiles_x, tiles_y;     // ceil(W/TW), ceil(H/TH)
   int num_tiles;            // N * tiles_y * tiles_x
   void* out;                // see ConvEpilogue
   const float* bias;        // [cout_total] in GEMM column order, or nullptr
@@ -46,17 +51,28 @@ struct ConvParams {
   int out_u8;               // EPI_HEAD_TANH: 0 -> fp32 NCHW [N,3,H,W]; 1 -> uint8 NHWC [N,H,W,3]
 };
 
-constexpr int kTileH = 8, kTileW = 16;
-constexpr int kStageBytes = (kTileH + 2) * kTileW * 128;   // 20480
-constexpr int kStagingBytes = 4 * 4096;                    // per-epilogue-warp transpose buffers
-constexpr int kConvThreads = 192;
+template <bool HALO1>
+struct ConvGeo {
+  static constexpr int TH = HALO1 ? 16 : 8;
+  static constexpr int TW = HALO1 ? 8 : 16;
+  static constexpr int kBoxW = HALO1 ? TW + 2 : TW;
+  static constexpr int kBoxH = TH + 2;
+  static constexpr int kLoads = HALO1 ? 1 : 3;                       // TMA fills per tile
+  static constexpr int kStageBytes = ((kBoxW * kBoxH * 128 + 1023) / 1024) * 1024;   // 23552 | 20480
+  static constexpr int kTxBytes = kBoxW * kBoxH * 128;               // bytes one fill delivers
+};
 
-template <int NS>
+template <int NS, bool HALO1>
 struct ConvCfg {
+  using Geo = ConvGeo<HALO1>;
   static constexpr int kWBytes = 9 * NS * 128;
-  static constexpr int kStages = (NS >= 128) ? 3 : 6;
+  static constexpr int kEpiWarps = (NS >= 128) ? 4 : 8;
+  static constexpr int kThreads = 64 + 32 * kEpiWarps;
+  static constexpr int kStagingBytes = kEpiWarps * 4096;
+  static constexpr int kStages = (NS >= 128) ? (HALO1 ? 2 : 3) : (HALO1 ? 5 : 6);
   static constexpr int kTmemCols = (2 * NS <= 32) ? 32 : (2 * NS <= 64 ? 64 : (2 * NS <= 128 ? 128 : 256));
-  static constexpr int kSmemBytes = kWBytes + kStages * kStageBytes + kStagingBytes + 1024 /*barriers*/ + 1024 /*align*/;
+  static constexpr int kSmemBytes = kWBytes + kStages * Geo::kStageBytes + kStagingBytes + 1024 /*barriers+bias*/ + 1024 /*align*/;
+  static_assert(kSmemBytes <= 232448, "exceeds the 227 KB per-CTA shared memory of sm_100");
 };
 
 FSR_DEVINL float apply_act(float v, int act, float slope) {
@@ -65,34 +81,19 @@ FSR_DEVINL float apply_act(float v, int act, float slope) {
   return v;
 }
 
-// Sum 64 per-lane values across the 32 lanes of a warp with a halving butterfly
-// (32+16+8+4+2 = 62 shuffles): afterwards lane L holds the totals of columns 2L and 2L+1.
-FSR_DEVINL void warp_reduce64(float (&v)[64], int lane) {
-#pragma unroll
-  for (int step = 0; step < 5; ++step) {
-    const int off = 16 >> step;
-    const int half = 32 >> step;
-    const bool up = (lane & off) != 0;
-#pragma unroll
-    for (int i = 0; i < half; ++i) {
-      const float send = up ? v[i] : v[i + half];
-      const float keep = up ? v[i + half] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-    }
-  }
-}
-
-template <int NS, int EPI, typename T>
-__global__ void __launch_bounds__(kConvThreads, 1)
+template <int NS, int EPI, typename T, bool HALO1>
+__global__ void __launch_bounds__(ConvCfg<NS, HALO1>::kThreads, 1)
 conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                    const ConvParams p) {
-  using Cfg = ConvCfg<NS>;
+  using Cfg = ConvCfg<NS, HALO1>;
+  using Geo = ConvGeo<HALO1>;
+  constexpr int TH = Geo::TH, TW = Geo::TW;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_w = smem;
   uint8_t* smem_a = smem_w + Cfg::kWBytes;
-  uint8_t* smem_stg = smem_a + Cfg::kStages * kStageBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stg + kStagingBytes);
+  uint8_t* smem_stg = smem_a + Cfg::kStages * Geo::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stg + Cfg::kStagingBytes);
   uint64_t* full_bar = bars;                       // [kStages]
   uint64_t* empty_bar = bars + Cfg::kStages;       // [kStages]
   uint64_t* w_bar = bars + 2 * Cfg::kStages;       // [1]
@@ -107,6 +108,10 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
   const int cta_in_slice = blockIdx.x / p.num_slices;
   const int ctas_per_slice = gridDim.x / p.num_slices;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
+  // contiguous tile range per CTA: consecutive tiles share halos (L2 locality) and mostly one image
+  // (InstanceNorm statistics stay in registers across tiles, see the epilogue)
+  const int t_begin = (int)(((long long)cta_in_slice * p.num_tiles) / ctas_per_slice);
+  const int t_end = (int)(((long long)(cta_in_slice + 1) * p.num_tiles) / ctas_per_slice);
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_x);
@@ -129,80 +134,135 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // =============================== TMA producer ===============================
-    if (lane == 0) {
+    // =============================== TMA producer (whole warp runs the loop, one elected lane issues)
+    if (elect_one()) {
       mbar_arrive_expect_tx(w_bar, Cfg::kWBytes);
       for (int tap = 0; tap < 9; ++tap)
         tma_load_2d(smem_w + tap * NS * 128, &tm_w, w_bar, 0, tap * p.cout_total + slice * NS);
-      int stage = 0; uint32_t phase = 0;
-      for (int t = cta_in_slice; t < p.num_tiles; t += ctas_per_slice) {
-        const int n = t / tiles_per_img;
-        const int rem = t - n * tiles_per_img;
-        const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
-        const int x0 = tx * kTileW, y0 = ty * kTileH;
-        for (int s = 0; s < 3; ++s) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
-          tma_load_4d(smem_a + stage * kStageBytes, &tm_x, &full_bar[stage], 0, x0 + s - 1, y0 - 1, n);
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
-        }
-      }
     }
     __syncwarp();
+    int stage = 0; uint32_t phase = 0;
+    for (int t = t_begin; t < t_end; ++t) {
+      const int n = t / tiles_per_img;
+      const int rem = t - n * tiles_per_img;
+      const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+      const int x0 = tx * TW, y0 = ty * TH;
+#pragma unroll
+      for (int s = 0; s < Geo::kLoads; ++s) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&full_bar[stage], Geo::kTxBytes);
+          tma_load_4d(smem_a + stage * Geo::kStageBytes, &tm_x, &full_bar[stage], 0,
+                      HALO1 ? x0 - 1 : x0 + s - 1, y0 - 1, n);
+        }
+        __syncwarp();
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
   } else if (warp == 1) {
-    // =============================== MMA issuer ===============================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(128, NS, std::is_same<T, __nv_bfloat16>::value);
-      const uint32_t w_base = smem_u32(smem_w);
-      mbar_wait(w_bar, 0);
+    // =============================== MMA issuer: warp-uniform control flow so that descriptors live in
+    // uniform registers; only the tcgen05 instructions are predicated on the elected lane.
+    constexpr uint32_t idesc = make_idesc_f16(128, NS, std::is_same<T, __nv_bfloat16>::value);
+    const uint32_t a_lo0 = desc_lo_sw128(smem_u32(smem_a));
+    const uint32_t b_lo0 = desc_lo_sw128(smem_u32(smem_w));
+    mbar_wait(w_bar, 0);
+    tc_fence_after();
+    int stage = 0; uint32_t phase = 0;
+    int it = 0;
+    for (int t = t_begin; t < t_end; ++t, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
-      int stage = 0; uint32_t phase = 0;
-      int it = 0;
-      for (int t = cta_in_slice; t < p.num_tiles; t += ctas_per_slice, ++it) {
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      const uint32_t d_tmem = tmem_base + acc * NS;
+      if constexpr (HALO1) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * NS;
-        for (int s = 0; s < 3; ++s) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t a_base = smem_u32(smem_a + stage * kStageBytes);
+        const uint32_t a_lo = a_lo0 + stage * (Geo::kStageBytes >> 4);
+        if (elect_one()) {
 #pragma unroll
           for (int r = 0; r < 3; ++r) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t adesc = make_kmajor_sw128_desc(a_base + r * (kTileW * 128) + k * 32);
-              const uint64_t bdesc = make_kmajor_sw128_desc(w_base + (r * 3 + s) * (NS * 128) + k * 32);
-              umma_f16(d_tmem, adesc, bdesc, idesc, (s | r | k) != 0 ? 1u : 0u);
+            for (int s = 0; s < 3; ++s) {
+              // halo row r*10+s: the start address is only 128-B aligned and core groups are 1280 B apart.
+              // The 128B swizzle XOR is a function of the absolute smem address bits [7,10) (measured on
+              // B200: SBO = 1280 reads TMA-written data correctly), so the base-offset field stays 0.
+              constexpr uint32_t kSbo = (uint32_t)((TW + 2) * 128) >> 4;     // 1280 B between core groups
+              const uint32_t hi = kSbo | (1u << 14) | (2u << 29);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t adesc = desc_join(a_lo + (((r * (TW + 2) + s) * 128 + k * 32) >> 4), hi);
+                const uint64_t bdesc = desc_join(b_lo0 + (((r * 3 + s) * (NS * 128) + k * 32) >> 4), kDescHiSw128);
+                umma_f16(d_tmem, adesc, bdesc, idesc, (s | r | k) != 0 ? 1u : 0u);
+              }
             }
           }
           umma_commit(&empty_bar[stage]);
+          umma_commit(&tfull_bar[acc]);
+        }
+        __syncwarp();
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      } else {
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_lo = a_lo0 + stage * (Geo::kStageBytes >> 4);
+          if (elect_one()) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t adesc = desc_join(a_lo + ((r * (TW * 128) + k * 32) >> 4), kDescHiSw128);
+                const uint64_t bdesc = desc_join(b_lo0 + (((r * 3 + s) * (NS * 128) + k * 32) >> 4), kDescHiSw128);
+                umma_f16(d_tmem, adesc, bdesc, idesc, (s | r | k) != 0 ? 1u : 0u);
+              }
+            }
+            umma_commit(&empty_bar[stage]);
+            if (s == 2) umma_commit(&tfull_bar[acc]);
+          }
+          __syncwarp();
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[acc]);
       }
     }
-    __syncwarp();
   } else {
-    // =============================== epilogue warps (2..5) ===============================
+    // =============================== epilogue warps ===============================
+    const int ew = warp - 2;
     const int q = warp & 3;                      // TMEM lane quarter this warp may access
-    uint8_t* stg = smem_stg + (warp - 2) * 4096;
+    const int egroup = ew >> 2;                  // with 8 warps: group g serves tiles with (it & 1) == g
+    const uint32_t stg = smem_u32(smem_stg + ew * 4096);   // warp-private 32 x 128 B transpose buffer
     const int m = q * 32 + lane;                 // accumulator row == pixel within the tile
-    const int yy = m / kTileW, xx = m % kTileW;
+    const int yy = m / TW, xx = m % TW;
     float prelu_a = 0.f;
     if (EPI == EPI_PS_PRELU || (EPI == EPI_BIAS_ACT && p.act == ACT_PRELU)) prelu_a = __ldg(p.alpha);
     const float slope = (EPI == EPI_PS_PRELU || p.act == ACT_PRELU) ? prelu_a : p.slope;
+    // InstanceNorm statistics of channels (2*lane, 2*lane+1) of the current image, carried across tiles
+    float st_s0 = 0.f, st_q0 = 0.f, st_s1 = 0.f, st_q1 = 0.f;
+    int st_n = -1;
+    auto flush_stats = [&](int img) {
+      if (EPI == EPI_RAW_STATS && img >= 0) {
+        float* st = p.stats + ((size_t)img * p.cout_total + slice * NS + 2 * lane) * 2;
+        atomicAdd(st + 0, st_s0);
+        atomicAdd(st + 1, st_q0);
+        atomicAdd(st + 2, st_s1);
+        atomicAdd(st + 3, st_q1);
+      }
+      st_s0 = st_q0 = st_s1 = st_q1 = 0.f;
+    };
     int it = 0;
-    for (int t = cta_in_slice; t < p.num_tiles; t += ctas_per_slice, ++it) {
+    for (int t = t_begin; t < t_end; ++t, ++it) {
       const int acc = it & 1;
+      if (Cfg::kEpiWarps == 8 && acc != egroup) continue;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int n = t / tiles_per_img;
       const int rem = t - n * tiles_per_img;
       const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
-      const int x0 = tx * kTileW, y0 = ty * kTileH;
+      const int x0 = tx * TW, y0 = ty * TH;
       const int y = y0 + yy, x = x0 + xx;
       const bool pvalid = (y < p.H) && (x < p.W);
+      const bool interior = (y0 + TH <= p.H) && (x0 + TW <= p.W);   // warp-uniform
+      if (EPI == EPI_RAW_STATS && n != st_n) { flush_stats(st_n); st_n = n; }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * NS;
@@ -236,50 +296,56 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
       } else {
 #pragma unroll 1
         for (int chunk = 0; chunk < NS / 64; ++chunk) {
-          float v[64];
+          uint32_t pk[32];                        // 64 output values packed to 2-byte pairs
           {
             uint32_t r0[32], r1[32];
             tmem_ld32(t_row + chunk * 64, r0);
             tmem_ld32(t_row + chunk * 64 + 32, r1);
             tmem_ld_wait();
+            if (chunk == NS / 64 - 1) {           // all TMEM reads of this accumulator are done
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            }
 #pragma unroll
-            for (int i = 0; i < 32; ++i) { v[i] = __uint_as_float(r0[i]); v[32 + i] = __uint_as_float(r1[i]); }
-          }
-          if (chunk == NS / 64 - 1) {           // all TMEM reads of this accumulator are done
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-          }
-          const int col0 = slice * NS + chunk * 64;   // first GEMM column of this chunk
-
-          if constexpr (EPI != EPI_RAW_STATS) {
-#pragma unroll
-            for (int i = 0; i < 64; ++i) {
-              float a = v[i] + smem_bias[chunk * 64 + i];
-              v[i] = (EPI == EPI_PS_PRELU) ? (a >= 0.f ? a : a * slope) : apply_act(a, p.act, slope);
+            for (int i = 0; i < 16; ++i) {
+              float a0 = __uint_as_float(r0[2 * i]), a1 = __uint_as_float(r0[2 * i + 1]);
+              float b0 = __uint_as_float(r1[2 * i]), b1 = __uint_as_float(r1[2 * i + 1]);
+              if constexpr (EPI != EPI_RAW_STATS) {
+                a0 += smem_bias[chunk * 64 + 2 * i];      a1 += smem_bias[chunk * 64 + 2 * i + 1];
+                b0 += smem_bias[chunk * 64 + 32 + 2 * i]; b1 += smem_bias[chunk * 64 + 32 + 2 * i + 1];
+                if constexpr (EPI == EPI_PS_PRELU) {
+                  a0 = a0 >= 0.f ? a0 : a0 * slope; a1 = a1 >= 0.f ? a1 : a1 * slope;
+                  b0 = b0 >= 0.f ? b0 : b0 * slope; b1 = b1 >= 0.f ? b1 : b1 * slope;
+                } else {
+                  a0 = apply_act(a0, p.act, slope); a1 = apply_act(a1, p.act, slope);
+                  b0 = apply_act(b0, p.act, slope); b1 = apply_act(b1, p.act, slope);
+                }
+              }
+              pk[i] = Cvt<T>::pack2(a0, a1);
+              pk[16 + i] = Cvt<T>::pack2(b0, b1);
             }
           }
+          const int col0 = slice * NS + chunk * 64;   // first GEMM column of this chunk
 
           // ---- registers -> swizzled smem (row = pixel, 8 x 16B chunks) -> coalesced global
           __syncwarp();
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            uint4 pk;
-            pk.x = Cvt<T>::pack2(v[8 * k + 0], v[8 * k + 1]);
-            pk.y = Cvt<T>::pack2(v[8 * k + 2], v[8 * k + 3]);
-            pk.z = Cvt<T>::pack2(v[8 * k + 4], v[8 * k + 5]);
-            pk.w = Cvt<T>::pack2(v[8 * k + 6], v[8 * k + 7]);
-            *reinterpret_cast<uint4*>(stg + lane * 128 + ((k ^ (lane & 7)) << 4)) = pk;
-          }
+          for (int k = 0; k < 8; ++k)
+            st_shared_v4(stg + lane * 128 + ((k ^ (lane & 7)) << 4), pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
           __syncwarp();
+          uint4 val[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int rrow = j * 4 + (lane >> 3);
-            const int c16 = lane & 7;
-            const uint4 val = *reinterpret_cast<const uint4*>(stg + rrow * 128 + ((c16 ^ (rrow & 7)) << 4));
+            val[j] = ld_shared_v4(stg + rrow * 128 + (((lane & 7) ^ (rrow & 7)) << 4));
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int rrow = j * 4 + (lane >> 3);
             const int mm = q * 32 + rrow;
-            const int py = y0 + mm / kTileW, px = x0 + mm % kTileW;
-            if (py < p.H && px < p.W) {
+            const int py = y0 + mm / TW, px = x0 + mm % TW;
+            if (interior || (py < p.H && px < p.W)) {
               T* dst;
               if constexpr (EPI == EPI_PS_PRELU) {
                 const int qq = col0 >> 6;               // GEMM column block = 2*i + j
@@ -288,26 +354,44 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
               } else {
                 dst = reinterpret_cast<T*>(p.out) + ((size_t)(n * p.H + py) * p.W + px) * p.cout_total + col0;
               }
-              *reinterpret_cast<uint4*>(dst + c16 * 8) = val;
+              *reinterpret_cast<uint4*>(dst + (lane & 7) * 8) = val[j];
             }
           }
 
           if constexpr (EPI == EPI_RAW_STATS) {
-            // InstanceNorm statistics from the fp32 accumulators (reference model.py:55,65,94,132)
-            float sq[64];
+            // InstanceNorm statistics (reference model.py:55,65,94,132) of the STORED (rounded) values:
+            // lane L owns channels 2L, 2L+1 = one 32-bit word per staged pixel row -> conflict-free
+            // column walk over the 32 rows of this warp; out-of-image rows are skipped (edge tiles).
+            const uint32_t colw = ((lane & 3) << 2);
+            if (interior) {
+              uint32_t w[32];
 #pragma unroll
-            for (int i = 0; i < 64; ++i) { v[i] = pvalid ? v[i] : 0.f; sq[i] = v[i] * v[i]; }
-            warp_reduce64(v, lane);
-            warp_reduce64(sq, lane);
-            float* st = p.stats + ((size_t)n * p.cout_total + col0 + 2 * lane) * 2;
-            atomicAdd(st + 0, v[0]);
-            atomicAdd(st + 1, sq[0]);
-            atomicAdd(st + 2, v[1]);
-            atomicAdd(st + 3, sq[1]);
+              for (int rr = 0; rr < 32; ++rr)
+                w[rr] = ld_shared_u32(stg + rr * 128 + ((((lane >> 2) ^ (rr & 7))) << 4) + colw);
+#pragma unroll
+              for (int rr = 0; rr < 32; ++rr) {
+                const float2 f = Cvt<T>::unpack2(w[rr]);
+                st_s0 += f.x; st_q0 = fmaf(f.x, f.x, st_q0);
+                st_s1 += f.y; st_q1 = fmaf(f.y, f.y, st_q1);
+              }
+            } else {
+#pragma unroll 4
+              for (int rr = 0; rr < 32; ++rr) {
+                const int mm = q * 32 + rr;
+                const bool ok = (y0 + mm / TW < p.H) && (x0 + mm % TW < p.W);
+                const uint32_t w = ld_shared_u32(stg + rr * 128 + ((((lane >> 2) ^ (rr & 7))) << 4) + colw);
+                const float2 f = Cvt<T>::unpack2(w);
+                if (ok) {
+                  st_s0 += f.x; st_q0 = fmaf(f.x, f.x, st_q0);
+                  st_s1 += f.y; st_q1 = fmaf(f.y, f.y, st_q1);
+                }
+              }
+            }
           }
         }
       }
     }
+    if (EPI == EPI_RAW_STATS) flush_stats(st_n);
   }
 
   tc_fence_before();

@@ -59,6 +59,21 @@ FSR_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// ---------------------------------------------------------------- explicit shared-space access
+FSR_DEVINL void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+FSR_DEVINL uint4 ld_shared_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+FSR_DEVINL uint32_t ld_shared_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+
 // ---------------------------------------------------------------- TMA
 FSR_DEVINL void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)m) : "memory");
@@ -148,6 +163,23 @@ FSR_DEVINL uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
   d |= (uint64_t)((smem_addr >> 7) & 0x7) << 49;  // base offset: 0 when 1024-B aligned
   d |= (uint64_t)2 << 61;
   return d;
+}
+
+// Split form for hot loops: the high word is constant for a 1024-B-aligned tile, the low word is
+// (addr >> 4) | LBO; advancing inside a tile = adding (bytes >> 4) to the low word.
+constexpr uint32_t kDescHiSw128 = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+FSR_DEVINL uint32_t desc_lo_sw128(uint32_t smem_addr) { return ((smem_addr & 0x3FFFF) >> 4) | (1u << 16); }
+FSR_DEVINL uint64_t desc_join(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | (uint64_t)lo; }
+
+// Warp-uniform leader election (same lane every time for the full mask).
+FSR_DEVINL bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 
 // Instruction descriptor for kind::f16: fp32 accumulate, A/B both K-major.

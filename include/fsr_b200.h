@@ -123,6 +123,11 @@ int fsr_profile_enable(int kernel_id);
 int fsr_profile_read(float* ms_out, int capacity);
 unsigned long long fsr_launch_count(void);
 
+/* A-operand staging of the tensor-core conv: 0 = three column-shifted halo tiles per 8x16-pixel tile,
+ * 1 = ONE halo tile per 16x8-pixel tile addressed through unaligned UMMA descriptors (2.6x less
+ * L2->SM traffic, the default).  Environment FSR_HALO1=0 selects mode 0 at start-up. */
+int fsr_set_halo_mode(int single_halo_tile);
+
 #ifdef __cplusplus
 }
 #endif

@@ -24,6 +24,10 @@ def nchw(x):
     return x.float().permute(0, 3, 1, 2).contiguous()
 
 
+from fast_srgan_b200 import _lib  # noqa: E402
+MODE = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+_lib.load().fsr_set_halo_mode(MODE)
+print("halo mode", MODE, flush=True)
 g = torch.Generator().manual_seed(0)
 N, H, W = 1, 16, 32
 x = nhwc(torch.randn((N, 64, H, W), generator=g).cuda())
@@ -53,11 +57,11 @@ for (N, H, W) in [(1, 8, 16), (2, 13, 21), (4, 90, 160), (32, 180, 320)]:
     serr = ((st - s_ref).abs() / (s_ref.abs() + 1.0)).max().item()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    for _ in range(5):
+    for _ in range(50):
         ops.conv3x3_c64_raw_stats(x, wp, st)
     ev1.record()
     torch.cuda.synchronize()
-    ms = ev0.elapsed_time(ev1) / 5
+    ms = ev0.elapsed_time(ev1) / 50
     fl = 2.0 * N * H * W * 64 * 64 * 9
     print(f"full conv N={N} {H}x{W}: max-abs {err:.3e} stats-rel {serr:.3e}  {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s", flush=True)
 print("DIAG DONE", flush=True)
