@@ -13,7 +13,7 @@ FSR_MAX_LAYERS = 32
 FSR_F16, FSR_BF16 = 0, 1
 EPI_RAW_STATS, EPI_BIAS_ACT, EPI_PS_PRELU, EPI_HEAD_TANH = 0, 1, 2, 3
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_PRELU = 0, 1, 2, 3
-K_NONE, K_NECK, K_CONV_RES, K_IN_APPLY, K_CONV_UP, K_CONV_HEAD, K_CONV_BIAS_ACT = -1, 0, 1, 2, 3, 4, 5
+K_NONE, K_NECK, K_CONV_RES, K_IN_APPLY, K_CONV_UP, K_CONV_HEAD, K_CONV_BIAS_ACT, K_CONV_GEN, K_CONV_WGRAD = -1, 0, 1, 2, 3, 4, 5, 6, 7
 
 _vp, _fp, _i, _f, _sz = C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_size_t
 
@@ -34,6 +34,26 @@ _SIGS = {
     "fsr_error_string": (C.c_char_p, [_i]),
     "fsr_pack_conv3x3_weight": (_i, [_fp, _fp, _vp, _fp, _i, _i, _i, _i, _i, _vp]),
     "fsr_conv3x3_c64": (_i, [_vp, _vp, _vp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _f, _i, _i, _vp]),
+    "fsr_conv3x3_gen": (_i, [_vp, _vp, _vp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp]),
+    "fsr_pack_conv3x3_weight_t": (_i, [_fp, _vp, _i, _i, _i, _i, _vp]),
+    "fsr_conv3x3_wgrad": (_i, [_vp, _vp, _fp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "fsr_parity_layout": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "fsr_maxpool2": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "fsr_maxpool2_relu_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "fsr_relu_bwd": (_i, [_vp, _vp, _vp, _sz, _i, _vp]),
+    "fsr_add": (_i, [_vp, _vp, _vp, _sz, _i, _vp]),
+    "fsr_conv1x1_to1_fwd": (_i, [_vp, _fp, _fp, _fp, _i, _i, _i, _vp]),
+    "fsr_conv1x1_to1_bwd": (_i, [_vp, _fp, _fp, _vp, _fp, _fp, _i, _i, _i, _vp]),
+    "fsr_bce_logits": (_i, [_fp, _fp, _f, _f, _i, _fp, _fp, _f, _vp]),
+    "fsr_smooth_l1": (_i, [_vp, _vp, _sz, _fp, _vp, _f, _i, _vp]),
+    "fsr_instnorm_bwd": (_i, [_vp, _fp, _vp, _fp, _vp, _fp, _fp, _i, _i, _i, _i, _f, _f, _i, _vp]),
+    "fsr_act_bwd": (_i, [_vp, _vp, _vp, _sz, _fp, _f, _i, _fp, _i, _vp]),
+    "fsr_ps_prelu_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _fp, _fp, _i, _vp]),
+    "fsr_tanh_bwd": (_i, [_fp, _fp, _fp, _sz, _vp]),
+    "fsr_wgrad_c3": (_i, [_fp, _vp, _fp, _i, _i, _i, _i, _i, _i, _vp]),
+    "fsr_bias_grad": (_i, [_vp, _fp, _sz, _i, _i, _vp]),
+    "fsr_bias_grad_nchw": (_i, [_fp, _fp, _i, _i, _sz, _vp]),
+    "fsr_adamw": (_i, [_fp, _fp, _fp, _fp, _sz, _f, _f, _f, _f, _f, _i, _f, _vp]),
     "fsr_neck_conv3x3": (_i, [_vp, _fp, _fp, _fp, _vp, _i, _i, _i, _i, _i, _f, _i, _i, _i, _vp]),
     "fsr_instnorm_apply": (_i, [_vp, _fp, _vp, _vp, _fp, _i, _i, _i, _i, _f, _f, _i, _vp]),
     "fsr_pixel_shuffle2": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),

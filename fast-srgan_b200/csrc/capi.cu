@@ -1,11 +1,15 @@
 // capi.cu - extern "C" entry points of libfsr_b200.so (see include/fsr_b200.h) and host launchers.
 #include "../../include/fsr_b200.h"
 #include "conv3x3_tc.cuh"
+#include "conv3x3_gen.cuh"
+#include "conv3x3_wgrad.cuh"
+#include "train_kernels.cuh"
 #include "elementwise.cuh"
 
 #include <cudaTypedefs.h>
 #include <atomic>
 #include <cstdlib>
+#include <cmath>
 #include <mutex>
 #include <vector>
 
@@ -75,12 +79,26 @@ int make_act_map(CUtensorMap* tm, const void* ptr, int N, int H, int W, int C, i
   return r == CUDA_SUCCESS ? FSR_OK : FSR_ERR_TENSORMAP;
 }
 
-// packed weights [rows][64] (2-byte elements), box {64, box_rows}
-int make_w_map(CUtensorMap* tm, const void* ptr, int rows, int box_rows, int dtype) {
+// same, but with an explicit element stride between images (parity-plane layouts)
+int make_act_map_strided(CUtensorMap* tm, const void* ptr, int N, int H, int W, int C, long long img_stride_elems,
+                         int bw, int bh, int dtype) {
   auto enc = get_encode_fn();
   if (!enc) return FSR_ERR_NO_DRIVER;
-  cuuint64_t gdim[2] = {64, (cuuint64_t)rows};
-  cuuint64_t gstr[1] = {128};
+  cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)img_stride_elems * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(tm, tm_dtype(dtype), 4, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? FSR_OK : FSR_ERR_TENSORMAP;
+}
+
+// packed weights [rows][cin] (2-byte elements), box {64, box_rows}
+int make_w_map(CUtensorMap* tm, const void* ptr, int rows, int box_rows, int dtype, int cin = 64) {
+  auto enc = get_encode_fn();
+  if (!enc) return FSR_ERR_NO_DRIVER;
+  cuuint64_t gdim[2] = {(cuuint64_t)cin, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)cin * 2};
   cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(tm, tm_dtype(dtype), 2, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -178,6 +196,173 @@ int conv_dispatch(const void* x, const void* w_packed, void* out, const float* b
   return FSR_ERR_BAD_ARG;
 }
 
+
+// ------------------------------------------------------------------ general conv (conv3x3_gen.cuh)
+template <int EPI, typename T, int MAXTAPS>
+int launch_gen(const CUtensorMap* maps, const CUtensorMap& tmw, GenParams& p, cudaStream_t st) {
+  using Cfg = GenCfg<MAXTAPS>;
+  auto kern = conv3x3_gen_kernel<EPI, T, MAXTAPS>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    FSR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_done = true;
+  }
+  int ctas_per_slice = num_sms() / p.num_slices;
+  if (ctas_per_slice < 1) ctas_per_slice = 1;
+  if (ctas_per_slice > p.num_tiles) ctas_per_slice = p.num_tiles;
+  const int grid = ctas_per_slice * p.num_slices;
+  {
+    LaunchScope scope(FSR_K_CONV_GEN, st);
+    kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], tmw, p);
+  }
+  return cuda_rc(cudaGetLastError());
+}
+
+template <typename T>
+int gen_dispatch(const void* x, const void* w_packed, void* out, const float* bias, float* stats, const float* alpha,
+                 int N, int H, int W, int cin, int cout, int stride, int mode, int epilogue, int act, float slope,
+                 int dtype, cudaStream_t st) {
+  if (N <= 0 || H <= 0 || W <= 0 || cin % 64 || cout % 64) return FSR_ERR_BAD_SHAPE;
+  if (stride != 1 && stride != 2) return FSR_ERR_BAD_ARG;
+  if (stride == 2 && ((H | W) & 1)) return FSR_ERR_BAD_SHAPE;
+  if (epilogue == FSR_EPI_RAW_STATS && !stats) return FSR_ERR_BAD_ARG;
+  if (epilogue != FSR_EPI_RAW_STATS && epilogue != FSR_EPI_BIAS_ACT) return FSR_ERR_BAD_ARG;
+  GenParams p{};
+  p.N = N; p.cin = cin; p.cout_total = cout; p.num_slices = cout / 64;
+  p.bias = bias; p.stats = stats; p.alpha = alpha; p.slope = slope; p.act = act;
+  CUtensorMap maps[4], tmw;
+  int rc;
+  if ((rc = make_w_map(&tmw, w_packed, 9 * cout, 64, dtype, cin))) return rc;
+  const int H2 = H / 2, W2 = W / 2;
+  auto finish = [&](int Ho, int Wo, void* o, long long img_stride, bool taps9) -> int {
+    p.Ho = Ho; p.Wo = Wo; p.out = o; p.out_img_stride = img_stride;
+    p.tiles_x = (Wo + 7) / 8; p.tiles_y = (Ho + 15) / 16; p.num_tiles = N * p.tiles_x * p.tiles_y;
+    if (epilogue == FSR_EPI_RAW_STATS)
+      return taps9 ? launch_gen<EPI_RAW_STATS, T, 9>(maps, tmw, p, st) : launch_gen<EPI_RAW_STATS, T, 4>(maps, tmw, p, st);
+    return taps9 ? launch_gen<EPI_BIAS_ACT, T, 9>(maps, tmw, p, st) : launch_gen<EPI_BIAS_ACT, T, 4>(maps, tmw, p, st);
+  };
+  if (stride == 1) {
+    // forward: out[y,x] += W[r,s] x[y+r-1, x+s-1];  dgrad (transposed, unflipped pack): dX[y,x] += W[r,s]^T dY[y+1-r, x+1-s]
+    if ((rc = make_act_map(&maps[0], x, N, H, W, cin, 10, 18, dtype))) return rc;
+    maps[1] = maps[2] = maps[3] = maps[0];
+    p.nkinds = 1;
+    GenKind& K = p.kinds[0];
+    K.map = 0; K.ntaps = 9; K.box_w = 10; K.box_rows = 180; K.dx = -1; K.dy = -1;
+    for (int r = 0; r < 3; ++r)
+      for (int s2 = 0; s2 < 3; ++s2) {
+        K.taps[r * 3 + s2].wrow = r * 3 + s2;
+        K.taps[r * 3 + s2].a_off = mode == 0 ? r * 10 + s2 : (2 - r) * 10 + (2 - s2);
+      }
+    return finish(H, W, out, (long long)H * W * cout, true);
+  }
+  if (mode == 0) {
+    // stride-2 forward: x is in parity-plane layout [N][4][H2][W2][cin]; input row 2y+r-1:
+    //   r=0 -> odd plane row y-1, r=1 -> even plane row y, r=2 -> odd plane row y   (same for columns)
+    const long long plane = (long long)H2 * W2 * cin;
+    for (int pl = 0; pl < 4; ++pl)
+      if ((rc = make_act_map_strided(&maps[pl], (const uint8_t*)x + (size_t)pl * plane * 2, N, H2, W2, cin, 4 * plane, 9, 17, dtype)))
+        return rc;
+    p.nkinds = 4;
+    for (int pr = 0; pr < 2; ++pr)
+      for (int ps = 0; ps < 2; ++ps) {
+        GenKind& K = p.kinds[pr * 2 + ps];
+        K.map = pr * 2 + ps; K.ntaps = 0; K.box_w = 9; K.box_rows = 153; K.dx = -1; K.dy = -1;
+        for (int r = 0; r < 3; ++r)
+          for (int s2 = 0; s2 < 3; ++s2)
+            if ((r != 1) == pr && (s2 != 1) == ps) {
+              K.taps[K.ntaps].wrow = r * 3 + s2;
+              K.taps[K.ntaps].a_off = (r != 0) * 9 + (s2 != 0);
+              ++K.ntaps;
+            }
+      }
+    return finish(H2, W2, out, (long long)H2 * W2 * cout, false);
+  }
+  // stride-2 dgrad: x = dY NHWC [N,H2,W2,cin]; out = dX parity planes [N][4][H2][W2][cout] (H, W = dX size)
+  //   dX[2y'+pr] : pr=0 -> r=1 reads dY[y'];  pr=1 -> r=0 reads dY[y'+1], r=2 reads dY[y']
+  if ((rc = make_act_map(&maps[0], x, N, H2, W2, cin, 9, 17, dtype))) return rc;
+  maps[1] = maps[2] = maps[3] = maps[0];
+  const long long oplane = (long long)H2 * W2 * cout;
+  for (int pr = 0; pr < 2; ++pr)
+    for (int ps = 0; ps < 2; ++ps) {
+      p.nkinds = 1;
+      GenKind& K = p.kinds[0];
+      K.map = 0; K.ntaps = 0; K.box_w = 9; K.box_rows = 153; K.dx = 0; K.dy = 0;
+      for (int r = 0; r < 3; ++r)
+        for (int s2 = 0; s2 < 3; ++s2)
+          if ((r != 1) == pr && (s2 != 1) == ps) {
+            K.taps[K.ntaps].wrow = r * 3 + s2;
+            K.taps[K.ntaps].a_off = (r == 0) * 9 + (s2 == 0);
+            ++K.ntaps;
+          }
+      T* o = reinterpret_cast<T*>(out) + (size_t)(pr * 2 + ps) * oplane;
+      if ((rc = finish(H2, W2, o, 4 * oplane, false))) return rc;
+    }
+  return FSR_OK;
+}
+
+
+// ------------------------------------------------------------------ weight gradient (conv3x3_wgrad.cuh)
+template <typename T>
+int wgrad_dispatch(const void* x, const void* dy, float* dw, int N, int H, int W, int cin, int cout, int stride,
+                   int ps_perm, int dtype, cudaStream_t st) {
+  if (N <= 0 || H <= 0 || W <= 0 || cin % 64 || cout % 64) return FSR_ERR_BAD_SHAPE;
+  if (stride != 1 && stride != 2) return FSR_ERR_BAD_ARG;
+  if (stride == 2 && ((H | W) & 1)) return FSR_ERR_BAD_SHAPE;
+  WgradParams p{};
+  const int Ho = H / stride, Wo = W / stride;
+  p.N = N; p.Ho = Ho; p.Wo = Wo; p.cin = cin; p.cout = cout; p.dw = dw; p.ps_perm = ps_perm;
+  p.tiles_x = (Wo + 7) / 8; p.tiles_y = (Ho + 15) / 16; p.num_tiles = N * p.tiles_x * p.tiles_y;
+  CUtensorMap mx[4], mdy;
+  int rc;
+  if ((rc = make_act_map(&mdy, dy, N, Ho, Wo, cout, 8, 16, dtype))) return rc;
+  if (stride == 1) {
+    p.nplanes = 1; p.box_w = 10; p.box_rows = 180; p.plane_bytes = 23552; p.dx = -1; p.dy = -1;
+    if ((rc = make_act_map(&mx[0], x, N, H, W, cin, 10, 18, dtype))) return rc;
+    mx[1] = mx[2] = mx[3] = mx[0];
+    for (int t = 0; t < 9; ++t) { p.tap_row[t] = (t / 3) * 10 + (t % 3); p.tap_id[t] = t; }
+  } else {
+    // X in parity planes [N][4][Ho][Wo][cin]; tap (r,s) -> plane ((r!=1),(s!=1)), row (r!=0)*9 + (s!=0)
+    p.nplanes = 4; p.box_w = 9; p.box_rows = 153; p.plane_bytes = 20480; p.dx = -1; p.dy = -1;
+    const long long plane = (long long)Ho * Wo * cin;
+    for (int pl = 0; pl < 4; ++pl)
+      if ((rc = make_act_map_strided(&mx[pl], (const uint8_t*)x + (size_t)pl * plane * 2, N, Ho, Wo, cin, 4 * plane, 9, 17, dtype)))
+        return rc;
+    // order taps by their absolute row inside the stage so that pair distances (LBO) are non-negative
+    int n = 0;
+    for (int pl = 0; pl < 4; ++pl)
+      for (int r = 0; r < 3; ++r)
+        for (int s2 = 0; s2 < 3; ++s2)
+          if ((r != 1) * 2 + (s2 != 1) == pl) {
+            p.tap_row[n] = pl * (20480 / 128) + (r != 0) * 9 + (s2 != 0);
+            p.tap_id[n] = r * 3 + s2;
+            ++n;
+          }
+    // within a plane rows may be unordered (e.g. plane 3: taps (0,0),(0,2),(2,0),(2,2) -> rows 0,1,9,10): sorted by construction
+  }
+  p.tap_row[9] = p.tap_row[8]; p.tap_id[9] = p.tap_id[8];
+  auto kern = conv3x3_wgrad_kernel<T>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    FSR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, WgradCfg::kSmemBytes));
+    attr_done = true;
+  }
+  const int npairs = (cin / 64) * (cout / 64);
+  int cpp = num_sms() / npairs;
+  if (cpp < 1) cpp = 1;
+  if (cpp > p.num_tiles) cpp = p.num_tiles;
+  {
+    LaunchScope scope(FSR_K_CONV_WGRAD, st);
+    kern<<<npairs * cpp, WgradCfg::kThreads, WgradCfg::kSmemBytes, st>>>(mx[0], mx[1], mx[2], mx[3], mdy, p);
+  }
+  return cuda_rc(cudaGetLastError());
+}
+
+inline int ew_blocks(size_t n, int per_block = 256) {
+  size_t b = (n + per_block - 1) / per_block;
+  const size_t cap = (size_t)num_sms() * 16;
+  return (int)(b > cap ? cap : (b < 1 ? 1 : b));
+}
+
 }  // namespace
 
 extern "C" {
@@ -221,6 +406,16 @@ int fsr_conv3x3_c64(const void* x, const void* w_packed, void* out, const float*
   if (dtype == FSR_BF16)
     return conv_dispatch<__nv_bfloat16>(x, w_packed, out, bias, stats, alpha, N, H, W, cout, epilogue, act, slope, out_u8, dtype, st);
   return conv_dispatch<__half>(x, w_packed, out, bias, stats, alpha, N, H, W, cout, epilogue, act, slope, out_u8, dtype, st);
+}
+
+int fsr_conv3x3_gen(const void* x, const void* w_packed, void* out, const float* bias, float* stats,
+                    const float* alpha, int N, int H, int W, int cin, int cout, int stride, int mode, int epilogue,
+                    int act, float slope, int dtype, void* stream) {
+  if (!x || !w_packed || !out) return FSR_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == FSR_BF16)
+    return gen_dispatch<__nv_bfloat16>(x, w_packed, out, bias, stats, alpha, N, H, W, cin, cout, stride, mode, epilogue, act, slope, dtype, st);
+  return gen_dispatch<__half>(x, w_packed, out, bias, stats, alpha, N, H, W, cin, cout, stride, mode, epilogue, act, slope, dtype, st);
 }
 
 int fsr_neck_conv3x3(const void* x, const float* w, const float* bias, const float* alpha, void* out, int N, int H,
@@ -382,6 +577,221 @@ int fsr_generator_forward(const FsrGeneratorParams* prm, const void* x, void* y,
   if ((rc = fsr_conv3x3_c64(b_u0, prm->up_w[1], b_u1, prm->up_b[1], nullptr, prm->up_alpha[1], N, 2 * H, 2 * W, 256, FSR_EPI_PS_PRELU, 0, 0.f, 0, dt, st))) return rc;
   if ((rc = fsr_conv3x3_c64(b_u1, prm->head_w, y, prm->head_b, nullptr, nullptr, N, 4 * H, 4 * W, 16, FSR_EPI_HEAD_TANH, 0, 0.f, out_u8, dt, st))) return rc;
   return FSR_OK;
+}
+
+
+// ====================================================================== training-step entry points
+#define FSR_T(expr_h, expr_b) do { if (dtype == FSR_BF16) { expr_b; } else { expr_h; } } while (0)
+
+int fsr_pack_conv3x3_weight_t(const float* w_oihw, void* w_packed, int cout, int cin, int ps_perm, int dtype, void* stream) {
+  // transposed pack for data-gradient convs: out[tap][ci][co(perm)] = W[co][ci][tap]  (rows = ci, K = co)
+  if (!w_oihw || !w_packed || cout <= 0 || cin <= 0) return FSR_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t total = (size_t)9 * cout * cin;
+  LaunchScope scope(FSR_K_NONE - 1, st);
+  FSR_T((pack_conv3x3_weight_t_kernel<__half><<<ew_blocks(total), 256, 0, st>>>(w_oihw, (__half*)w_packed, cout, cin, ps_perm)),
+        (pack_conv3x3_weight_t_kernel<__nv_bfloat16><<<ew_blocks(total), 256, 0, st>>>(w_oihw, (__nv_bfloat16*)w_packed, cout, cin, ps_perm)));
+  return cuda_rc(cudaGetLastError());
+}
+
+int fsr_conv3x3_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int cin, int cout, int stride,
+                      int ps_perm, int dtype, void* stream) {
+  if (!x || !dy || !dw) return FSR_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == FSR_BF16) return wgrad_dispatch<__nv_bfloat16>(x, dy, dw, N, H, W, cin, cout, stride, ps_perm, dtype, st);
+  return wgrad_dispatch<__half>(x, dy, dw, N, H, W, cin, cout, stride, ps_perm, dtype, st);
+}
+
+int fsr_parity_layout(const void* in, void* out, int N, int H, int W, int C, int to_parity, int dtype, void* stream) {
+  if (!in || !out || C % 8 || ((H | W) & 1)) return FSR_ERR_BAD_ARG;
+  (void)dtype;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t total = (size_t)N * H * W * (C / 8);
+  LaunchScope scope(FSR_K_NONE - 1, st);
+  if (to_parity) parity_layout_kernel<true><<<ew_blocks(total), 256, 0, st>>>((const uint4*)in, (uint4*)out, N, H, W, C / 8);
+  else parity_layout_kernel<false><<<ew_blocks(total), 256, 0, st>>>((const uint4*)in, (uint4*)out, N, H, W, C / 8);
+  return cuda_rc(cudaGetLastError());
+}
+
+int fsr_maxpool2(const void* in, void* out, int N, int H, int W, int C, int dtype, void* stream) {
+  if (!in || !out || C % 8 || ((H | W) & 1)) return FSR_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t total = (size_t)N * (H / 2) * (W / 2) * (C / 8);
+  LaunchScope scope(FSR_K_NONE - 1, st);
+  FSR_T((maxpool2_fwd_kernel<__half><<<ew_blocks(total), 256, 0, st>>>((const __half*)in, (__half*)out, N, H, W, C)),
+        (maxpool2_fwd_kernel<__nv_bfloat16><<<ew_blocks(total), 256, 0, st>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, N, H, W, C)));
+  return cuda_rc(cudaGetLastError());
+}
+
+int fsr_maxpool2_relu_bwd(const void* in, const void* dout, void* din, int N, int H, int W, int C, int dtype, void* stream) {
+  if (!in || !dout || !din || ((H | W) & 1)) return FSR_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t total = (size_t)N * (H / 2) * (W / 2) * C;
+  LaunchScope scope(FSR_K_NONE - 1, st);
+  FSR_T((maxpool2_relu_bwd_kernel<__half><<<ew_blocks(total), 256, 0, st>>>((const __half*)in, (const __half*)dout, (__half*)din, N, H, W, C)),
+        (maxpool2_relu_bwd_kernel<__nv_bfloat16><<<ew_blocks(total), 256, 0, st>>>((const __nv_bfloat16*)in, (const __nv_bfloat16*)dout, (__nv_bfloat16*)din, N, H, W, C)));
+  return cuda_rc(cudaGetLastError());
+}
+
+int fsr_relu_bwd(const void* y, const void* dy, void* dx, size_t n_elems, int dtype, void* stream) {
+  if (!y || !dy || !dx || n_elems % 8) return FSR_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  LaunchScope scope(FSR_K_NONE - 1, st);
+  FSR_T((relu_bwd_kernel<__half><<<ew_blocks(n_elems / 8), 256, 0, st>>>((const uint4*)y, (const uint4*)dy, (uint4*)dx, n_elems / 8)),
+        (relu_bwd_kernel<__nv_bfloat16><<<ew_blocks(n_elems / 8), 256, 0, st>>>((const uint4*)y, (const uint4*)dy, (uint4*)dx, n_elems / 8)));
+  return cuda_rc(cudaGetLastError());
+}
+
+int fsr_add(const void* a, const void* b, void* out, size_t n_elems, int dtype, void* stream) {
+  if (!a || !b || !out || n_elems % 8) return FSR_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  LaunchScope scope(FSR_K_NONE - 1, st);
+  FSR_T((add_kernel<__half><<<ew_blocks(n_elems / 8), 256, 0, st>>>((const uint4*)a, (const uint4*)b, (uint4*)out, n_elems / 8)),
+        (add_kernel<__nv_bfloat16><<<ew_blocks(n_elems / 8), 256, 0, st>>>((const uint4*)a, (const uint4*)b, (uint4*)out, n_elems / 8)));
+  return cuda_rc(cudaGetLastError());
+}
+
+int fsr_conv1x1_to1_fwd(const void* x, const float* w, const float* b, float* z, int npix, int C, int dtype, void* stream) {
+  if (!x || !w || !b || !z || C % 64) return FSR_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int blocks = (npix * 32 + 255) / 256;
+  LaunchScope scope(FSR_K_NONE - 1, st);
+  FSR_T((conv1x1_to1_fwd_kernel<__half><<<blocks, 256, 0, st>>>((const __half*)x, w, b, z, npix, C)),
+        (conv1x1_to1_fwd_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, w, b, z, npix, C)));
+  return cuda_rc(cudaGetLastError());
+}
+
+int fsr_conv1x1_to1_bwd(const void* x, const float* w, const float* dz, void* dx, float* dw, float* db, int npix, int C,
+                        int dtype, void* stream) {
+  if (!x || !w || !dz) return FSR_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  int blocks = (npix + 15) / 16;
+  if (blocks > num_sms() * 4) blocks = num_sms() * 4;
+  LaunchScope scope(FSR_K_NONE - 1, st);
+  FSR_T((conv1x1_to1_bwd_kernel<__half><<<blocks, 256, 0, st>>>((const __half*)x, w, dz, (__half*)dx, dw, db, npix, C)),
+        (conv1x1_to1_bwd_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, w, dz, (__nv_bfloat16*)dx, dw, db, npix, C)));
+  return cuda_rc(cudaGetLastError());
+}
+
+int fsr_bce_logits(const float* z, const float* noise, float lab_scale, float lab_shift, int n, float* loss_out, float* dz,
+                   float grad_scale, void* stream) {
+  if (!z || !noise || !loss_out || n <= 0) return FSR_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  LaunchScope scope(FSR_K_NONE - 1, st);
+  bce_logits_kernel<<<1, 256, 0, st>>>(z, noise, lab_scale, lab_shift, n, loss_out, dz, grad_scale);
+  return cuda_rc(cudaGetLastError());
+}
+
+int fsr_smooth_l1(const void* a, const void* b, size_t n, float* loss_acc, void* da, float grad_scale, int dtype, void* stream) {
+  if (!a || !b || !loss_acc) return FSR_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  LaunchScope scope(FSR_K_NONE - 1, st);
+  if (dtype == 2) smooth_l1_f32_kernel<<<ew_blocks(n), 256, 0, st>>>((const float*)a, (const float*)b, n, loss_acc, (float*)da, grad_scale);
+  else FSR_T((smooth_l1_kernel<__half><<<ew_blocks(n), 256, 0, st>>>((const __half*)a, (const __half*)b, n, loss_acc, (__half*)da, grad_scale)),
+             (smooth_l1_kernel<__nv_bfloat16><<<ew_blocks(n), 256, 0, st>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, n, loss_acc, (__nv_bfloat16*)da, grad_scale)));
+  return cuda_rc(cudaGetLastError());
+}
+
+int fsr_instnorm_bwd(const void* raw, const float* stats, const void* dy, float* red, void* draw, const float* alpha,
+                     float* dalpha, int N, int HW, int C, int act, float slope, float eps, int dtype, void* stream) {
+  if (!raw || !stats || !dy || !red || !draw || C % 8 || 256 % (C / 8)) return FSR_ERR_BAD_ARG;
+  if (act == FSR_ACT_PRELU && !alpha) return FSR_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  InBwdParams p{raw, stats, dy, red, draw, alpha, dalpha, slope, act, HW, C, eps};
+  const size_t nvec = (size_t)HW * (C / 8);
+  int bpi = (int)((nvec + 256 * 8 - 1) / (256 * 8));
+  const int cap = (num_sms() * 4 + N - 1) / N;
+  if (bpi > cap) bpi = cap;
+  if (bpi < 1) bpi = 1;
+  dim3 grid(bpi, N);
+  const size_t sm = (size_t)4 * C * sizeof(float);
+  FSR_CUDA(cudaMemsetAsync(red, 0, (size_t)N * C * 2 * sizeof(float), st));
+  {
+    LaunchScope scope(FSR_K_NONE - 1, st);
+    FSR_T((instnorm_bwd_kernel<__half, 1><<<grid, 256, sm, st>>>(p)), (instnorm_bwd_kernel<__nv_bfloat16, 1><<<grid, 256, sm, st>>>(p)));
+  }
+  {
+    LaunchScope scope(FSR_K_NONE - 1, st);
+    FSR_T((instnorm_bwd_kernel<__half, 2><<<grid, 256, sm, st>>>(p)), (instnorm_bwd_kernel<__nv_bfloat16, 2><<<grid, 256, sm, st>>>(p)));
+  }
+  return cuda_rc(cudaGetLastError());
+}
+
+int fsr_act_bwd(const void* y, const void* dy, void* dv, size_t n_elems, const float* alpha, float slope, int act,
+                float* dalpha, int dtype, void* stream) {
+  if (!y || !dy || !dv || n_elems % 8) return FSR_ERR_BAD_ARG;
+  if (act == FSR_ACT_PRELU && !alpha) return FSR_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  LaunchScope scope(FSR_K_NONE - 1, st);
+  FSR_T((act_bwd_kernel<__half><<<ew_blocks(n_elems / 8), 256, 0, st>>>((const uint4*)y, (const uint4*)dy, (uint4*)dv, n_elems / 8, alpha, slope, act, dalpha)),
+        (act_bwd_kernel<__nv_bfloat16><<<ew_blocks(n_elems / 8), 256, 0, st>>>((const uint4*)y, (const uint4*)dy, (uint4*)dv, n_elems / 8, alpha, slope, act, dalpha)));
+  return cuda_rc(cudaGetLastError());
+}
+
+int fsr_ps_prelu_bwd(const void* U, const void* dU, void* dconv, int N, int H, int W, const float* alpha, float* dalpha,
+                     int dtype, void* stream) {
+  if (!U || !dU || !dconv || !alpha) return FSR_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t total = (size_t)N * H * W * 32;
+  LaunchScope scope(FSR_K_NONE - 1, st);
+  FSR_T((ps_prelu_bwd_kernel<__half><<<ew_blocks(total), 256, 0, st>>>((const __half*)U, (const __half*)dU, (__half*)dconv, N, H, W, alpha, dalpha)),
+        (ps_prelu_bwd_kernel<__nv_bfloat16><<<ew_blocks(total), 256, 0, st>>>((const __nv_bfloat16*)U, (const __nv_bfloat16*)dU, (__nv_bfloat16*)dconv, N, H, W, alpha, dalpha)));
+  return cuda_rc(cudaGetLastError());
+}
+
+int fsr_tanh_bwd(const float* y, const float* dy, float* dpre, size_t n, void* stream) {
+  if (!y || !dy || !dpre) return FSR_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  LaunchScope scope(FSR_K_NONE - 1, st);
+  tanh_bwd_kernel<<<ew_blocks(n), 256, 0, st>>>(y, dy, dpre, n);
+  return cuda_rc(cudaGetLastError());
+}
+
+int fsr_wgrad_c3(const float* img, const void* act, float* out, int N, int H, int W, int C64, int flip, int dtype, void* stream) {
+  if (!img || !act || !out || C64 % 64) return FSR_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t total = (size_t)N * H * W;
+  int bx = (int)((total + 4 * 64 - 1) / (4 * 64));
+  if (bx > num_sms() * 4) bx = num_sms() * 4;
+  if (bx < 1) bx = 1;
+  dim3 grid(bx, C64 / 64);
+  LaunchScope scope(FSR_K_NONE - 1, st);
+  FSR_T((wgrad_c3_kernel<__half><<<grid, 256, 0, st>>>(img, (const __half*)act, out, N, H, W, C64, flip)),
+        (wgrad_c3_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(img, (const __nv_bfloat16*)act, out, N, H, W, C64, flip)));
+  return cuda_rc(cudaGetLastError());
+}
+
+int fsr_bias_grad(const void* g, float* db, size_t npix, int C, int dtype, void* stream) {
+  if (!g || !db) return FSR_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  int blocks = (int)((npix + 63) / 64);
+  if (blocks > num_sms() * 4) blocks = num_sms() * 4;
+  if (blocks < 1) blocks = 1;
+  LaunchScope scope(FSR_K_NONE - 1, st);
+  FSR_T((bias_grad_kernel<__half><<<blocks, 256, 0, st>>>((const __half*)g, db, npix, C)),
+        (bias_grad_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)g, db, npix, C)));
+  return cuda_rc(cudaGetLastError());
+}
+
+int fsr_bias_grad_nchw(const float* g, float* db, int N, int C, size_t HW, void* stream) {
+  if (!g || !db) return FSR_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  int bx = (int)((HW + 255) / 256);
+  if (bx > 64) bx = 64;
+  LaunchScope scope(FSR_K_NONE - 1, st);
+  bias_grad_nchw_kernel<<<dim3(bx, C), 256, 0, st>>>(g, db, N, C, HW);
+  return cuda_rc(cudaGetLastError());
+}
+
+int fsr_adamw(float* p, const float* g, float* m, float* v, size_t n, float lr, float b1, float b2, float eps, float wd,
+              int step, float grad_scale, void* stream) {
+  if (!p || !g || !m || !v || step < 1) return FSR_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const float bc1 = 1.0f - powf(b1, (float)step);
+  const float bc2s = sqrtf(1.0f - powf(b2, (float)step));
+  LaunchScope scope(FSR_K_NONE - 1, st);
+  adamw_kernel<<<ew_blocks(n), 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, wd, bc1, bc2s, grad_scale);
+  return cuda_rc(cudaGetLastError());
 }
 
 }  // extern "C"

@@ -259,6 +259,21 @@ __global__ void pack_conv3x3_weight_kernel(const float* __restrict__ w, T* __res
   }
 }
 
+// Data-gradient pack: out[tap][ci][col] = W[oc(col)][ci][tap]  (rows = input channel, K = output channel,
+// taps unflipped - the flip lives in the tap table of the general conv).  ps_perm: col = q*(cout/4)+c <-> oc = 4c+q.
+template <typename T>
+__global__ void pack_conv3x3_weight_t_kernel(const float* __restrict__ w, T* __restrict__ out, int cout, int cin, int ps_perm) {
+  const size_t total = (size_t)9 * cin * cout;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int col = (int)(idx % cout);
+    const int ci = (int)((idx / cout) % cin);
+    const int tap = (int)(idx / ((size_t)cout * cin));
+    int oc = col;
+    if (ps_perm) { const int cq = cout / 4; oc = 4 * (col % cq) + col / cq; }
+    out[idx] = Cvt<T>::from_f(w[((size_t)oc * cin + ci) * 9 + tap]);
+  }
+}
+
 __global__ void permute_bias_ps_kernel(const float* __restrict__ b, float* __restrict__ out, int cout, int cout_pad,
                                        int ps_perm) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x;

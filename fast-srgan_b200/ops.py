@@ -141,3 +141,202 @@ def nhwc_to_nchw(x: torch.Tensor):
     L.check(L.load().fsr_nhwc_to_nchw_f32(x.data_ptr(), out.data_ptr(), N, C, H * W, L.dtype_code(x.dtype),
                                           L.stream_ptr(x.device)), "nhwc->nchw")
     return out
+
+
+# ============================================================ training-step kernels (trainer.py:168-196)
+def pack_conv3x3_t(weight: torch.Tensor, dtype: torch.dtype, ps_perm: bool = False) -> torch.Tensor:
+    """dgrad pack: OIHW fp32 -> [9][cin][cout(perm)] (rows = input channel, K = output channel)."""
+    _cuda(weight)
+    cout, cin = weight.shape[0], weight.shape[1]
+    w = weight.detach().float().contiguous()
+    wp = torch.empty((9, cin, cout), dtype=dtype, device=w.device)
+    L.check(L.load().fsr_pack_conv3x3_weight_t(w.data_ptr(), wp.data_ptr(), cout, cin, int(ps_perm), L.dtype_code(dtype),
+                                               L.stream_ptr(w.device)), "pack_t")
+    return wp
+
+
+def conv3x3_gen(x, w_packed, cout, stride=1, mode=0, epilogue=L.EPI_BIAS_ACT, bias=None, act=L.ACT_NONE, slope=0.0,
+                alpha=None, stats=None, hw=None):
+    """General tensor-core conv (see include/fsr_b200.h: fsr_conv3x3_gen).
+    mode 0 stride 1: x NHWC [N,H,W,cin]; mode 0 stride 2: x parity planes [N,4,H/2,W/2,cin];
+    mode 1 stride 1: x = dY; mode 1 stride 2: x = dY [N,H/2,W/2,cin] -> parity-plane dX.  hw = (H, W) of the
+    conv input (forward) / of dX (mode 1); inferred for stride 1."""
+    _cuda(x, w_packed, bias, alpha)
+    dt = L.dtype_code(x.dtype)
+    cin = x.shape[-1]
+    if stride == 1:
+        N, H, W, _ = x.shape
+        out = torch.empty((N, H, W, cout), dtype=x.dtype, device=x.device)
+    elif mode == 0:
+        N, _, H2, W2, _ = x.shape
+        H, W = 2 * H2, 2 * W2
+        out = torch.empty((N, H2, W2, cout), dtype=x.dtype, device=x.device)
+    else:
+        N, H2, W2, _ = x.shape
+        H, W = 2 * H2, 2 * W2
+        out = torch.empty((N, 4, H2, W2, cout), dtype=x.dtype, device=x.device)
+    if epilogue == L.EPI_RAW_STATS and stats is None:
+        stats = torch.zeros((N, cout, 2), dtype=torch.float32, device=x.device)
+    L.check(L.load().fsr_conv3x3_gen(x.data_ptr(), w_packed.data_ptr(), out.data_ptr(), L.ptr(bias), L.ptr(stats), L.ptr(alpha),
+                                     N, H, W, cin, cout, stride, mode, epilogue, act, slope, dt, L.stream_ptr(x.device)),
+            "conv3x3_gen")
+    return (out, stats) if epilogue == L.EPI_RAW_STATS else out
+
+
+def conv3x3_wgrad(x, dy, dw, stride=1, ps_perm=False):
+    """dw (fp32 OIHW, accumulated) += wgrad(x, dy).  stride 2: x in parity planes [N,4,H/2,W/2,cin]."""
+    _cuda(x, dy, dw)
+    if stride == 1:
+        N, H, W, cin = x.shape
+    else:
+        N, _, H2, W2, cin = x.shape
+        H, W = 2 * H2, 2 * W2
+    cout = dy.shape[-1]
+    L.check(L.load().fsr_conv3x3_wgrad(x.data_ptr(), dy.data_ptr(), dw.data_ptr(), N, H, W, cin, cout, stride, int(ps_perm),
+                                       L.dtype_code(x.dtype), L.stream_ptr(x.device)), "wgrad")
+    return dw
+
+
+def parity_layout(x, to_parity=True):
+    _cuda(x)
+    if to_parity:
+        N, H, W, C = x.shape
+        out = torch.empty((N, 4, H // 2, W // 2, C), dtype=x.dtype, device=x.device)
+    else:
+        N, _, H2, W2, C = x.shape
+        H, W = 2 * H2, 2 * W2
+        out = torch.empty((N, H, W, C), dtype=x.dtype, device=x.device)
+    L.check(L.load().fsr_parity_layout(x.data_ptr(), out.data_ptr(), N, H, W, C, int(to_parity), L.dtype_code(x.dtype),
+                                       L.stream_ptr(x.device)), "parity")
+    return out
+
+
+def maxpool2(x):
+    _cuda(x)
+    N, H, W, C = x.shape
+    out = torch.empty((N, H // 2, W // 2, C), dtype=x.dtype, device=x.device)
+    L.check(L.load().fsr_maxpool2(x.data_ptr(), out.data_ptr(), N, H, W, C, L.dtype_code(x.dtype), L.stream_ptr(x.device)), "maxpool")
+    return out
+
+
+def maxpool2_relu_bwd(x, dout):
+    _cuda(x, dout)
+    N, H, W, C = x.shape
+    din = torch.empty_like(x)
+    L.check(L.load().fsr_maxpool2_relu_bwd(x.data_ptr(), dout.data_ptr(), din.data_ptr(), N, H, W, C, L.dtype_code(x.dtype),
+                                           L.stream_ptr(x.device)), "maxpool bwd")
+    return din
+
+
+def relu_bwd(y, dy):
+    _cuda(y, dy)
+    dx = torch.empty_like(y)
+    L.check(L.load().fsr_relu_bwd(y.data_ptr(), dy.data_ptr(), dx.data_ptr(), y.numel(), L.dtype_code(y.dtype), L.stream_ptr(y.device)), "relu bwd")
+    return dx
+
+
+def add(a, b, out=None):
+    _cuda(a, b)
+    if out is None:
+        out = torch.empty_like(a)
+    L.check(L.load().fsr_add(a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel(), L.dtype_code(a.dtype), L.stream_ptr(a.device)), "add")
+    return out
+
+
+def conv1x1_to1_fwd(x, w, b):
+    """x NHWC [N,H,W,C], w fp32 [C], b fp32 [1] -> fp32 logits [N,H,W]."""
+    _cuda(x, w, b)
+    N, H, W, C = x.shape
+    z = torch.empty((N, H, W), dtype=torch.float32, device=x.device)
+    L.check(L.load().fsr_conv1x1_to1_fwd(x.data_ptr(), w.data_ptr(), b.data_ptr(), z.data_ptr(), N * H * W, C,
+                                         L.dtype_code(x.dtype), L.stream_ptr(x.device)), "conv1x1 fwd")
+    return z
+
+
+def conv1x1_to1_bwd(x, w, dz, dw=None, db=None, need_dx=True):
+    _cuda(x, w, dz, dw, db)
+    N, H, W, C = x.shape
+    dx = torch.empty_like(x) if need_dx else None
+    L.check(L.load().fsr_conv1x1_to1_bwd(x.data_ptr(), w.data_ptr(), dz.data_ptr(), L.ptr(dx), L.ptr(dw), L.ptr(db), N * H * W, C,
+                                         L.dtype_code(x.dtype), L.stream_ptr(x.device)), "conv1x1 bwd")
+    return dx
+
+
+def bce_logits(z, noise, lab_scale, lab_shift, loss_out, dz=None, grad_scale=1.0):
+    _cuda(z, noise, loss_out, dz)
+    L.check(L.load().fsr_bce_logits(z.data_ptr(), noise.data_ptr(), lab_scale, lab_shift, z.numel(), loss_out.data_ptr(), L.ptr(dz),
+                                    grad_scale, L.stream_ptr(z.device)), "bce")
+    return loss_out
+
+
+def smooth_l1(a, b, loss_acc, da=None, grad_scale=1.0):
+    _cuda(a, b, loss_acc, da)
+    dt = 2 if a.dtype == torch.float32 else L.dtype_code(a.dtype)
+    L.check(L.load().fsr_smooth_l1(a.data_ptr(), b.data_ptr(), a.numel(), loss_acc.data_ptr(), L.ptr(da), grad_scale, dt,
+                                   L.stream_ptr(a.device)), "smooth l1")
+    return loss_acc
+
+
+def instnorm_bwd(raw, stats, dy, act=L.ACT_NONE, slope=0.0, alpha=None, dalpha=None, eps=1e-5):
+    _cuda(raw, stats, dy, alpha, dalpha)
+    N, H, W, C = raw.shape
+    red = torch.empty((N, C, 2), dtype=torch.float32, device=raw.device)
+    draw = torch.empty_like(raw)
+    L.check(L.load().fsr_instnorm_bwd(raw.data_ptr(), stats.data_ptr(), dy.data_ptr(), red.data_ptr(), draw.data_ptr(), L.ptr(alpha),
+                                      L.ptr(dalpha), N, H * W, C, act, slope, eps, L.dtype_code(raw.dtype), L.stream_ptr(raw.device)),
+            "instnorm bwd")
+    return draw
+
+
+def act_bwd(y, dy, act, slope=0.0, alpha=None, dalpha=None):
+    _cuda(y, dy, alpha, dalpha)
+    dv = torch.empty_like(y)
+    L.check(L.load().fsr_act_bwd(y.data_ptr(), dy.data_ptr(), dv.data_ptr(), y.numel(), L.ptr(alpha), slope, act, L.ptr(dalpha),
+                                 L.dtype_code(y.dtype), L.stream_ptr(y.device)), "act bwd")
+    return dv
+
+
+def ps_prelu_bwd(U, dU, alpha, dalpha=None):
+    _cuda(U, dU, alpha, dalpha)
+    N, H2, W2, C = U.shape
+    H, W = H2 // 2, W2 // 2
+    dconv = torch.empty((N, H, W, 256), dtype=U.dtype, device=U.device)
+    L.check(L.load().fsr_ps_prelu_bwd(U.data_ptr(), dU.data_ptr(), dconv.data_ptr(), N, H, W, alpha.data_ptr(), L.ptr(dalpha),
+                                      L.dtype_code(U.dtype), L.stream_ptr(U.device)), "ps prelu bwd")
+    return dconv
+
+
+def tanh_bwd(y, dy):
+    _cuda(y, dy)
+    dpre = torch.empty_like(y)
+    L.check(L.load().fsr_tanh_bwd(y.data_ptr(), dy.data_ptr(), dpre.data_ptr(), y.numel(), L.stream_ptr(y.device)), "tanh bwd")
+    return dpre
+
+
+def wgrad_c3(img, act, out, flip=False):
+    """out fp32 [3*9][C64] += sum img[n,c3,y+dy,x+dx] * act[n,y,x,c]."""
+    _cuda(img, act, out)
+    N, H, W, C = act.shape
+    L.check(L.load().fsr_wgrad_c3(img.data_ptr(), act.data_ptr(), out.data_ptr(), N, H, W, C, int(flip), L.dtype_code(act.dtype),
+                                  L.stream_ptr(act.device)), "wgrad c3")
+    return out
+
+
+def bias_grad(g, db):
+    _cuda(g, db)
+    C = g.shape[-1]
+    L.check(L.load().fsr_bias_grad(g.data_ptr(), db.data_ptr(), g.numel() // C, C, L.dtype_code(g.dtype), L.stream_ptr(g.device)), "bias grad")
+    return db
+
+
+def bias_grad_nchw(g, db):
+    _cuda(g, db)
+    N, C, H, W = g.shape
+    L.check(L.load().fsr_bias_grad_nchw(g.data_ptr(), db.data_ptr(), N, C, H * W, L.stream_ptr(g.device)), "bias grad nchw")
+    return db
+
+
+def adamw(p, g, m, v, lr, step, b1=0.9, b2=0.999, eps=1e-8, wd=1e-2, grad_scale=1.0):
+    _cuda(p, g, m, v)
+    L.check(L.load().fsr_adamw(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, b1, b2, eps, wd, step, grad_scale,
+                               L.stream_ptr(p.device)), "adamw")

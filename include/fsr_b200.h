@@ -61,6 +61,19 @@ int fsr_conv3x3_c64(const void* x, const void* w_packed, void* out, const float*
                     const float* alpha, int N, int H, int W, int cout, int epilogue, int act, float slope,
                     int out_u8, int dtype, void* stream);
 
+/* General 3x3 / pad 1 convolution on tcgen05: cin, cout multiples of 64, stride 1 or 2, forward (mode 0)
+ * or data gradient (mode 1).  Replaces torch.nn.Conv2d at model.py:124-131 (SimpleBlock.conv), the
+ * torchvision VGG19 convs behind model.py:8, and autograd's convolution_backward (input gradient) for
+ * trainer.py:180,195.  H, W = spatial size of the conv INPUT (forward) / of dX (mode 1).
+ *   mode 0, stride 1: x [N,H,W,cin] NHWC -> out [N,H,W,cout]
+ *   mode 0, stride 2: x in parity-plane layout [N][4][H/2][W/2][cin] -> out [N,H/2,W/2,cout] NHWC
+ *   mode 1, stride 1: x = dY [N,H,W,cin=Cout_fwd]; w packed with transpose=1 -> out = dX [N,H,W,cout=Cin_fwd]
+ *   mode 1, stride 2: x = dY [N,H/2,W/2,cin]; out = dX in parity-plane layout [N][4][H/2][W/2][cout]
+ * epilogue: FSR_EPI_RAW_STATS (out + InstanceNorm sum/sumsq) or FSR_EPI_BIAS_ACT. */
+int fsr_conv3x3_gen(const void* x, const void* w_packed, void* out, const float* bias, float* stats,
+                    const float* alpha, int N, int H, int W, int cin, int cout, int stride, int mode, int epilogue,
+                    int act, float slope, int dtype, void* stream);
+
 /* Conv2d(3 -> cout, k3, p1) + bias + activation, direct (HBM-bound; K = 27 is no tensor-core shape).
  * Replaces model.py:75-78 (Generator.neck, PReLU) and :143-146 (Discriminator.neck, LeakyReLU 0.2);
  * vgg_norm=1 also folds VGG19.forward's renormalisation model.py:21-22 into the load (VGG conv1_1).
@@ -82,6 +95,62 @@ int fsr_pixel_shuffle2(const void* in, void* out, int N, int H, int W, int C, in
 /* Module-boundary layout conversion (the reference is NCHW fp32 everywhere, inference.py:50-51). */
 int fsr_nchw_f32_to_nhwc(const float* in, void* out, int N, int C, int HW, int dtype, void* stream);
 int fsr_nhwc_to_nchw_f32(const void* in, float* out, int N, int C, int HW, int dtype, void* stream);
+
+/* ====================== GAN training step (trainer.py:168-196): backward, losses, optimiser ======================
+ * Tensors are NHWC `dtype` unless stated; gradients of parameters are fp32 in torch's OIHW layout, ACCUMULATED (+=). */
+
+/* dgrad pack: out[tap][ci][col] = W[oc(col)][ci][tap] (rows = input channel, K = output channel); feed to
+ * fsr_conv3x3_gen(mode=1) with cin := Cout_fwd, cout := Cin_fwd. */
+int fsr_pack_conv3x3_weight_t(const float* w_oihw, void* w_packed, int cout, int cin, int ps_perm, int dtype, void* stream);
+
+/* Weight gradient of a 3x3/pad-1 conv on tcgen05 (autograd convolution_backward, weight part):
+ * dw[co,ci,r,s] += sum dY[n,y,x,co] * X[n, stride*y+r-1, stride*x+s-1, ci].  H, W = X spatial size;
+ * stride 2: X in parity-plane layout.  ps_perm: dY columns are pixel-shuffle-permuted (UpSamplingBlock). */
+int fsr_conv3x3_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int cin, int cout, int stride,
+                      int ps_perm, int dtype, void* stream);
+
+/* NHWC [N,H,W,C] <-> parity planes [N][4][H/2][W/2][C] (input layout of stride-2 convs, model.py:124-131). */
+int fsr_parity_layout(const void* in, void* out, int N, int H, int W, int C, int to_parity, int dtype, void* stream);
+
+/* torch.nn.MaxPool2d(2) of VGG19.features (model.py:8) and its backward fused with the preceding ReLU's. */
+int fsr_maxpool2(const void* in, void* out, int N, int H, int W, int C, int dtype, void* stream);
+int fsr_maxpool2_relu_bwd(const void* in, const void* dout, void* din, int N, int H, int W, int C, int dtype, void* stream);
+int fsr_relu_bwd(const void* y, const void* dy, void* dx, size_t n_elems, int dtype, void* stream);
+int fsr_add(const void* a, const void* b, void* out, size_t n_elems, int dtype, void* stream);
+
+/* Discriminator's final Conv2d(8F -> 1, k1) (model.py:184-186): fp32 logits z[npix]; backward. */
+int fsr_conv1x1_to1_fwd(const void* x, const float* w, const float* b, float* z, int npix, int C, int dtype, void* stream);
+int fsr_conv1x1_to1_bwd(const void* x, const float* w, const float* dz, void* dx, float* dw, float* db, int npix, int C,
+                        int dtype, void* stream);
+
+/* BCEWithLogitsLoss (trainer.py:41,177,178,188) with labels t = lab_scale*noise + lab_shift (trainer.py:175,176,187):
+ * loss_out[0] = mean loss; dz (nullable) = grad_scale * dloss/dz. */
+int fsr_bce_logits(const float* z, const float* noise, float lab_scale, float lab_shift, int n, float* loss_out, float* dz,
+                   float grad_scale, void* stream);
+/* SmoothL1Loss(beta=1) (trainer.py:43,192 / :109): loss_acc[0] += SUM of elementwise losses (caller divides by n);
+ * da (nullable) = grad_scale * dsum/da.  dtype 2 = fp32 operands (pretrain step on images). */
+int fsr_smooth_l1(const void* a, const void* b, size_t n, float* loss_acc, void* da, float grad_scale, int dtype, void* stream);
+
+/* InstanceNorm2d (+PReLU|LeakyReLU) backward (model.py:55-56,65,94,132-133): from the conv output `raw`, its forward
+ * statistics and dY, writes dRaw; PReLU slope gradient accumulated into dalpha.  red = [N][C][2] fp32 scratch. */
+int fsr_instnorm_bwd(const void* raw, const float* stats, const void* dy, float* red, void* draw, const float* alpha,
+                     float* dalpha, int N, int HW, int C, int act, float slope, float eps, int dtype, void* stream);
+/* activation backward from the stored post-activation tensor (neck PReLU / LeakyReLU). */
+int fsr_act_bwd(const void* y, const void* dy, void* dv, size_t n_elems, const float* alpha, float slope, int act,
+                float* dalpha, int dtype, void* stream);
+/* UpSamplingBlock (model.py:39-40) backward glue: dU [N,2H,2W,64] -> dConv [N,H,W,256] (permuted columns). */
+int fsr_ps_prelu_bwd(const void* U, const void* dU, void* dconv, int N, int H, int W, const float* alpha, float* dalpha,
+                     int dtype, void* stream);
+/* head tanh backward (model.py:109): dpre = dy * (1 - y^2), fp32 NCHW. */
+int fsr_tanh_bwd(const float* y, const float* dy, float* dpre, size_t n, void* stream);
+/* weight gradient of a 3x3 conv with a 3-channel side (necks: flip=0, img = conv input; head: flip=1, img = dpre):
+ * out[(c3*9 + tap)*C64 + c64] += sum img[n,c3,y+dy,x+dx] * act[n,y,x,c64]. */
+int fsr_wgrad_c3(const float* img, const void* act, float* out, int N, int H, int W, int C64, int flip, int dtype, void* stream);
+int fsr_bias_grad(const void* g, float* db, size_t npix, int C, int dtype, void* stream);
+int fsr_bias_grad_nchw(const float* g, float* db, int N, int C, size_t HW, void* stream);
+/* torch.optim.AdamW (trainer.py:33-38,181,196) on flat fp32 buffers; g is multiplied by grad_scale first. */
+int fsr_adamw(float* p, const float* g, float* m, float* v, size_t n, float lr, float b1, float b2, float eps, float wd,
+              int step, float grad_scale, void* stream);
 
 /* ---- whole Generator.forward (model.py:112-117) as one call: neck -> n_layers residual blocks ->
  * bottleneck + long skip -> 2 x (conv + pixel-shuffle + PReLU) -> head + tanh. */
@@ -117,7 +186,7 @@ int fsr_generator_forward(const FsrGeneratorParams* prm, const void* x, void* y,
  * fsr_profile_read() synchronises those events, writes the elapsed milliseconds and clears the list.
  * fsr_launch_count() = number of kernels this library has launched so far in this process. */
 enum { FSR_K_NONE = -1, FSR_K_NECK = 0, FSR_K_CONV_RES = 1, FSR_K_IN_APPLY = 2, FSR_K_CONV_UP = 3,
-       FSR_K_CONV_HEAD = 4, FSR_K_CONV_BIAS_ACT = 5 };
+       FSR_K_CONV_HEAD = 4, FSR_K_CONV_BIAS_ACT = 5, FSR_K_CONV_GEN = 6, FSR_K_CONV_WGRAD = 7 };
 #define FSR_PROFILE_MAX 4096
 int fsr_profile_enable(int kernel_id);
 int fsr_profile_read(float* ms_out, int capacity);
