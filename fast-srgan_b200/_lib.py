@@ -35,7 +35,7 @@ _SIGS = {
     "fsr_pack_conv3x3_weight": (_i, [_fp, _fp, _vp, _fp, _i, _i, _i, _i, _i, _vp]),
     "fsr_conv3x3_c64": (_i, [_vp, _vp, _vp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _f, _i, _i, _vp]),
     "fsr_conv3x3_gen": (_i, [_vp, _vp, _vp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp]),
-    "fsr_pack_conv3x3_weight_t": (_i, [_fp, _vp, _i, _i, _i, _i, _vp]),
+    "fsr_pack_conv3x3_weight_t": (_i, [_fp, _vp, _i, _i, _i, _i, _i, _fp, _i, _vp]),
     "fsr_conv3x3_wgrad": (_i, [_vp, _vp, _fp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "fsr_parity_layout": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "fsr_maxpool2": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
@@ -50,8 +50,8 @@ _SIGS = {
     "fsr_act_bwd": (_i, [_vp, _vp, _vp, _sz, _fp, _f, _i, _fp, _i, _vp]),
     "fsr_ps_prelu_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _fp, _fp, _i, _vp]),
     "fsr_tanh_bwd": (_i, [_fp, _fp, _fp, _sz, _vp]),
-    "fsr_wgrad_c3": (_i, [_fp, _vp, _fp, _i, _i, _i, _i, _i, _i, _vp]),
-    "fsr_bias_grad": (_i, [_vp, _fp, _sz, _i, _i, _vp]),
+    "fsr_wgrad_c3": (_i, [_fp, _vp, _fp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "fsr_bias_grad": (_i, [_vp, _fp, _sz, _i, _i, _i, _vp]),
     "fsr_bias_grad_nchw": (_i, [_fp, _fp, _i, _i, _sz, _vp]),
     "fsr_adamw": (_i, [_fp, _fp, _fp, _fp, _sz, _f, _f, _f, _f, _f, _i, _f, _vp]),
     "fsr_neck_conv3x3": (_i, [_vp, _fp, _fp, _fp, _vp, _i, _i, _i, _i, _i, _f, _i, _i, _i, _vp]),

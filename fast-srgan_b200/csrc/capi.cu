@@ -188,7 +188,7 @@ int conv_dispatch(const void* x, const void* w_packed, void* out, const float* b
       return launch_conv_mode<128, EPI_PS_PRELU, T>(x, w_packed, 9 * 256, p, dtype, st);
     }
     case FSR_EPI_HEAD_TANH: {
-      if (cout != 16) return FSR_ERR_BAD_ARG;   // padded head: 3 real + 13 zero rows
+      if (cout != 16 || out_u8 < 0 || out_u8 > 3) return FSR_ERR_BAD_ARG;   // padded head: 3 real + 13 zero rows
       p.cout_total = 16; p.num_slices = 1;
       return launch_conv_mode<16, EPI_HEAD_TANH, T>(x, w_packed, 9 * 16, p, dtype, st);
     }
@@ -583,14 +583,15 @@ int fsr_generator_forward(const FsrGeneratorParams* prm, const void* x, void* y,
 // ====================================================================== training-step entry points
 #define FSR_T(expr_h, expr_b) do { if (dtype == FSR_BF16) { expr_b; } else { expr_h; } } while (0)
 
-int fsr_pack_conv3x3_weight_t(const float* w_oihw, void* w_packed, int cout, int cin, int ps_perm, int dtype, void* stream) {
-  // transposed pack for data-gradient convs: out[tap][ci][co(perm)] = W[co][ci][tap]  (rows = ci, K = co)
-  if (!w_oihw || !w_packed || cout <= 0 || cin <= 0) return FSR_ERR_BAD_ARG;
+int fsr_pack_conv3x3_weight_t(const float* w_oihw, void* w_packed, int cout, int cin, int ps_perm, int flip, int row_pad,
+                              const float* row_scale, int dtype, void* stream) {
+  // transposed pack for data-gradient convs (rows = forward input channel, K = forward output channel)
+  if (!w_oihw || !w_packed || cout <= 0 || cin <= 0 || row_pad < cin) return FSR_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t total = (size_t)9 * cout * cin;
+  const size_t total = (size_t)9 * cout * row_pad;
   LaunchScope scope(FSR_K_NONE - 1, st);
-  FSR_T((pack_conv3x3_weight_t_kernel<__half><<<ew_blocks(total), 256, 0, st>>>(w_oihw, (__half*)w_packed, cout, cin, ps_perm)),
-        (pack_conv3x3_weight_t_kernel<__nv_bfloat16><<<ew_blocks(total), 256, 0, st>>>(w_oihw, (__nv_bfloat16*)w_packed, cout, cin, ps_perm)));
+  FSR_T((pack_conv3x3_weight_t_kernel<__half><<<ew_blocks(total), 256, 0, st>>>(w_oihw, (__half*)w_packed, cout, cin, ps_perm, flip, row_pad, row_scale)),
+        (pack_conv3x3_weight_t_kernel<__nv_bfloat16><<<ew_blocks(total), 256, 0, st>>>(w_oihw, (__nv_bfloat16*)w_packed, cout, cin, ps_perm, flip, row_pad, row_scale)));
   return cuda_rc(cudaGetLastError());
 }
 
@@ -747,7 +748,8 @@ int fsr_tanh_bwd(const float* y, const float* dy, float* dpre, size_t n, void* s
   return cuda_rc(cudaGetLastError());
 }
 
-int fsr_wgrad_c3(const float* img, const void* act, float* out, int N, int H, int W, int C64, int flip, int dtype, void* stream) {
+int fsr_wgrad_c3(const float* img, const void* act, float* out, int N, int H, int W, int C64, int flip, int layout, int dtype,
+                 void* stream) {
   if (!img || !act || !out || C64 % 64) return FSR_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t total = (size_t)N * H * W;
@@ -756,20 +758,20 @@ int fsr_wgrad_c3(const float* img, const void* act, float* out, int N, int H, in
   if (bx < 1) bx = 1;
   dim3 grid(bx, C64 / 64);
   LaunchScope scope(FSR_K_NONE - 1, st);
-  FSR_T((wgrad_c3_kernel<__half><<<grid, 256, 0, st>>>(img, (const __half*)act, out, N, H, W, C64, flip)),
-        (wgrad_c3_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(img, (const __nv_bfloat16*)act, out, N, H, W, C64, flip)));
+  FSR_T((wgrad_c3_kernel<__half><<<grid, 256, 0, st>>>(img, (const __half*)act, out, N, H, W, C64, flip, layout)),
+        (wgrad_c3_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(img, (const __nv_bfloat16*)act, out, N, H, W, C64, flip, layout)));
   return cuda_rc(cudaGetLastError());
 }
 
-int fsr_bias_grad(const void* g, float* db, size_t npix, int C, int dtype, void* stream) {
+int fsr_bias_grad(const void* g, float* db, size_t npix, int C, int ps_perm, int dtype, void* stream) {
   if (!g || !db) return FSR_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   int blocks = (int)((npix + 63) / 64);
   if (blocks > num_sms() * 4) blocks = num_sms() * 4;
   if (blocks < 1) blocks = 1;
   LaunchScope scope(FSR_K_NONE - 1, st);
-  FSR_T((bias_grad_kernel<__half><<<blocks, 256, 0, st>>>((const __half*)g, db, npix, C)),
-        (bias_grad_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)g, db, npix, C)));
+  FSR_T((bias_grad_kernel<__half><<<blocks, 256, 0, st>>>((const __half*)g, db, npix, C, ps_perm)),
+        (bias_grad_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)g, db, npix, C, ps_perm)));
   return cuda_rc(cudaGetLastError());
 }
 

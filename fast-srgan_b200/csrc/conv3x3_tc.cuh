@@ -48,7 +48,8 @@ struct ConvParams {
   const float* alpha;       // device pointer to the PReLU slope (ACT_PRELU)
   float slope;              // LeakyReLU slope (ACT_LRELU)
   int act;                  // ActMode (EPI_BIAS_ACT)
-  int out_u8;               // EPI_HEAD_TANH: 0 -> fp32 NCHW [N,3,H,W]; 1 -> uint8 NHWC [N,H,W,3]
+  int out_u8;               // EPI_HEAD_TANH: 0 -> tanh, fp32 NCHW [N,3,H,W]; 1 -> tanh, uint8 NHWC [N,H,W,3];
+                            //                2 -> linear (no tanh) fp32 NCHW store; 3 -> linear, accumulate (+=)
 };
 
 template <bool HALO1>
@@ -277,8 +278,11 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         if (pvalid) {
           float o[3];
 #pragma unroll
-          for (int c = 0; c < 3; ++c) o[c] = tanhf(__uint_as_float(r[c]) + smem_bias[c]);
-          if (p.out_u8) {
+          for (int c = 0; c < 3; ++c) {
+            const float v = __uint_as_float(r[c]) + smem_bias[c];
+            o[c] = p.out_u8 >= 2 ? v : tanhf(v);
+          }
+          if (p.out_u8 == 1) {
             // reference inference.py:54-56: ((y+1)/2*255).astype(uint8)  (truncation)
             uint8_t* o8 = reinterpret_cast<uint8_t*>(p.out) + ((size_t)(n * p.H + y) * p.W + x) * 3;
 #pragma unroll
@@ -290,7 +294,10 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
             float* of = reinterpret_cast<float*>(p.out);
             const size_t plane = (size_t)p.H * p.W;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) of[((size_t)n * 3 + c) * plane + (size_t)y * p.W + x] = o[c];
+            for (int c = 0; c < 3; ++c) {
+              float* dst = of + ((size_t)n * 3 + c) * plane + (size_t)y * p.W + x;
+              *dst = (p.out_u8 == 3) ? *dst + o[c] : o[c];
+            }
           }
         }
       } else {

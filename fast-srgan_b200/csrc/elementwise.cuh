@@ -259,18 +259,26 @@ __global__ void pack_conv3x3_weight_kernel(const float* __restrict__ w, T* __res
   }
 }
 
-// Data-gradient pack: out[tap][ci][col] = W[oc(col)][ci][tap]  (rows = input channel, K = output channel,
-// taps unflipped - the flip lives in the tap table of the general conv).  ps_perm: col = q*(cout/4)+c <-> oc = 4c+q.
+// Data-gradient pack: out[tap'][ci (rows, padded to row_pad)][col] = scale[ci] * W[oc(col)][ci][flip ? 8-tap' : tap']
+// (rows = forward INPUT channel, K = forward OUTPUT channel).  flip=0 for the general conv (its tap table
+// carries the flip), flip=1 for the resident-weight 64-channel / head-style kernels.  ps_perm: col = q*(cout/4)+c
+// <-> oc = 4c+q.  row_scale (nullable, [cin]) folds a per-input-channel factor (VGG renorm chain rule).
 template <typename T>
-__global__ void pack_conv3x3_weight_t_kernel(const float* __restrict__ w, T* __restrict__ out, int cout, int cin, int ps_perm) {
-  const size_t total = (size_t)9 * cin * cout;
+__global__ void pack_conv3x3_weight_t_kernel(const float* __restrict__ w, T* __restrict__ out, int cout, int cin, int ps_perm,
+                                             int flip, int row_pad, const float* __restrict__ row_scale) {
+  const size_t total = (size_t)9 * row_pad * cout;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
     const int col = (int)(idx % cout);
-    const int ci = (int)((idx / cout) % cin);
-    const int tap = (int)(idx / ((size_t)cout * cin));
-    int oc = col;
-    if (ps_perm) { const int cq = cout / 4; oc = 4 * (col % cq) + col / cq; }
-    out[idx] = Cvt<T>::from_f(w[((size_t)oc * cin + ci) * 9 + tap]);
+    const int ci = (int)((idx / cout) % row_pad);
+    const int tap = (int)(idx / ((size_t)cout * row_pad));
+    float v = 0.f;
+    if (ci < cin) {
+      int oc = col;
+      if (ps_perm) { const int cq = cout / 4; oc = 4 * (col % cq) + col / cq; }
+      v = w[((size_t)oc * cin + ci) * 9 + (flip ? 8 - tap : tap)];
+      if (row_scale) v *= row_scale[ci];
+    }
+    out[idx] = Cvt<T>::from_f(v);
   }
 }
 

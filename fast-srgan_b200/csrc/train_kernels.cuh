@@ -404,7 +404,8 @@ __global__ void __launch_bounds__(256) tanh_bwd_kernel(const float* __restrict__
 // act = x).  out[(c3*9 + tap)*C64 + c64] fp32 (+=).  Block = 64 threads-channels x pixel chunks.
 template <typename T>
 __global__ void __launch_bounds__(256) wgrad_c3_kernel(const float* __restrict__ img, const T* __restrict__ act,
-                                                       float* __restrict__ out, int N, int H, int W, int C64, int flip) {
+                                                       float* __restrict__ out, int N, int H, int W, int C64, int flip,
+                                                       int layout /*0: [27][C64]; 1: OIHW [3][C64][9] (head); 2: OIHW [C64][3][9] (neck)*/) {
   // thread: channel c = threadIdx.x % 64 (+ blockIdx.y * 64), pixel lane pl = threadIdx.x / 64 (4 lanes)
   const int c = blockIdx.y * 64 + (threadIdx.x & 63);
   const int pl = threadIdx.x >> 6;
@@ -434,20 +435,29 @@ __global__ void __launch_bounds__(256) wgrad_c3_kernel(const float* __restrict__
 #pragma unroll
   for (int k = 0; k < 27; ++k) atomicAdd(&red[k][threadIdx.x & 63], acc[k]);
   __syncthreads();
-  for (int k = threadIdx.x; k < 27 * 64; k += blockDim.x)
-    atomicAdd(out + (size_t)(k / 64) * C64 + blockIdx.y * 64 + (k % 64), red[k / 64][k % 64]);
+  for (int k = threadIdx.x; k < 27 * 64; k += blockDim.x) {
+    const int t27 = k / 64, c64 = blockIdx.y * 64 + (k % 64);
+    const int c3 = t27 / 9, tap = t27 % 9;
+    size_t idx;
+    if (layout == 1) idx = ((size_t)c3 * C64 + c64) * 9 + tap;
+    else if (layout == 2) idx = ((size_t)c64 * 3 + c3) * 9 + tap;
+    else idx = (size_t)t27 * C64 + c64;
+    atomicAdd(out + idx, red[t27][k % 64]);
+  }
 }
 
 // bias gradient: db[c] += sum over pixels of g[pix, c]  (g NHWC T, C channels)
 template <typename T>
-__global__ void __launch_bounds__(256) bias_grad_kernel(const T* __restrict__ g, float* __restrict__ db, size_t npix, int C) {
+__global__ void __launch_bounds__(256) bias_grad_kernel(const T* __restrict__ g, float* __restrict__ db, size_t npix, int C,
+                                                        int ps_perm /* g columns pixel-shuffle-permuted: col q*C/4+c <-> channel 4c+q */) {
   // block covers a pixel chunk; thread t handles channel t % C... generic: loop channels by stride
   const size_t per = (npix + gridDim.x - 1) / gridDim.x;
   const size_t p0 = (size_t)blockIdx.x * per, p1 = min(npix, p0 + per);
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float acc = 0.f;
     for (size_t p = p0; p < p1; ++p) acc += Cvt<T>::to_f(g[p * C + c]);
-    atomicAdd(db + c, acc);
+    const int cq = C >> 2;
+    atomicAdd(db + (ps_perm ? 4 * (c % cq) + c / cq : c), acc);
   }
 }
 // fp32 NCHW variant (head bias: g = dpre [N,3,H,W])

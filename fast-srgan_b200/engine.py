@@ -1,0 +1,382 @@
+"""Functional training engine: forward + hand-written backward of Generator / Discriminator / VGG19
+on libfsr_b200 kernels, and the GAN step of reference trainer.py:168-196.
+
+No autograd: the networks are static, so the backward pass is an explicit reverse walk over saved
+activations (every FLOP in libfsr_b200.so; torch only owns memory).  Parameter gradients are
+accumulated in fp32 straight into torch-layout (OIHW) views of ONE flat buffer per network, which is
+what the NCCL all-reduce and the fused AdamW consume.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+
+from . import _lib as L
+from . import ops
+
+D_STRIDES = (2, 1, 2, 1, 2, 1, 2)                       # reference model.py:148-183
+VGG_PLAN = [64, 64, "M", 128, 128, "M", 256, 256, 256, 256, "M", 512, 512, 512, 512, "M", 512, 512, 512]
+
+
+def vgg_conv_indices() -> List[int]:
+    """torchvision `features` indices of the 16 convs kept by features[:34] (model.py:8)."""
+    idx, i = [], 0
+    for v in VGG_PLAN:
+        if v == "M":
+            i += 1
+        else:
+            idx.append(i)
+            i += 2
+    return idx
+
+
+class FlatParams:
+    """All parameters of a module re-pointed into one flat fp32 buffer (+ flat grad / Adam moments)."""
+
+    def __init__(self, module: torch.nn.Module, with_optimizer: bool = True):
+        params = [(n, p) for n, p in module.named_parameters()]
+        self.names = [n for n, _ in params]
+        dev = params[0][1].device
+        # 4-element alignment per tensor so every view is 16-byte aligned
+        self.offsets, off = {}, 0
+        for n, p in params:
+            self.offsets[n] = off
+            off += (p.numel() + 3) // 4 * 4
+        self.numel = off
+        self.flat = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.p: Dict[str, torch.Tensor] = {}
+        self.g: Dict[str, torch.Tensor] = {}
+        for n, p in params:
+            o = self.offsets[n]
+            view = self.flat[o:o + p.numel()].view_as(p)
+            view.copy_(p.data)
+            p.data = view                                  # the module now aliases the flat buffer
+            self.p[n] = view
+            self.g[n] = self.grad[o:o + p.numel()].view_as(p)
+        if with_optimizer:
+            self.m = torch.zeros_like(self.flat)
+            self.v = torch.zeros_like(self.flat)
+        self.step_count = 0
+        self.version = 0
+        module._fsr_flat = self                            # lets the module's own forward reuse this aliasing
+
+    def aliases(self, module) -> bool:
+        n, p = next(iter(module.named_parameters()))
+        return p.data_ptr() == self.p[n].data_ptr()
+
+    def zero_grad(self):
+        self.grad.zero_()
+
+    def adamw_step(self, lr: float, grad_scale: float = 1.0):
+        """torch.optim.AdamW defaults of trainer.py:33-38 (betas .9/.999, eps 1e-8, weight_decay 1e-2)."""
+        self.step_count += 1
+        ops.adamw(self.flat, self.grad, self.m, self.v, lr, self.step_count, grad_scale=grad_scale)
+        self.version += 1
+
+
+# ====================================================================================== Generator
+class GeneratorNet:
+    """model.py:72-117 forward (saving activations) and backward."""
+
+    def __init__(self, module, fp: FlatParams, dtype: torch.dtype):
+        self.m, self.fp, self.dt = module, fp, dtype
+        self.L = module.n_layers
+        self._packed_version = -1
+        self.P: Dict[str, torch.Tensor] = {}
+
+    def _convs64(self):
+        names = []
+        for i in range(self.L):
+            names += [f"stem.{i}.conv1.weight", f"stem.{i}.conv2.weight"]
+        return names + ["bottleneck.0.weight"]
+
+    def pack(self, need_bwd: bool):
+        if self._packed_version == self.fp.version and (not need_bwd or "bwd" in self.P):
+            return
+        p, P, dt = self.fp.p, {}, self.dt
+        for n in self._convs64():
+            P[n], _ = ops.pack_conv3x3(p[n], None, dt)
+            if need_bwd:
+                P[n + ".t"] = ops.pack_conv3x3_t(p[n], dt, flip=True)              # c64-kernel dgrad
+        for i in range(2):
+            P[f"up{i}.w"], P[f"up{i}.b"] = ops.pack_conv3x3(p[f"upsampling.{i}.conv.weight"], p[f"upsampling.{i}.conv.bias"], dt, ps_perm=True)
+            if need_bwd:
+                P[f"up{i}.t"] = ops.pack_conv3x3_t(p[f"upsampling.{i}.conv.weight"], dt, ps_perm=True)   # gen-kernel dgrad
+        P["head.w"], P["head.b"] = ops.pack_conv3x3(p["head.0.weight"], p["head.0.bias"], dt, cout_pad=16)
+        if need_bwd:
+            # head dgrad = direct 3->64 conv with transposed, flipped weights (K = 27: CUDA cores)
+            P["head.t"] = p["head.0.weight"].permute(1, 0, 2, 3).flip(2, 3).contiguous()
+            P["bwd"] = torch.empty(0)
+        self.P, self._packed_version = P, self.fp.version
+
+    def forward(self, lr_img: torch.Tensor, save: bool):
+        self.pack(need_bwd=save)
+        p, P, dt = self.fp.p, self.P, self.dt
+        a0 = ops.neck_conv3x3(lr_img, p["neck.0.weight"], p["neck.0.bias"], dt, act=L.ACT_PRELU, alpha=p["neck.1.weight"])
+        cur, blocks = a0, []
+        for i in range(self.L):
+            raw1, st1 = ops.conv3x3_c64_raw_stats(cur, P[f"stem.{i}.conv1.weight"])
+            y1 = ops.instnorm_apply(raw1, st1, act=L.ACT_PRELU, alpha=p[f"stem.{i}.relu1.weight"])
+            raw2, st2 = ops.conv3x3_c64_raw_stats(y1, P[f"stem.{i}.conv2.weight"])
+            out = ops.instnorm_apply(raw2, st2, residual=cur)
+            if save:
+                blocks.append((cur, raw1, st1, y1, raw2, st2))
+            cur = out
+        rawb, stb = ops.conv3x3_c64_raw_stats(cur, P["bottleneck.0.weight"])
+        xb = ops.instnorm_apply(rawb, stb, residual=a0)
+        U0 = ops.conv3x3_c64_ps_prelu(xb, P["up0.w"], P["up0.b"], p["upsampling.0.relu.weight"])
+        U1 = ops.conv3x3_c64_ps_prelu(U0, P["up1.w"], P["up1.b"], p["upsampling.1.relu.weight"])
+        sr = ops.conv3x3_c64_head(U1, P["head.w"], P["head.b"])
+        ctx = dict(lr=lr_img, a0=a0, blocks=blocks, x_last=cur, rawb=rawb, stb=stb, xb=xb, U0=U0, U1=U1, sr=sr) if save else None
+        return sr, ctx
+
+    def backward(self, ctx, d_sr: torch.Tensor):
+        """d_sr: fp32 NCHW gradient w.r.t. the generator output; accumulates into fp.g."""
+        p, g, P, dt = self.fp.p, self.fp.g, self.P, self.dt
+        dpre = ops.tanh_bwd(ctx["sr"], d_sr)                                           # model.py:109
+        ops.wgrad_c3(dpre, ctx["U1"], g["head.0.weight"], flip=True, layout=1)
+        ops.bias_grad_nchw(dpre, g["head.0.bias"])
+        dU = ops.neck_conv3x3(dpre, P["head.t"], None, dt, act=L.ACT_NONE)              # dgrad of model.py:103-108
+        for i, (U, xin) in ((1, (ctx["U1"], ctx["U0"])), (0, (ctx["U0"], ctx["xb"]))):   # model.py:39-40
+            dconv = ops.ps_prelu_bwd(U, dU, p[f"upsampling.{i}.relu.weight"], g[f"upsampling.{i}.relu.weight"])
+            ops.conv3x3_wgrad(xin, dconv, g[f"upsampling.{i}.conv.weight"], ps_perm=True)
+            ops.bias_grad(dconv, g[f"upsampling.{i}.conv.bias"], ps_perm=True)
+            dU = ops.conv3x3_gen(dconv, P[f"up{i}.t"], 64, mode=1)
+        dxb = dU
+        drawb = ops.instnorm_bwd(ctx["rawb"], ctx["stb"], dxb)                          # model.py:94
+        ops.conv3x3_wgrad(ctx["x_last"], drawb, g["bottleneck.0.weight"])
+        dcur = ops.conv3x3_c64_bias_act(drawb, P["bottleneck.0.weight.t"], None)
+        for i in reversed(range(self.L)):                                               # model.py:67-69
+            xin, raw1, st1, y1, raw2, st2 = ctx["blocks"][i]
+            draw2 = ops.instnorm_bwd(raw2, st2, dcur)
+            ops.conv3x3_wgrad(y1, draw2, g[f"stem.{i}.conv2.weight"])
+            dy1 = ops.conv3x3_c64_bias_act(draw2, P[f"stem.{i}.conv2.weight.t"], None)
+            draw1 = ops.instnorm_bwd(raw1, st1, dy1, act=L.ACT_PRELU, alpha=p[f"stem.{i}.relu1.weight"],
+                                     dalpha=g[f"stem.{i}.relu1.weight"])
+            ops.conv3x3_wgrad(xin, draw1, g[f"stem.{i}.conv1.weight"])
+            din = ops.conv3x3_c64_bias_act(draw1, P[f"stem.{i}.conv1.weight.t"], None)
+            dcur = ops.add(din, dcur)                                                   # + skip (model.py:69)
+        da0 = ops.add(dcur, dxb)                                                        # + long skip (model.py:115)
+        dv = ops.act_bwd(ctx["a0"], da0, L.ACT_PRELU, alpha=p["neck.1.weight"], dalpha=g["neck.1.weight"])
+        ops.wgrad_c3(ctx["lr"], dv, g["neck.0.weight"], flip=False, layout=2)           # model.py:76
+        ops.bias_grad(dv, g["neck.0.bias"])
+
+
+# ====================================================================================== Discriminator
+class DiscriminatorNet:
+    """model.py:139-193 forward (saving activations) and backward."""
+
+    def __init__(self, module, fp: FlatParams, dtype: torch.dtype):
+        self.m, self.fp, self.dt = module, fp, dtype
+        F_ = module.n_filters
+        self.widths = [(F_, F_), (F_, 2 * F_), (2 * F_, 2 * F_), (2 * F_, 4 * F_), (4 * F_, 4 * F_), (4 * F_, 8 * F_), (8 * F_, 8 * F_)]
+        self._packed_version = -1
+        self.P: Dict[str, torch.Tensor] = {}
+
+    def pack(self, need_bwd: bool):
+        if self._packed_version == self.fp.version and (not need_bwd or "bwd" in self.P):
+            return
+        p, P, dt = self.fp.p, {}, self.dt
+        for i in range(7):
+            w = p[f"stem.{i}.conv.weight"]
+            P[f"w{i}"], _ = ops.pack_conv3x3(w, None, dt)
+            if need_bwd:
+                P[f"t{i}"] = ops.pack_conv3x3_t(w, dt)
+        if need_bwd:
+            P["neck.t"] = ops.pack_conv3x3_t(p["neck.0.weight"], dt, flip=True, row_pad=16)   # 64 -> 3 image gradient
+            P["bwd"] = torch.empty(0)
+        self.P, self._packed_version = P, self.fp.version
+
+    def forward(self, img: torch.Tensor, save: bool):
+        self.pack(need_bwd=save)
+        p, P, dt = self.fp.p, self.P, self.dt
+        d0 = ops.neck_conv3x3(img, p["neck.0.weight"], p["neck.0.bias"], dt, act=L.ACT_LRELU, slope=0.2)
+        cur, layers = d0, []
+        for i, s in enumerate(D_STRIDES):
+            cout = self.widths[i][1]
+            xin = ops.parity_layout(cur, True) if s == 2 else cur
+            raw, st = ops.conv3x3_gen(xin, P[f"w{i}"], cout, stride=s, epilogue=L.EPI_RAW_STATS)
+            act = ops.instnorm_apply(raw, st, act=L.ACT_LRELU, slope=0.01)
+            if save:
+                layers.append((xin, raw, st))
+            cur = act
+        z = ops.conv1x1_to1_fwd(cur, p["stem.7.weight"].view(-1), p["stem.7.bias"])
+        ctx = dict(img=img, d0=d0, layers=layers, act6=cur) if save else None
+        return z, ctx
+
+    def backward(self, ctx, dz: torch.Tensor, wgrad: bool, d_img: Optional[torch.Tensor]):
+        """dz fp32 [N,6,6].  wgrad: accumulate parameter gradients (D step).  d_img: fp32 NCHW image-gradient
+        accumulator (G step; the wasted D weight gradients of trainer.py:195 are skipped - never consumed)."""
+        p, g, P = self.fp.p, self.fp.g, self.P
+        dcur = ops.conv1x1_to1_bwd(ctx["act6"], p["stem.7.weight"].view(-1), dz,
+                                   g["stem.7.weight"].view(-1) if wgrad else None, g["stem.7.bias"] if wgrad else None)
+        for i in reversed(range(7)):
+            xin, raw, st = ctx["layers"][i]
+            s = D_STRIDES[i]
+            draw = ops.instnorm_bwd(raw, st, dcur, act=L.ACT_LRELU, slope=0.01)
+            if wgrad:
+                ops.conv3x3_wgrad(xin, draw, g[f"stem.{i}.conv.weight"], stride=s)
+            if i == 0 and not (wgrad or d_img is not None):
+                break
+            dx = ops.conv3x3_gen(draw, P[f"t{i}"], self.widths[i][0], stride=s, mode=1)
+            dcur = ops.parity_layout(dx, False) if s == 2 else dx
+        dv = ops.act_bwd(ctx["d0"], dcur, L.ACT_LRELU, slope=0.2)
+        if wgrad:
+            ops.wgrad_c3(ctx["img"], dv, g["neck.0.weight"], flip=False, layout=2)
+            ops.bias_grad(dv, g["neck.0.bias"])
+        if d_img is not None:
+            ops.conv3x3_c64_head(dv, P["neck.t"], None, out_u8=3, out=d_img)
+
+
+# ====================================================================================== VGG19[:34]
+class VGGNet:
+    """model.py:5-23: renorm + vgg19.features[:34] (frozen).  forward + data gradient only."""
+
+    def __init__(self, module, dtype: torch.dtype):
+        self.m, self.dt = module, dtype
+        self.idx = vgg_conv_indices()
+        self.P: Dict[str, torch.Tensor] = {}
+        self._packed = False
+
+    def pack(self, need_bwd: bool):
+        if self._packed and (not need_bwd or "bwd" in self.P):
+            return
+        sd = {k: v for k, v in self.m.state_dict().items()}
+        P, dt = self.P, self.dt
+        for j, i in enumerate(self.idx):
+            w, b = sd[f"vgg.{i}.weight"], sd[f"vgg.{i}.bias"]
+            if j == 0:
+                P["w0"], P["b0"] = w.float().contiguous(), b.float().contiguous()
+                if need_bwd:
+                    scale = (0.5 / sd["std"].view(-1)).float().contiguous()          # d/dx of ((x+1)/2 - mean)/std
+                    P["t0"] = ops.pack_conv3x3_t(w, dt, flip=True, row_pad=16, row_scale=scale)
+            else:
+                if f"w{j}" not in P:
+                    P[f"w{j}"], P[f"b{j}"] = ops.pack_conv3x3(w, b, dt)
+                if need_bwd:
+                    P[f"t{j}"] = ops.pack_conv3x3_t(w, dt)
+        if need_bwd:
+            P["bwd"] = torch.empty(0)
+        self._packed = True
+
+    def forward(self, img: torch.Tensor, save: bool):
+        self.pack(need_bwd=save)
+        P, dt = self.P, self.dt
+        acts, j = [], 0
+        cur = None
+        for v in VGG_PLAN:
+            if v == "M":
+                pooled = ops.maxpool2(cur)
+                if save:
+                    acts[-1] = (acts[-1][0], True)
+                cur = pooled
+            else:
+                if j == 0:
+                    cur = ops.neck_conv3x3(img, P["w0"], P["b0"], dt, act=L.ACT_RELU, vgg_norm=True)
+                else:
+                    cur = ops.conv3x3_gen(cur, P[f"w{j}"], v, bias=P[f"b{j}"], act=L.ACT_RELU)
+                if save:
+                    acts.append((cur, False))
+                j += 1
+        return cur, (dict(acts=acts) if save else None)
+
+    def backward(self, ctx, dfeat: torch.Tensor, d_img: torch.Tensor):
+        """dfeat: gradient w.r.t. relu5_3 features (NHWC dtype); accumulates the image gradient into d_img (fp32 NCHW)."""
+        P = self.P
+        acts = ctx["acts"]
+        widths = [v for v in VGG_PLAN if v != "M"]
+        dcur = dfeat
+        for j in reversed(range(len(acts))):
+            a, pooled = acts[j]
+            da = ops.maxpool2_relu_bwd(a, dcur) if pooled else ops.relu_bwd(a, dcur)
+            if j == 0:
+                ops.conv3x3_c64_head(da, P["t0"], None, out_u8=3, out=d_img)
+            else:
+                dcur = ops.conv3x3_gen(da, P[f"t{j}"], widths[j - 1], mode=1)
+
+
+# ====================================================================================== GAN step
+class GANEngine:
+    """One iteration of trainer.py:168-196 (`train_step`) and of the pre-training loop (:104-111)."""
+
+    def __init__(self, generator, discriminator, vgg, lr_g: float, lr_d: float, dtype: torch.dtype = torch.bfloat16,
+                 loss_scale: Optional[float] = None, process_group=None):
+        self.dt = dtype
+        self.gp, self.dp = FlatParams(generator), FlatParams(discriminator)
+        self.G = GeneratorNet(generator, self.gp, dtype)
+        self.D = DiscriminatorNet(discriminator, self.dp, dtype)
+        self.V = VGGNet(vgg, dtype)
+        self.lr_g, self.lr_d = lr_g, lr_d
+        # fp16 gradients (1/numel-scaled losses) would underflow: static loss scale; bf16 needs none
+        self.S = float(loss_scale) if loss_scale is not None else (4096.0 if dtype == torch.float16 else 1.0)
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+
+    def _allreduce(self, flat_grad: torch.Tensor):
+        if self.world > 1:
+            torch.distributed.all_reduce(flat_grad, group=self.pg)     # NCCL sum over NVLink; 1/world is folded into AdamW
+
+    def train_step(self, lr_img: torch.Tensor, hr_img: torch.Tensor, noise: Dict[str, torch.Tensor]):
+        """lr_img [B,3,h,w], hr_img [B,3,4h,4w] fp32 NCHW in [-1,1] (this rank's shard);
+        noise = {"d_real","d_fake","g_real"}: uniform [0,1) tensors shaped like D's output (trainer.py:175,176,187)."""
+        S, dev = self.S, lr_img.device
+        lr_img, hr_img = lr_img.contiguous().float(), hr_img.contiguous().float()
+        B = lr_img.shape[0]
+        n_real = noise["d_real"].reshape(B, -1).contiguous().float()
+        n_fake = noise["d_fake"].reshape(B, -1).contiguous().float()
+        n_g = noise["g_real"].reshape(B, -1).contiguous().float()
+        losses = torch.zeros(4, dtype=torch.float32, device=dev)       # loss_real, loss_fake, adv (unscaled bce), content sum
+
+        # ---------------- discriminator step (trainer.py:171-181)
+        self.dp.zero_grad()
+        sr, _ = self.G.forward(lr_img, save=False)                      # :173 (.detach())
+        z_real, ctx_r = self.D.forward(hr_img, save=True)               # :172
+        z_fake, ctx_f = self.D.forward(sr, save=True)                   # :174
+        dz_r, dz_f = torch.empty_like(z_real), torch.empty_like(z_fake)
+        ops.bce_logits(z_real, n_real, 0.3, 0.8, losses[0:1], dz_r, grad_scale=0.5 * S)      # :175,177,179
+        ops.bce_logits(z_fake, n_fake, 0.3, 0.0, losses[1:2], dz_f, grad_scale=0.5 * S)      # :176,178,179
+        self.D.backward(ctx_r, dz_r, wgrad=True, d_img=None)            # :180
+        self.D.backward(ctx_f, dz_f, wgrad=True, d_img=None)
+        del ctx_r, ctx_f
+        self._allreduce(self.dp.grad)
+        self.dp.adamw_step(self.lr_d, grad_scale=1.0 / (S * self.world))   # :181
+
+        # ---------------- generator step (trainer.py:184-196)
+        self.gp.zero_grad()
+        sr, ctx_g = self.G.forward(lr_img, save=True)                   # :185
+        z, ctx_d = self.D.forward(sr, save=True)                        # :186 (updated D)
+        dz = torch.empty_like(z)
+        ops.bce_logits(z, n_g, 0.3, 0.7, losses[2:3], dz, grad_scale=0.5 * 0.1 * S)          # :187-188,194
+        fake_f, ctx_v = self.V.forward(sr, save=True)                   # :190
+        real_f, _ = self.V.forward(hr_img, save=False)                  # :191
+        dfeat = torch.empty_like(fake_f)
+        ops.smooth_l1(fake_f, real_f, losses[3:4], dfeat, grad_scale=0.5 * S / fake_f.numel())   # :192,194
+        d_sr = torch.zeros_like(sr)
+        self.V.backward(ctx_v, dfeat, d_sr)                             # :195
+        self.D.backward(ctx_d, dz, wgrad=False, d_img=d_sr)
+        self.G.backward(ctx_g, d_sr)
+        self._allreduce(self.gp.grad)
+        self.gp.adamw_step(self.lr_g, grad_scale=1.0 / (S * self.world))   # :196
+        self.G.m._packed_key = None                                        # the module's inference cache is stale now
+        nfeat = float(fake_f.numel())
+        return dict(loss_real=losses[0], loss_fake=losses[1], adv_loss=0.1 * losses[2], content_loss=losses[3] / nfeat,
+                    sr=sr)
+
+    def pretrain_step(self, lr_img: torch.Tensor, hr_img: torch.Tensor):
+        """trainer.py:104-111: generator-only SmoothL1 warm-up."""
+        S = self.S
+        lr_img, hr_img = lr_img.contiguous().float(), hr_img.contiguous().float()
+        self.gp.zero_grad()
+        sr, ctx = self.G.forward(lr_img, save=True)
+        loss = torch.zeros(1, dtype=torch.float32, device=lr_img.device)
+        d_sr = torch.empty_like(sr)
+        ops.smooth_l1(sr, hr_img, loss, d_sr, grad_scale=S / sr.numel())
+        self.G.backward(ctx, d_sr)
+        self._allreduce(self.gp.grad)
+        self.gp.adamw_step(self.lr_g, grad_scale=1.0 / (S * self.world))
+        self.G.m._packed_key = None
+        return dict(loss=loss[0] / float(sr.numel()), sr=sr)

@@ -223,3 +223,80 @@ class Generator(torch.nn.Module):
         if out is None:
             out = torch.empty((N, 4 * H, 4 * W, 3), dtype=torch.uint8, device=img.device)
         return self._run(img, out, N, H, W, 1, 1)
+
+
+class Discriminator(torch.nn.Module):
+    """Reference model.py:139-193 on B200 kernels: neck conv + LeakyReLU(0.2), seven SimpleBlocks
+    (strides 2,1,2,1,2,1,2; widths F,2F,2F,4F,4F,8F,8F), 1x1 conv -> patch-logit map [N,1,H/16,W/16]."""
+
+    def __init__(self, config, compute_dtype: Optional[torch.dtype] = None):
+        super().__init__()
+        self.config = config
+        self.n_filters = F_ = int(config.n_filters)
+        self.neck = torch.nn.Sequential(_Conv(3, F_, bias=True), _Empty())
+        widths = [(F_, F_, 2), (F_, 2 * F_, 1), (2 * F_, 2 * F_, 2), (2 * F_, 4 * F_, 1), (4 * F_, 4 * F_, 2),
+                  (4 * F_, 8 * F_, 1), (8 * F_, 8 * F_, 2)]
+        self.stem = torch.nn.Sequential(*[SimpleBlock(ci, co, s) for ci, co, s in widths], _Conv(8 * F_, 1, k=1, bias=True))
+        self.compute_dtype = compute_dtype or _default_dtype()
+        self._net = None
+
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        return super().load_state_dict(_strip_prefix(state_dict), strict=strict, assign=assign)
+
+    def _engine(self):
+        from .engine import DiscriminatorNet, FlatParams
+        fp = getattr(self, "_fsr_flat", None)
+        if fp is None or not fp.aliases(self):               # first use, or .to(device) re-allocated the parameters
+            if self.n_filters != 64:
+                raise RuntimeError("this build of libfsr_b200 supports discriminator.n_filters == 64 only")
+            fp = FlatParams(self, with_optimizer=False)
+            self._net = None
+        if self._net is None or self._net.fp is not fp:
+            self._net = DiscriminatorNet(self, fp, self.compute_dtype)
+        return self._net
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        Generator._require_cuda(x)
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and x.requires_grad:
+            raise RuntimeError("autograd through fast_srgan_b200 modules is not supported: use Trainer.train_step "
+                               "(hand-written backward kernels, trainer.py:168-196)")
+        net = self._engine()
+        net.fp.version += 1            # parameters may have been changed by the caller (load_state_dict / optimizer)
+        z, _ = net.forward(x.contiguous().float(), save=False)
+        return z.unsqueeze(1)
+
+
+class VGG19(torch.nn.Module):
+    """Reference model.py:5-23: frozen vgg19.features[:34] (-> relu5_3) behind the [-1,1] -> ImageNet renorm.
+    ImageNet weights are loaded with load_state_dict (keys vgg.{idx}.weight/bias); there is no download here."""
+
+    def __init__(self, compute_dtype: Optional[torch.dtype] = None):
+        super().__init__()
+        from .engine import VGG_PLAN, vgg_conv_indices
+        mods: Dict[str, torch.nn.Module] = {}
+        cin = 3
+        for idx, cout in zip(vgg_conv_indices(), [v for v in VGG_PLAN if v != "M"]):
+            conv = _Conv(cin, cout, bias=True)
+            torch.nn.init.kaiming_normal_(conv.weight, mode="fan_out", nonlinearity="relu")   # torchvision's VGG init
+            torch.nn.init.zeros_(conv.bias)
+            mods[str(idx)] = conv
+            cin = cout
+        self.vgg = torch.nn.ModuleDict(mods)
+        for p in self.parameters():
+            p.requires_grad = False
+        self.register_buffer("mean", torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1))
+        self.register_buffer("std", torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1))
+        self.compute_dtype = compute_dtype or _default_dtype()
+        self._net = None
+
+    def _engine(self):
+        from .engine import VGGNet
+        if self._net is None:
+            self._net = VGGNet(self, self.compute_dtype)
+        return self._net
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        Generator._require_cuda(x)
+        feat, _ = self._engine().forward(x.contiguous().float(), save=False)
+        from . import ops
+        return ops.nhwc_to_nchw(feat)

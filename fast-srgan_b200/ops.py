@@ -69,12 +69,15 @@ def conv3x3_c64_ps_prelu(x, w_packed, bias_packed, alpha):
     return out
 
 
-def conv3x3_c64_head(x, w_packed, bias_packed, out_u8: bool = False):
-    """Generator.head (model.py:102-110): x [N,H,W,64] -> fp32 NCHW [N,3,H,W] or uint8 NHWC."""
+def conv3x3_c64_head(x, w_packed, bias_packed, out_u8=False, out=None):
+    """Generator.head (model.py:102-110): x [N,H,W,64] -> fp32 NCHW [N,3,H,W] or uint8 NHWC.
+    out_u8: 0/False tanh->fp32, 1/True tanh->uint8, 2 linear fp32 store, 3 linear fp32 accumulate into `out`."""
     _cuda(x, w_packed, bias_packed)
     N, H, W, C = x.shape
     assert C == 64 and w_packed.shape[1] == 16 and x.is_contiguous()
-    if out_u8:
+    if out is not None:
+        pass
+    elif int(out_u8) == 1:
         out = torch.empty((N, H, W, 3), dtype=torch.uint8, device=x.device)
     else:
         out = torch.empty((N, 3, H, W), dtype=torch.float32, device=x.device)
@@ -144,14 +147,18 @@ def nhwc_to_nchw(x: torch.Tensor):
 
 
 # ============================================================ training-step kernels (trainer.py:168-196)
-def pack_conv3x3_t(weight: torch.Tensor, dtype: torch.dtype, ps_perm: bool = False) -> torch.Tensor:
-    """dgrad pack: OIHW fp32 -> [9][cin][cout(perm)] (rows = input channel, K = output channel)."""
-    _cuda(weight)
+def pack_conv3x3_t(weight: torch.Tensor, dtype: torch.dtype, ps_perm: bool = False, flip: bool = False,
+                   row_pad: Optional[int] = None, row_scale: Optional[torch.Tensor] = None, out=None) -> torch.Tensor:
+    """dgrad pack: OIHW fp32 -> [9][cin (pad)][cout(perm)] (rows = input channel, K = output channel)."""
+    _cuda(weight, row_scale)
     cout, cin = weight.shape[0], weight.shape[1]
-    w = weight.detach().float().contiguous()
-    wp = torch.empty((9, cin, cout), dtype=dtype, device=w.device)
-    L.check(L.load().fsr_pack_conv3x3_weight_t(w.data_ptr(), wp.data_ptr(), cout, cin, int(ps_perm), L.dtype_code(dtype),
-                                               L.stream_ptr(w.device)), "pack_t")
+    row_pad = row_pad or cin
+    w = weight.detach()
+    if w.dtype != torch.float32 or not w.is_contiguous():
+        w = w.float().contiguous()
+    wp = out if out is not None else torch.empty((9, row_pad, cout), dtype=dtype, device=w.device)
+    L.check(L.load().fsr_pack_conv3x3_weight_t(w.data_ptr(), wp.data_ptr(), cout, cin, int(ps_perm), int(flip), row_pad,
+                                               L.ptr(row_scale), L.dtype_code(dtype), L.stream_ptr(w.device)), "pack_t")
     return wp
 
 
@@ -313,19 +320,19 @@ def tanh_bwd(y, dy):
     return dpre
 
 
-def wgrad_c3(img, act, out, flip=False):
-    """out fp32 [3*9][C64] += sum img[n,c3,y+dy,x+dx] * act[n,y,x,c]."""
+def wgrad_c3(img, act, out, flip=False, layout=0):
+    """out fp32 += sum img[n,c3,y+dy,x+dx] * act[n,y,x,c]; layout 0 [27][C], 1 OIHW [3][C][3][3], 2 OIHW [C][3][3][3]."""
     _cuda(img, act, out)
     N, H, W, C = act.shape
-    L.check(L.load().fsr_wgrad_c3(img.data_ptr(), act.data_ptr(), out.data_ptr(), N, H, W, C, int(flip), L.dtype_code(act.dtype),
+    L.check(L.load().fsr_wgrad_c3(img.data_ptr(), act.data_ptr(), out.data_ptr(), N, H, W, C, int(flip), layout, L.dtype_code(act.dtype),
                                   L.stream_ptr(act.device)), "wgrad c3")
     return out
 
 
-def bias_grad(g, db):
+def bias_grad(g, db, ps_perm=False):
     _cuda(g, db)
     C = g.shape[-1]
-    L.check(L.load().fsr_bias_grad(g.data_ptr(), db.data_ptr(), g.numel() // C, C, L.dtype_code(g.dtype), L.stream_ptr(g.device)), "bias grad")
+    L.check(L.load().fsr_bias_grad(g.data_ptr(), db.data_ptr(), g.numel() // C, C, int(ps_perm), L.dtype_code(g.dtype), L.stream_ptr(g.device)), "bias grad")
     return db
 
 

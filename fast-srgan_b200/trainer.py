@@ -1,0 +1,89 @@
+"""Mirror of the reference's trainer.py `Trainer` on the B200 engine.
+
+`Trainer(config)` builds Generator / Discriminator / VGG19 like trainer.py:15-51 and exposes
+  train_step(lr, hr, noise=None)  - one iteration of the GAN loop body trainer.py:168-196
+  pretrain_step(lr, hr)           - one iteration of trainer.py:104-111
+  pretrain(...) / train(...)      - the loops of trainer.py:89-141 / :158-233 over a dataloader
+  save_checkpoints(step)          - the four files of trainer.py:143-156
+TensorBoard / torchmetrics logging (trainer.py:17,46-78,198-233) is observability, not compute: scalars
+are returned to the caller instead (out of scope).
+Multi-GPU: construct under torchrun after torch.distributed.init_process_group("nccl"); each rank feeds its
+own shard of the mini-batch, gradients are summed with one NCCL all-reduce per network per step.
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, Optional
+
+import torch
+
+from .engine import GANEngine
+from .model import VGG19, Discriminator, Generator
+
+
+class Trainer:
+    def __init__(self, config, compute_dtype: Optional[torch.dtype] = None, vgg_state_dict=None):
+        self.config = config
+        dev = torch.device(config.training.device if str(config.training.device).startswith("cuda") else "cuda")
+        if not torch.cuda.is_available():
+            raise RuntimeError("fast_srgan_b200.Trainer needs a CUDA (sm_100a) device - there is no CPU fallback")
+        dt = compute_dtype or (torch.float16 if os.environ.get("FSR_TRAIN_DTYPE", "bf16") == "fp16" else torch.bfloat16)
+        self.generator = Generator(config=config.generator, compute_dtype=dt).to(dev)
+        self.discriminator = Discriminator(config=config.discriminator, compute_dtype=dt).to(dev)
+        self.perceptual_network = VGG19(compute_dtype=dt).to(dev)      # trainer.py:22 (weights: load_state_dict)
+        if vgg_state_dict is not None:
+            self.perceptual_network.load_state_dict(vgg_state_dict)
+        self.perceptual_network.eval()
+        self.device = dev
+        self._dtype = dt
+        self._engine: Optional[GANEngine] = None
+        self._noise_gen = torch.Generator(device=dev)
+        self._noise_gen.manual_seed(int(getattr(getattr(config, "experiment", None), "seed", 0) or 0))
+
+    @property
+    def engine(self) -> GANEngine:
+        """Built lazily so that load_state_dict() on the modules before the first step is honoured."""
+        if self._engine is None:
+            t = self.config.training
+            self._engine = GANEngine(self.generator, self.discriminator, self.perceptual_network,
+                                     lr_g=float(t.generator_lr), lr_d=float(t.discriminator_lr), dtype=self._dtype)
+        return self._engine
+
+    def _label_noise(self, B: int, hw) -> Dict[str, torch.Tensor]:
+        # trainer.py:175,176,187 draw torch.rand_like(y); here a per-rank CUDA generator (pass `noise` for parity runs)
+        return {k: torch.rand((B, 1) + tuple(hw), generator=self._noise_gen, device=self.device) for k in ("d_real", "d_fake", "g_real")}
+
+    def train_step(self, lr_images: torch.Tensor, hr_images: torch.Tensor, *, noise: Optional[Dict[str, torch.Tensor]] = None):
+        lr_images = lr_images.to(self.device, non_blocking=True)       # trainer.py:168-170
+        hr_images = hr_images.to(self.device, non_blocking=True)
+        if noise is None:
+            noise = self._label_noise(lr_images.shape[0], (hr_images.shape[2] // 16, hr_images.shape[3] // 16))
+        else:
+            noise = {k: v.to(self.device) for k, v in noise.items()}
+        return self.engine.train_step(lr_images, hr_images, noise)
+
+    def pretrain_step(self, lr_images: torch.Tensor, hr_images: torch.Tensor):
+        return self.engine.pretrain_step(lr_images.to(self.device, non_blocking=True), hr_images.to(self.device, non_blocking=True))
+
+    def pretrain(self, train_dataloader, val_dataloader=None):
+        last = None
+        for lr_images, hr_images in train_dataloader:                  # trainer.py:99-111
+            last = self.pretrain_step(lr_images, hr_images)
+        return last
+
+    def train(self, train_dataloader, val_dataloader=None):
+        last = None
+        for lr_images, hr_images in train_dataloader:                  # trainer.py:165-196
+            last = self.train_step(lr_images, hr_images)
+        return last
+
+    def save_checkpoints(self, step: int):
+        """trainer.py:143-156: generator / discriminator state dicts + optimizer states under runs/<name>/."""
+        save_dir = os.path.join("runs", self.config.experiment.name)
+        os.makedirs(save_dir, exist_ok=True)
+        torch.save(self.generator.state_dict(), os.path.join(save_dir, f"generator_epoch_{step}.pt"))
+        torch.save(self.discriminator.state_dict(), os.path.join(save_dir, f"discriminator_epoch_{step}.pt"))
+        e = self.engine
+        for name, fp in (("generator", e.gp), ("discriminator", e.dp)):
+            torch.save({"step": fp.step_count, "exp_avg": fp.m, "exp_avg_sq": fp.v, "names": fp.names, "offsets": fp.offsets},
+                       os.path.join(save_dir, f"{name}_optim_epoch_{step}.pt"))

@@ -55,7 +55,9 @@ int fsr_pack_conv3x3_weight(const float* w_oihw, const float* bias, void* w_pack
  *     RAW_STATS : out [N,H,W,cout] dtype, stats [N,cout,2] fp32 += (sum, sumsq)   (caller zeroes stats)
  *     BIAS_ACT  : out [N,H,W,cout] dtype = act(conv + bias)
  *     PS_PRELU  : cout = 256: out [N,2H,2W,64] dtype = PReLU(PixelShuffle2(conv + bias)); alpha = device ptr
- *     HEAD_TANH : cout_pad = 16 (3 real): out fp32 [N,3,H,W] (out_u8=0) or uint8 [N,H,W,3] (out_u8=1)
+ *     HEAD_TANH : cout_pad = 16 (3 real): out fp32 [N,3,H,W] (out_u8=0) or uint8 [N,H,W,3] (out_u8=1);
+ *                 out_u8=2|3: no tanh, fp32 NCHW store | accumulate (the 64->3 data gradients of the
+ *                 3-channel first layers: VGG conv1_1, Discriminator.neck)
  */
 int fsr_conv3x3_c64(const void* x, const void* w_packed, void* out, const float* bias, float* stats,
                     const float* alpha, int N, int H, int W, int cout, int epilogue, int act, float slope,
@@ -99,9 +101,12 @@ int fsr_nhwc_to_nchw_f32(const void* in, float* out, int N, int C, int HW, int d
 /* ====================== GAN training step (trainer.py:168-196): backward, losses, optimiser ======================
  * Tensors are NHWC `dtype` unless stated; gradients of parameters are fp32 in torch's OIHW layout, ACCUMULATED (+=). */
 
-/* dgrad pack: out[tap][ci][col] = W[oc(col)][ci][tap] (rows = input channel, K = output channel); feed to
- * fsr_conv3x3_gen(mode=1) with cin := Cout_fwd, cout := Cin_fwd. */
-int fsr_pack_conv3x3_weight_t(const float* w_oihw, void* w_packed, int cout, int cin, int ps_perm, int dtype, void* stream);
+/* dgrad pack: out[tap'][ci (padded to row_pad)][col] = row_scale[ci] * W[oc(col)][ci][flip ? 8-tap' : tap']
+ * (rows = forward input channel, K = forward output channel).  flip=0 feeds fsr_conv3x3_gen(mode=1) (cin := Cout_fwd,
+ * cout := Cin_fwd); flip=1 feeds fsr_conv3x3_c64 (a data gradient IS a stride-1 conv with transposed, flipped
+ * weights).  row_scale (nullable) folds VGG19.forward's renormalisation chain rule (model.py:21-22). */
+int fsr_pack_conv3x3_weight_t(const float* w_oihw, void* w_packed, int cout, int cin, int ps_perm, int flip, int row_pad,
+                              const float* row_scale, int dtype, void* stream);
 
 /* Weight gradient of a 3x3/pad-1 conv on tcgen05 (autograd convolution_backward, weight part):
  * dw[co,ci,r,s] += sum dY[n,y,x,co] * X[n, stride*y+r-1, stride*x+s-1, ci].  H, W = X spatial size;
@@ -145,8 +150,9 @@ int fsr_ps_prelu_bwd(const void* U, const void* dU, void* dconv, int N, int H, i
 int fsr_tanh_bwd(const float* y, const float* dy, float* dpre, size_t n, void* stream);
 /* weight gradient of a 3x3 conv with a 3-channel side (necks: flip=0, img = conv input; head: flip=1, img = dpre):
  * out[(c3*9 + tap)*C64 + c64] += sum img[n,c3,y+dy,x+dx] * act[n,y,x,c64]. */
-int fsr_wgrad_c3(const float* img, const void* act, float* out, int N, int H, int W, int C64, int flip, int dtype, void* stream);
-int fsr_bias_grad(const void* g, float* db, size_t npix, int C, int dtype, void* stream);
+int fsr_wgrad_c3(const float* img, const void* act, float* out, int N, int H, int W, int C64, int flip, int layout, int dtype,
+                 void* stream);   /* layout 0: [27][C64]; 1: OIHW [3][C64][3][3] (head); 2: OIHW [C64][3][3][3] (necks) */
+int fsr_bias_grad(const void* g, float* db, size_t npix, int C, int ps_perm, int dtype, void* stream);
 int fsr_bias_grad_nchw(const float* g, float* db, int N, int C, size_t HW, void* stream);
 /* torch.optim.AdamW (trainer.py:33-38,181,196) on flat fp32 buffers; g is multiplied by grad_scale first. */
 int fsr_adamw(float* p, const float* g, float* m, float* v, size_t n, float lr, float b1, float b2, float eps, float wd,

@@ -118,6 +118,45 @@ def make_vgg19_state(seed: int = 99, width_div: int = 1) -> StateDict:
     return sd
 
 
+# --------------------------------------------------------------------------- storage-rounding emulation
+# The B200 engine stores activations / packed weights in fp16|bf16 (fp32 accumulation).  To separate "what any
+# 16-bit-storage implementation must lose" from implementation error, the oracle can emulate exactly that: with
+# `storage_rounding(dtype)` active every conv weight, conv output and activation tensor is rounded to `dtype`
+# (straight-through in backward) while all arithmetic stays in the caller's precision (fp64 in the tests).
+_STORAGE_DTYPE = None
+
+
+class _RoundSTE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, dt):
+        return x.to(dt).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, None
+
+
+class storage_rounding:
+    def __init__(self, dtype):
+        self.dtype = dtype
+
+    def __enter__(self):
+        global _STORAGE_DTYPE
+        self.prev, _STORAGE_DTYPE = _STORAGE_DTYPE, self.dtype
+
+    def __exit__(self, *a):
+        global _STORAGE_DTYPE
+        _STORAGE_DTYPE = self.prev
+
+
+def _q(t: Tensor) -> Tensor:
+    return t if _STORAGE_DTYPE is None else _RoundSTE.apply(t, _STORAGE_DTYPE)
+
+
+def _conv(x, w, b=None, stride=1, padding=1, quant_w=True):
+    return _q(F.conv2d(x, _q(w) if quant_w else w, b, stride=stride, padding=padding))
+
+
 # --------------------------------------------------------------------------- building blocks
 def instance_norm(x: Tensor, eps: float = 1e-5) -> Tensor:
     """torch.nn.InstanceNorm2d defaults: affine=False, biased variance, eps=1e-5
@@ -142,23 +181,24 @@ def pixel_shuffle2(x: Tensor) -> Tensor:
 # --------------------------------------------------------------------------- networks
 def residual_block(sd: StateDict, p: str, x: Tensor) -> Tensor:
     """reference model.py:67-69:  bn2(conv2(relu1(bn1(conv1(x))))) + x."""
-    y = prelu(instance_norm(F.conv2d(x, sd[p + "conv1.weight"], padding=1)), sd[p + "relu1.weight"])
-    return instance_norm(F.conv2d(y, sd[p + "conv2.weight"], padding=1)) + x
+    y = _q(prelu(instance_norm(_conv(x, sd[p + "conv1.weight"])), sd[p + "relu1.weight"]))
+    return _q(instance_norm(_conv(y, sd[p + "conv2.weight"])) + x)
 
 
 def generator_forward(sd: StateDict, x: Tensor, n_layers: Optional[int] = None) -> Tensor:
     """reference model.py:112-117."""
     if n_layers is None:
         n_layers = sum(1 for k in sd if k.startswith("stem.") and k.endswith("conv1.weight"))
-    residual = prelu(F.conv2d(x, sd["neck.0.weight"], sd["neck.0.bias"], padding=1), sd["neck.1.weight"])
+    # (the 3-channel neck runs on CUDA cores with fp32 weights; only its output is stored rounded)
+    residual = _q(prelu(F.conv2d(x, sd["neck.0.weight"], sd["neck.0.bias"], padding=1), sd["neck.1.weight"]))
     y = residual
     for i in range(n_layers):
         y = residual_block(sd, f"stem.{i}.", y)
-    y = instance_norm(F.conv2d(y, sd["bottleneck.0.weight"], padding=1)) + residual   # model.py:115
+    y = _q(instance_norm(_conv(y, sd["bottleneck.0.weight"])) + residual)             # model.py:115
     for i in range(2):                                                                  # model.py:39-40
-        y = F.conv2d(y, sd[f"upsampling.{i}.conv.weight"], sd[f"upsampling.{i}.conv.bias"], padding=1)
-        y = prelu(pixel_shuffle2(y), sd[f"upsampling.{i}.relu.weight"])
-    y = F.conv2d(y, sd["head.0.weight"], sd["head.0.bias"], padding=1)                  # model.py:102-110
+        y = F.conv2d(y, _q(sd[f"upsampling.{i}.conv.weight"]), sd[f"upsampling.{i}.conv.bias"], padding=1)
+        y = _q(prelu(pixel_shuffle2(y), sd[f"upsampling.{i}.relu.weight"]))             # fused epilogue: rounded once
+    y = F.conv2d(y, _q(sd["head.0.weight"]), sd["head.0.bias"], padding=1)              # model.py:102-110 (fp32 out)
     return torch.tanh(y)
 
 
@@ -167,10 +207,10 @@ D_STRIDES = (2, 1, 2, 1, 2, 1, 2)  # reference model.py:148-183
 
 def discriminator_forward(sd: StateDict, x: Tensor) -> Tensor:
     """reference model.py:191-193 (neck :143-146, SimpleBlock :135-136, 1x1 conv :184-186)."""
-    y = F.leaky_relu(F.conv2d(x, sd["neck.0.weight"], sd["neck.0.bias"], padding=1), 0.2)
+    y = _q(F.leaky_relu(F.conv2d(x, sd["neck.0.weight"], sd["neck.0.bias"], padding=1), 0.2))
     for i, s in enumerate(D_STRIDES):
-        y = F.conv2d(y, sd[f"stem.{i}.conv.weight"], stride=s, padding=1)
-        y = F.leaky_relu(instance_norm(y), 0.01)        # torch.nn.LeakyReLU() default slope
+        y = _conv(y, sd[f"stem.{i}.conv.weight"], stride=s)
+        y = _q(F.leaky_relu(instance_norm(y), 0.01))    # torch.nn.LeakyReLU() default slope
     return F.conv2d(y, sd["stem.7.weight"], sd["stem.7.bias"])
 
 
@@ -184,7 +224,7 @@ def vgg19_forward(sd: StateDict, x: Tensor) -> Tensor:
             y = F.max_pool2d(y, kernel_size=2, stride=2)
         else:
             i = next(convs)
-            y = F.relu(F.conv2d(y, sd[f"vgg.{i}.weight"], sd[f"vgg.{i}.bias"], padding=1))
+            y = _q(F.relu(F.conv2d(y, _q(sd[f"vgg.{i}.weight"]) if i > 0 else sd[f"vgg.{i}.weight"], sd[f"vgg.{i}.bias"], padding=1)))
     return y
 
 

@@ -241,6 +241,24 @@ def test_upsample_head_neck_backward_glue(dt):
     assert rel_err(db3, dy.sum((0, 2, 3))) <= 1e-4
 
 
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("mode", ["prelu", "lrelu"])
+def test_act_bwd(dt, mode):
+    from fast_srgan_b200 import ops, _lib as L
+    v = rnd((2, 64, 9, 11), 40).requires_grad_(True)
+    alpha = torch.tensor([0.3], device="cuda", requires_grad=True)
+    y = F.prelu(v, alpha) if mode == "prelu" else F.leaky_relu(v, 0.2)
+    dy = rnd((2, 64, 9, 11), 41).to(dt).float()
+    yq = y.detach().to(dt).float()
+    y.backward(dy)
+    dalpha = torch.zeros(1, device="cuda")
+    act = L.ACT_PRELU if mode == "prelu" else L.ACT_LRELU
+    dv = ops.act_bwd(nhwc(yq, dt), nhwc(dy, dt), act, slope=0.2, alpha=alpha.detach(), dalpha=dalpha)
+    assert rel_err(nchw(dv), v.grad) <= 2 * EPS[dt] + 1e-6
+    if mode == "prelu":
+        assert abs(dalpha.item() - alpha.grad.item()) <= 4 * EPS[dt] * dy.abs().mul(yq.abs()).sum().item() / 0.3 + 1e-4
+
+
 def test_adamw_matches_torch():
     from fast_srgan_b200 import ops
     p = rnd((1000,), 30)

@@ -1,0 +1,145 @@
+"""GPU parity of Discriminator / VGG19 forward and of one GAN train step (trainer.py:168-196) against the
+CPU oracle (and, through it, the committed fp64 run of the unmodified reference).
+
+Gradient tolerances: SURVEY/oracle measurements show the reference's OWN fp32 gradients differ from its fp64
+run by up to ~1.5e-2 (max-abs / abs-max) per tensor, because InstanceNorm over 6x6..12x12 planes is
+ill-conditioned.  The engine computes with bf16|fp16 operands and fp32 accumulation, so parity is asserted in
+relative L2 norm per tensor against the fp64 oracle with the bounds written below."""
+import types
+
+import pytest
+import torch
+
+import srgan_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def seeded(shape, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.rand(shape, generator=g) * 2 - 1
+
+
+def ns(**k):
+    return types.SimpleNamespace(**k)
+
+
+@pytest.mark.parametrize("dt,tol", [(torch.float16, 4e-3), (torch.bfloat16, 3e-2)])
+def test_discriminator_forward(golden, dt, tol):
+    from fast_srgan_b200.model import Discriminator
+    sd = O.make_discriminator_state(64, seed=4321)
+    d = Discriminator(ns(n_filters=64), compute_dtype=dt)
+    d.load_state_dict(sd)
+    d = d.cuda()
+    x = seeded((2, 3, 96, 96), 11)
+    with torch.no_grad():
+        y = d(x.cuda()).cpu()
+    err = (y.numpy() - golden["d64_y"]).__abs__().max()
+    print(f"discriminator {dt}: max-abs vs reference golden {err:.3e} (|y| max {abs(golden['d64_y']).max():.3f})")
+    assert y.shape == (2, 1, 6, 6) and err <= tol
+
+
+@pytest.mark.parametrize("dt,tol", [(torch.float16, 3e-3), (torch.bfloat16, 4e-2)])
+def test_vgg_forward(golden, dt, tol):
+    from fast_srgan_b200.model import VGG19
+    sd = O.make_vgg19_state(seed=99)
+    v = VGG19(compute_dtype=dt)
+    v.load_state_dict(sd)
+    v = v.cuda()
+    x = seeded((1, 3, 32, 32), 13)
+    with torch.no_grad():
+        y = v(x.cuda()).cpu()
+    ref = golden["vgg_y"]
+    err = abs(y.numpy() - ref).max() / abs(ref).max()
+    print(f"vgg19 {dt}: rel max err vs reference golden {err:.3e}")
+    assert y.shape == ref.shape and err <= tol
+
+
+def _oracle_step(B, storage=None):
+    """fp64 oracle of one step; storage=dtype additionally rounds every stored tensor like a 16-bit engine would."""
+    import contextlib
+    c = lambda sd: {k: v.double().clone() for k, v in sd.items()}
+    og, od, ov = c(O.make_generator_state(64, 8, 1234)), c(O.make_discriminator_state(64, 4321)), c(O.make_vgg19_state(99))
+    lr_img, hr_img = seeded((B, 3, 24, 24), 21), seeded((B, 3, 96, 96), 22)
+    gn = torch.Generator().manual_seed(23)
+    noise = {k: torch.rand((B, 1, 6, 6), generator=gn) for k in ("d_real", "d_fake", "g_real")}
+    with (O.storage_rounding(storage) if storage is not None else contextlib.nullcontext()):
+        res = O.gan_step(og, od, ov, lr_img.double(), hr_img.double(), {k: v.double() for k, v in noise.items()},
+                         O.AdamWState(og, 1e-4), O.AdamWState(od, 1e-4))
+    return res, og, od, lr_img, hr_img, noise
+
+
+def _run_step(dt, B=2):
+    from fast_srgan_b200.trainer import Trainer
+    cfg = ns(experiment=ns(name="t", seed=0), generator=ns(n_filters=64, n_layers=8), discriminator=ns(n_filters=64, n_layers=7),
+             training=ns(device="cuda", generator_lr=1e-4, discriminator_lr=1e-4))
+    tr = Trainer(cfg, compute_dtype=dt)
+    tr.generator.load_state_dict(O.make_generator_state(64, 8, 1234))
+    tr.discriminator.load_state_dict(O.make_discriminator_state(64, 4321))
+    tr.perceptual_network.load_state_dict(O.make_vgg19_state(99))
+    res, og, od, lr_img, hr_img, noise = _oracle_step(B)
+    out = tr.train_step(lr_img, hr_img, noise=noise)
+    torch.cuda.synchronize()
+    return tr, out, res, og, od
+
+
+@pytest.mark.parametrize("dt,ltol", [(torch.bfloat16, 5e-3), (torch.float16, 1e-3)])
+def test_gan_train_step_vs_fp64_oracle(golden, dt, ltol):
+    """Losses: tight.  Gradients: these are ill-conditioned (InstanceNorm over 6x6..24x24 planes followed by
+    kinked activations): ROUNDING THE STORED ACTIVATIONS ALONE - emulated in the fp64 oracle with
+    storage_rounding(dtype), no other change - already moves them by ~10 % (fp16) / ~30 % (bf16) in relative L2
+    (the reference's own fp32 run is ~1.5e-2 from its fp64 run).  The engine must be as good as that emulation:
+        err_engine(tensor) <= 1.6 * err_emulation(tensor) + 0.03     (both measured against the fp64 oracle)."""
+    tr, out, res, og, od = _run_step(dt)
+    for k in ("loss_real", "loss_fake", "adv_loss", "content_loss"):
+        ref = float(golden[f"step64_{k}"])         # the reference's own fp64 run (oracle == reference to 1e-9)
+        got = out[k].item()
+        print(f"{k}: engine {got:.6f} reference-fp64 {ref:.6f}")
+        assert abs(got - ref) <= ltol * max(1.0, abs(ref))
+    emu, _, _, _, _, _ = _oracle_step(2, storage=dt)
+    e = tr.engine
+    rel = lambda a, b: ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+    for name, fp, key in (("D", e.dp, "d_grads"), ("G", e.gp, "g_grads")):
+        for k, gref in res[key].items():
+            got = fp.g[k].double().cpu() / e.S
+            err, err_emu = rel(got, gref), rel(emu[key][k], gref)
+            cos = (got.flatten() @ gref.flatten() / (got.norm() * gref.norm()).clamp_min(1e-30)).item()
+            print(f"{name} grad {k:28s} engine {err:.3e}  16-bit-storage emulation {err_emu:.3e}  cos {cos:.4f}")
+            assert err <= 1.6 * err_emu + 0.03, (name, k, err, err_emu)
+            if gref.numel() > 1:
+                assert cos >= (0.85 if dt == torch.bfloat16 else 0.95), (name, k, cos)
+    # parameters after AdamW: the first step moves every weight by ~lr*sign(g) (m/sqrt(v) = +-1)
+    for name, fp, ref_after, sd0 in (("D", e.dp, od, O.make_discriminator_state(64, 4321)),
+                                     ("G", e.gp, og, O.make_generator_state(64, 8, 1234))):
+        for k, pref in ref_after.items():
+            got = fp.p[k].double().cpu()
+            assert (got - pref).abs().max().item() <= 2.05e-4           # |delta| <= 2*lr (+wd) even if a sign flips
+            upd_ref, upd_got = pref - sd0[k].double(), got - sd0[k].double()
+            agree = (torch.sign(upd_ref) == torch.sign(upd_got)).double().mean().item()
+            if pref.numel() > 1:
+                assert agree >= 0.8, (name, k, agree)
+
+
+def test_train_step_updates_inference_weights():
+    """After a step the Generator module (inference path) must see the updated parameters."""
+    tr, out, res, og, od = _run_step(torch.bfloat16)
+    x = seeded((1, 3, 24, 24), 5)
+    with torch.no_grad():
+        y = tr.generator(x.cuda()).cpu()
+        ref = O.generator_forward({k: v.float() for k, v in og.items()}, x)
+    assert (y - ref).abs().max().item() <= 3e-2
+
+
+def test_pretrain_step_runs_and_reduces_loss():
+    from fast_srgan_b200.trainer import Trainer
+    cfg = ns(experiment=ns(name="t", seed=0), generator=ns(n_filters=64, n_layers=2), discriminator=ns(n_filters=64, n_layers=7),
+             training=ns(device="cuda", generator_lr=1e-3, discriminator_lr=1e-4))
+    tr = Trainer(cfg, compute_dtype=torch.bfloat16)
+    tr.generator.load_state_dict(O.make_generator_state(64, 2, 7))
+    lr_img = seeded((4, 3, 16, 16), 1)
+    hr_img = torch.nn.functional.interpolate(lr_img, scale_factor=4, mode="bilinear")
+    l0 = tr.pretrain_step(lr_img, hr_img)["loss"].item()
+    for _ in range(30):
+        l1 = tr.pretrain_step(lr_img, hr_img)["loss"].item()
+    print("pretrain loss", l0, "->", l1)
+    assert l1 < l0
