@@ -318,7 +318,8 @@ class GANEngine:
 
     def _allreduce(self, flat_grad: torch.Tensor):
         if self.world > 1:
-            torch.distributed.all_reduce(flat_grad, group=self.pg)     # NCCL sum over NVLink; 1/world is folded into AdamW
+            from .distributed import allreduce_flat
+            allreduce_flat(flat_grad, self.pg)                         # NCCL sum over NVLink; 1/world is folded into AdamW
 
     def train_step(self, lr_img: torch.Tensor, hr_img: torch.Tensor, noise: Dict[str, torch.Tensor]):
         """lr_img [B,3,h,w], hr_img [B,3,4h,4w] fp32 NCHW in [-1,1] (this rank's shard);

@@ -1,0 +1,75 @@
+"""world_size-2 gloo test (CPU) of the data-parallel host logic: batch / label-noise sharding, the flat gradient
+buffer layout and the all-reduce, checked with the oracle: mean over ranks of shard gradients == full-batch gradient
+(InstanceNorm is per-sample, so batch sharding is exact - SURVEY.md 8e)."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import types
+    import srgan_oracle as O
+    from fast_srgan_b200 import distributed as D
+    from fast_srgan_b200.engine import FlatParams
+    from fast_srgan_b200.model import Discriminator
+    torch.set_num_threads(2)
+    r, _, w = D.init_from_env("gloo")
+    assert (r, w) == (rank, world)
+    B = 4
+    g = torch.Generator().manual_seed(3)
+    hr = torch.rand((B, 3, 32, 32), generator=g) * 2 - 1
+    noise = {"d_real": torch.rand((B, 1, 2, 2), generator=g)}
+    dsd = O.make_discriminator_state(64, seed=4321)
+
+    def d_grads(x, n):
+        d = {k: v.double().clone().requires_grad_(True) for k, v in dsd.items()}
+        O.bce_with_logits_mean(O.discriminator_forward(d, x.double()), (0.3 * n + 0.8).double()).backward()
+        return {k: v.grad for k, v in d.items()}
+
+    # this rank's shard -> gradients into the flat buffer the engine all-reduces
+    mod = Discriminator(types.SimpleNamespace(n_filters=64))
+    mod.load_state_dict(dsd)
+    fp = FlatParams(mod, with_optimizer=False)
+    assert fp.aliases(mod) and fp.numel >= sum(p.numel() for p in mod.parameters())
+    gl = d_grads(D.shard_batch(hr, rank, world), D.shard_noise(noise, rank, world)["d_real"])
+    for k, v in gl.items():
+        fp.g[k].copy_(v.float())
+    D.allreduce_flat(fp.grad)
+    fp.grad.mul_(1.0 / world)                      # the factor the engine folds into AdamW
+    full = d_grads(hr, noise["d_real"])
+    worst = max(((fp.g[k].double() - full[k]).norm() / full[k].norm()).item() for k in full)
+    ret[rank] = worst
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_allreduce_matches_full_batch():
+    world = 2
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    port = 29000 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    assert len(ret) == world and max(ret.values()) <= 1e-5, dict(ret)
+
+
+def test_shard_ranges():
+    sys.path.insert(0, ROOT)
+    from fast_srgan_b200 import distributed as D
+    assert [D.shard_range(256, r, 8) for r in (0, 7)] == [(0, 32), (224, 256)]
+    try:
+        D.shard_range(10, 0, 4)
+        assert False
+    except ValueError:
+        pass

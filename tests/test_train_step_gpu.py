@@ -100,14 +100,20 @@ def test_gan_train_step_vs_fp64_oracle(golden, dt, ltol):
     e = tr.engine
     rel = lambda a, b: ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
     for name, fp, key in (("D", e.dp, "d_grads"), ("G", e.gp, "g_grads")):
+        scal = max([v.abs().item() for v in res[key].values() if v.numel() == 1] + [1e-30])
         for k, gref in res[key].items():
             got = fp.g[k].double().cpu() / e.S
             err, err_emu = rel(got, gref), rel(emu[key][k], gref)
             cos = (got.flatten() @ gref.flatten() / (got.norm() * gref.norm()).clamp_min(1e-30)).item()
             print(f"{name} grad {k:28s} engine {err:.3e}  16-bit-storage emulation {err_emu:.3e}  cos {cos:.4f}")
-            assert err <= 1.6 * err_emu + 0.03, (name, k, err, err_emu)
             if gref.numel() > 1:
+                assert err <= 1.6 * err_emu + 0.03, (name, k, err, err_emu)
                 assert cos >= (0.85 if dt == torch.bfloat16 else 0.95), (name, k, cos)
+            else:
+                # single PReLU slopes: a sum with heavy cancellation - one number has no norm to average over, so
+                # bound its absolute error by the scale of this network's slope gradients
+                aerr, aemu = (got - gref).abs().item(), (emu[key][k] - gref).abs().item()
+                assert aerr <= max(3.0 * aemu, 0.1 * scal), (name, k, aerr, aemu, scal)
     # parameters after AdamW: the first step moves every weight by ~lr*sign(g) (m/sqrt(v) = +-1)
     for name, fp, ref_after, sd0 in (("D", e.dp, od, O.make_discriminator_state(64, 4321)),
                                      ("G", e.gp, og, O.make_generator_state(64, 8, 1234))):
