@@ -2,6 +2,7 @@
 #include "../../include/fsr_b200.h"
 #include "conv3x3_tc.cuh"
 #include "conv3x3_gen.cuh"
+#include "conv3x3_head.cuh"
 #include "conv3x3_wgrad.cuh"
 #include "train_kernels.cuh"
 #include "elementwise.cuh"
@@ -162,6 +163,30 @@ int launch_conv_mode(const void* x, const void* w_packed, int w_rows, const Conv
   return launch_conv<NS, EPI, T, false>(x, w_packed, w_rows, p, dtype, st);
 }
 
+// 3-output-channel conv as 1x1 GEMM + shift-add epilogue (conv3x3_head.cuh)
+template <typename T>
+int launch_head(const void* x, const void* w_packed, ConvParams p, int dtype, cudaStream_t st) {
+  auto kern = conv3x3_head_kernel<T>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    FSR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, HeadCfg::kSmemBytes));
+    attr_done = true;
+  }
+  p.tiles_x = (p.W + HeadCfg::TW - 1) / HeadCfg::TW;
+  p.tiles_y = (p.H + HeadCfg::TH - 1) / HeadCfg::TH;
+  p.num_tiles = p.N * p.tiles_x * p.tiles_y;
+  CUtensorMap tmx;
+  int rc = make_act_map(&tmx, x, p.N, p.H, p.W, 64, HeadCfg::BW, HeadCfg::BH, dtype);
+  if (rc) return rc;
+  int grid = num_sms();
+  if (grid > p.num_tiles) grid = p.num_tiles;
+  {
+    LaunchScope scope(FSR_K_CONV_HEAD, st);
+    kern<<<grid, HeadCfg::kThreads, HeadCfg::kSmemBytes, st>>>(tmx, reinterpret_cast<const T*>(w_packed), p);
+  }
+  return cuda_rc(cudaGetLastError());
+}
+
 template <typename T>
 int conv_dispatch(const void* x, const void* w_packed, void* out, const float* bias, float* stats, const float* alpha,
                   int N, int H, int W, int cout, int epilogue, int act, float slope, int out_u8, int dtype,
@@ -190,6 +215,7 @@ int conv_dispatch(const void* x, const void* w_packed, void* out, const float* b
     case FSR_EPI_HEAD_TANH: {
       if (cout != 16 || out_u8 < 0 || out_u8 > 3) return FSR_ERR_BAD_ARG;   // padded head: 3 real + 13 zero rows
       p.cout_total = 16; p.num_slices = 1;
+      if (halo_mode()) return launch_head<T>(x, w_packed, p, dtype, st);
       return launch_conv_mode<16, EPI_HEAD_TANH, T>(x, w_packed, 9 * 16, p, dtype, st);
     }
   }
@@ -753,13 +779,13 @@ int fsr_wgrad_c3(const float* img, const void* act, float* out, int N, int H, in
   if (!img || !act || !out || C64 % 64) return FSR_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t total = (size_t)N * H * W;
-  int bx = (int)((total + 4 * 64 - 1) / (4 * 64));
+  int bx = (int)((total + 255) / 256);           // >= 256 pixels per block
   if (bx > num_sms() * 4) bx = num_sms() * 4;
   if (bx < 1) bx = 1;
   dim3 grid(bx, C64 / 64);
   LaunchScope scope(FSR_K_NONE - 1, st);
-  FSR_T((wgrad_c3_kernel<__half><<<grid, 256, 0, st>>>(img, (const __half*)act, out, N, H, W, C64, flip, layout)),
-        (wgrad_c3_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(img, (const __nv_bfloat16*)act, out, N, H, W, C64, flip, layout)));
+  FSR_T((wgrad_c3_kernel<__half><<<grid, 224, 0, st>>>(img, (const __half*)act, out, N, H, W, C64, flip, layout)),
+        (wgrad_c3_kernel<__nv_bfloat16><<<grid, 224, 0, st>>>(img, (const __nv_bfloat16*)act, out, N, H, W, C64, flip, layout)));
   return cuda_rc(cudaGetLastError());
 }
 

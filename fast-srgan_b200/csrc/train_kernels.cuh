@@ -403,46 +403,49 @@ __global__ void __launch_bounds__(256) tanh_bwd_kernel(const float* __restrict__
 // the conv INPUT (neck: img = x, act = dOut) and (1-r,1-s) when it is the OUTPUT gradient (head: img = dpre,
 // act = x).  out[(c3*9 + tap)*C64 + c64] fp32 (+=).  Block = 64 threads-channels x pixel chunks.
 template <typename T>
-__global__ void __launch_bounds__(256) wgrad_c3_kernel(const float* __restrict__ img, const T* __restrict__ act,
+__global__ void __launch_bounds__(224) wgrad_c3_kernel(const float* __restrict__ img, const T* __restrict__ act,
                                                        float* __restrict__ out, int N, int H, int W, int C64, int flip,
                                                        int layout /*0: [27][C64]; 1: OIHW [3][C64][9] (head); 2: OIHW [C64][3][9] (neck)*/) {
-  // thread: channel c = threadIdx.x % 64 (+ blockIdx.y * 64), pixel lane pl = threadIdx.x / 64 (4 lanes)
-  const int c = blockIdx.y * 64 + (threadIdx.x & 63);
-  const int pl = threadIdx.x >> 6;
+  // thread = (k = c3*9 + tap, 8-channel group): one image value + one 16-B activation vector -> 8 FMAs per pixel;
+  // a block walks a contiguous pixel range and issues 8 atomics per thread at the end.
+  const int k = threadIdx.x >> 3, cg = threadIdx.x & 7;
+  if (k >= 27) return;
+  const int c3 = k / 9, r = (k % 9) / 3, s = k % 3;
+  const int dy = flip ? 1 - r : r - 1, dx = flip ? 1 - s : s - 1;
+  const int cbase = blockIdx.y * 64 + cg * 8;
   const size_t total = (size_t)N * H * W;
-  float acc[27];
+  const size_t per = (total + gridDim.x - 1) / gridDim.x;
+  const size_t p0 = (size_t)blockIdx.x * per, p1 = min(total, p0 + per);
+  float acc[8];
 #pragma unroll
-  for (int k = 0; k < 27; ++k) acc[k] = 0.f;
-  for (size_t pix = (size_t)blockIdx.x * 4 + pl; pix < total; pix += (size_t)gridDim.x * 4) {
-    const int x = (int)(pix % W);
-    const int y = (int)((pix / W) % H);
-    const int n = (int)(pix / ((size_t)W * H));
-    const float a = Cvt<T>::to_f(act[pix * C64 + c]);
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (p0 < p1) {
+    int x = (int)(p0 % W), y = (int)((p0 / W) % H), n = (int)(p0 / ((size_t)W * H));
+    for (size_t pix = p0; pix < p1; ++pix) {
+      const int yy = y + dy, xx = x + dx;
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+        const float v = __ldg(img + ((size_t)(n * 3 + c3) * H + yy) * W + xx);
+        const uint4 a = *reinterpret_cast<const uint4*>(act + pix * C64 + cbase);
+        const uint32_t au[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
-    for (int c3 = 0; c3 < 3; ++c3)
-#pragma unroll
-      for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int s = 0; s < 3; ++s) {
-          const int yy = y + (flip ? 1 - r : r - 1), xx = x + (flip ? 1 - s : s - 1);
-          const float v = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(img + ((size_t)(n * 3 + c3) * H + yy) * W + xx) : 0.f;
-          acc[c3 * 9 + r * 3 + s] = fmaf(v, a, acc[c3 * 9 + r * 3 + s]);
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = Cvt<T>::unpack2(au[j]);
+          acc[2 * j] = fmaf(v, f.x, acc[2 * j]);
+          acc[2 * j + 1] = fmaf(v, f.y, acc[2 * j + 1]);
         }
+      }
+      if (++x == W) { x = 0; if (++y == H) { y = 0; ++n; } }
+    }
   }
-  __shared__ float red[27][64];
-  for (int k = threadIdx.x; k < 27 * 64; k += blockDim.x) (&red[0][0])[k] = 0.f;
-  __syncthreads();
+  const int tap = k % 9;
 #pragma unroll
-  for (int k = 0; k < 27; ++k) atomicAdd(&red[k][threadIdx.x & 63], acc[k]);
-  __syncthreads();
-  for (int k = threadIdx.x; k < 27 * 64; k += blockDim.x) {
-    const int t27 = k / 64, c64 = blockIdx.y * 64 + (k % 64);
-    const int c3 = t27 / 9, tap = t27 % 9;
+  for (int j = 0; j < 8; ++j) {
+    const int c64 = cbase + j;
     size_t idx;
     if (layout == 1) idx = ((size_t)c3 * C64 + c64) * 9 + tap;
     else if (layout == 2) idx = ((size_t)c64 * 3 + c3) * 9 + tap;
-    else idx = (size_t)t27 * C64 + c64;
-    atomicAdd(out + idx, red[t27][k % 64]);
+    else idx = (size_t)k * C64 + c64;
+    atomicAdd(out + idx, acc[j]);
   }
 }
 
