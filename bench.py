@@ -171,6 +171,8 @@ def main():
     ap.add_argument("--dtype", default=os.environ.get("FSR_DTYPE", "fp16"), choices=["fp16", "bf16"])
     ap.add_argument("--l2-group", type=int, default=int(os.environ.get("FSR_L2_GROUP", "0")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--streams", type=int, default=int(os.environ.get("FSR_STREAMS", "1")),
+                    help="sub-batches of the forward run concurrently on internal side streams (1 = single stream)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -202,6 +204,7 @@ def main():
     gen = gen.to(dev).eval()
     gen.l2_group = args.l2_group
     lib = L.load()
+    lib.fsr_set_overlap_streams(args.streams)
 
     g = torch.Generator().manual_seed(100 + rank)
     x_dev = (torch.rand((BATCH, 3, H, W), generator=g) * 2 - 1).to(dev)
@@ -304,7 +307,9 @@ def main():
         avg = sum(up1) / len(up1)
         ach = up1_flops / (avg * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": "conv3x3_c64_kernel<128,EPI_PS_PRELU> (upsampling.1.conv, 360x640, 64->256)",
-                "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak, "traffic": None,
+                "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
+                "traffic": 4.779e9,   # dram__bytes_read+write per launch, ncu --set full (profiles/r01/ncu_full_upsample_convs.md); algorithmic 4.72e9
+                "traffic_source": "profiles/r01/ncu_full_upsample_convs.md",
                 "avg_launch_ms": avg, "launches_timed": len(up1), "flops_per_launch": up1_flops, "peak_source": peak_src}
     total_flops = gen_flops_per_frame(H, W) * BATCH
     line = {
@@ -314,7 +319,7 @@ def main():
         "config": {"workload": f"generator-only 4x SR {H}x{W}->{4*H}x{4*W}, batch {BATCH}/GPU, L={NL} F={NF} (BASELINE configs[1])",
                    "parallelism": f"{world} independent replicas (frames shard, no collective)",
                    "l2": "activations streamed per step (>5 GB) exceed the 126 MB L2; no explicit flush",
-                   "l2_group": args.l2_group},
+                   "l2_group": args.l2_group, "overlap_streams": args.streams},
         "whole_model_tflops": total_flops / (ms_step * 1e-3) / 1e12 * 1.0,
         "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": e2e_fps, "unit": UNIT, "h2d_bytes_per_step": BATCH * H * W * 3,

@@ -548,11 +548,61 @@ size_t fsr_generator_workspace_bytes(int N, int H, int W, int n_filters, int n_l
   return 4 * P + 4 * P + 16 * P + stats + 4096;
 }
 
+// Sub-batches of the forward run on internal side streams so that the HBM-bound kernels of one sub-batch
+// (InstanceNorm apply, head) overlap the tensor-bound convolutions of the other: the persistent conv CTAs
+// leave ~10 K registers and 5 KB smem per SM, enough for one elementwise block to co-reside.
+int g_overlap = -1;
+cudaStream_t g_side[4] = {nullptr, nullptr, nullptr, nullptr};
+cudaEvent_t g_fork = nullptr, g_join[4] = {nullptr, nullptr, nullptr, nullptr};
+int overlap_parts() {
+  if (g_overlap < 0) {
+    const char* e = getenv("FSR_STREAMS");
+    g_overlap = e ? atoi(e) : 1;   // measured on B200 (power-capped): 2-4 sub-batches overlap but do not shorten the step
+    if (g_overlap < 1) g_overlap = 1;
+    if (g_overlap > 4) g_overlap = 4;
+  }
+  return g_overlap;
+}
+
+int fsr_set_overlap_streams(int parts) {
+  g_overlap = parts < 1 ? 1 : (parts > 4 ? 4 : parts);
+  return FSR_OK;
+}
+
+static int generator_chain(const FsrGeneratorParams* prm, const uint8_t* xin, uint8_t* yout, uint8_t* res, uint8_t* xb,
+                           uint8_t* raw, uint8_t* yb, uint8_t* u0, uint8_t* u1, float* stats, size_t stats_per_conv,
+                           int nb, int H, int W, int in_u8, int out_u8, cudaStream_t st) {
+  const int F = 64, L = prm->n_layers, dt = prm->dtype;
+  int rc;
+  // neck (model.py:75-78)
+  if ((rc = fsr_neck_conv3x3(xin, prm->neck_w, prm->neck_b, prm->neck_alpha, res, nb, H, W, F, FSR_ACT_PRELU, 0.f, in_u8, 0, dt, st)))
+    return rc;
+  const uint8_t* cur = res;
+  for (int l = 0; l < L; ++l) {   // ResidualBlock.forward (model.py:67-69)
+    float* s1 = stats + (size_t)(2 * l) * stats_per_conv;
+    float* s2 = stats + (size_t)(2 * l + 1) * stats_per_conv;
+    if ((rc = fsr_conv3x3_c64(cur, prm->stem_w1[l], raw, nullptr, s1, nullptr, nb, H, W, F, FSR_EPI_RAW_STATS, 0, 0.f, 0, dt, st))) return rc;
+    if ((rc = fsr_instnorm_apply(raw, s1, nullptr, yb, prm->stem_alpha[l], nb, H * W, F, FSR_ACT_PRELU, 0.f, 1e-5f, dt, st))) return rc;
+    if ((rc = fsr_conv3x3_c64(yb, prm->stem_w2[l], raw, nullptr, s2, nullptr, nb, H, W, F, FSR_EPI_RAW_STATS, 0, 0.f, 0, dt, st))) return rc;
+    if ((rc = fsr_instnorm_apply(raw, s2, cur, xb, nullptr, nb, H * W, F, FSR_ACT_NONE, 0.f, 1e-5f, dt, st))) return rc;
+    cur = xb;
+  }
+  {   // bottleneck + long skip (model.py:86-95, 115)
+    float* sb = stats + (size_t)(2 * L) * stats_per_conv;
+    if ((rc = fsr_conv3x3_c64(cur, prm->bott_w, raw, nullptr, sb, nullptr, nb, H, W, F, FSR_EPI_RAW_STATS, 0, 0.f, 0, dt, st))) return rc;
+    if ((rc = fsr_instnorm_apply(raw, sb, res, xb, nullptr, nb, H * W, F, FSR_ACT_NONE, 0.f, 1e-5f, dt, st))) return rc;
+  }
+  // upsampling x2 (model.py:39-40) and head (model.py:102-110)
+  if ((rc = fsr_conv3x3_c64(xb, prm->up_w[0], u0, prm->up_b[0], nullptr, prm->up_alpha[0], nb, H, W, 256, FSR_EPI_PS_PRELU, 0, 0.f, 0, dt, st))) return rc;
+  if ((rc = fsr_conv3x3_c64(u0, prm->up_w[1], u1, prm->up_b[1], nullptr, prm->up_alpha[1], nb, 2 * H, 2 * W, 256, FSR_EPI_PS_PRELU, 0, 0.f, 0, dt, st))) return rc;
+  return fsr_conv3x3_c64(u1, prm->head_w, yout, prm->head_b, nullptr, nullptr, nb, 4 * H, 4 * W, 16, FSR_EPI_HEAD_TANH, 0, 0.f, out_u8, dt, st);
+}
+
 int fsr_generator_forward(const FsrGeneratorParams* prm, const void* x, void* y, void* workspace, size_t ws_bytes,
                           int N, int H, int W, int in_u8, int out_u8, int group, void* stream) {
   if (!prm || !x || !y || !workspace) return FSR_ERR_BAD_ARG;
   if (prm->n_filters != 64 || prm->n_layers < 0 || prm->n_layers > FSR_MAX_LAYERS) return FSR_ERR_BAD_SHAPE;
-  const int F = 64, L = prm->n_layers, dt = prm->dtype;
+  const int F = 64, L = prm->n_layers;
   if (ws_bytes < fsr_generator_workspace_bytes(N, H, W, F, L)) return FSR_ERR_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t P = align_up((size_t)N * H * W * F * 2, 1024);
@@ -567,41 +617,43 @@ int fsr_generator_forward(const FsrGeneratorParams* prm, const void* x, void* y,
   const size_t stats_per_conv = (size_t)N * F * 2;
   FSR_CUDA(cudaMemsetAsync(b_stats, 0, (size_t)(2 * L + 1) * stats_per_conv * sizeof(float), st));
 
-  if (group <= 0 || group > N) group = N;
+  // group > 0: that many images per sequential chunk (kept for A/B: L2-resident groups); else `parts` concurrent
+  // sub-batches on side streams
+  int parts = 1, per;
+  if (group > 0 && group < N) { per = group; }
+  else { parts = overlap_parts(); if (parts > N) parts = N; per = (N + parts - 1) / parts; }
+  const bool concurrent = !(group > 0 && group < N) && parts > 1;
+  if (concurrent) {
+    if (!g_fork) {
+      FSR_CUDA(cudaEventCreateWithFlags(&g_fork, cudaEventDisableTiming));
+      for (int i = 0; i < 4; ++i) {
+        FSR_CUDA(cudaStreamCreateWithFlags(&g_side[i], cudaStreamNonBlocking));
+        FSR_CUDA(cudaEventCreateWithFlags(&g_join[i], cudaEventDisableTiming));
+      }
+    }
+    FSR_CUDA(cudaEventRecord(g_fork, st));
+  }
   const size_t img_bytes = (size_t)H * W * F * 2;
   const size_t in_img = in_u8 ? (size_t)H * W * 3 : (size_t)H * W * 3 * sizeof(float);
-  int rc;
-  for (int n0 = 0; n0 < N; n0 += group) {
-    const int nb = (N - n0 < group) ? (N - n0) : group;
-    uint8_t* res = b_res + n0 * img_bytes;
-    uint8_t* xb = b_x + n0 * img_bytes;
-    uint8_t* raw = b_raw + n0 * img_bytes;
-    uint8_t* yb = b_y + n0 * img_bytes;
-    const uint8_t* xin = reinterpret_cast<const uint8_t*>(x) + n0 * in_img;
-    // neck (model.py:75-78)
-    if ((rc = fsr_neck_conv3x3(xin, prm->neck_w, prm->neck_b, prm->neck_alpha, res, nb, H, W, F, FSR_ACT_PRELU, 0.f,
-                               in_u8, 0, dt, st)))
-      return rc;
-    const uint8_t* cur = res;
-    for (int l = 0; l < L; ++l) {   // ResidualBlock.forward (model.py:67-69)
-      float* s1 = b_stats + (size_t)(2 * l) * stats_per_conv + (size_t)n0 * F * 2;
-      float* s2 = b_stats + (size_t)(2 * l + 1) * stats_per_conv + (size_t)n0 * F * 2;
-      if ((rc = fsr_conv3x3_c64(cur, prm->stem_w1[l], raw, nullptr, s1, nullptr, nb, H, W, F, FSR_EPI_RAW_STATS, 0, 0.f, 0, dt, st))) return rc;
-      if ((rc = fsr_instnorm_apply(raw, s1, nullptr, yb, prm->stem_alpha[l], nb, H * W, F, FSR_ACT_PRELU, 0.f, 1e-5f, dt, st))) return rc;
-      if ((rc = fsr_conv3x3_c64(yb, prm->stem_w2[l], raw, nullptr, s2, nullptr, nb, H, W, F, FSR_EPI_RAW_STATS, 0, 0.f, 0, dt, st))) return rc;
-      if ((rc = fsr_instnorm_apply(raw, s2, cur, xb, nullptr, nb, H * W, F, FSR_ACT_NONE, 0.f, 1e-5f, dt, st))) return rc;
-      cur = xb;
+  const size_t out_img = out_u8 == 1 ? (size_t)16 * H * W * 3 : (size_t)16 * H * W * 3 * sizeof(float);
+  int rc, part = 0;
+  for (int n0 = 0; n0 < N; n0 += per, ++part) {
+    const int nb = (N - n0 < per) ? (N - n0) : per;
+    cudaStream_t s = st;
+    if (concurrent && part > 0) {
+      s = g_side[part - 1];
+      FSR_CUDA(cudaStreamWaitEvent(s, g_fork, 0));
     }
-    {   // bottleneck + long skip (model.py:86-95, 115)
-      float* sb = b_stats + (size_t)(2 * L) * stats_per_conv + (size_t)n0 * F * 2;
-      if ((rc = fsr_conv3x3_c64(cur, prm->bott_w, raw, nullptr, sb, nullptr, nb, H, W, F, FSR_EPI_RAW_STATS, 0, 0.f, 0, dt, st))) return rc;
-      if ((rc = fsr_instnorm_apply(raw, sb, res, xb, nullptr, nb, H * W, F, FSR_ACT_NONE, 0.f, 1e-5f, dt, st))) return rc;
+    rc = generator_chain(prm, reinterpret_cast<const uint8_t*>(x) + n0 * in_img, reinterpret_cast<uint8_t*>(y) + n0 * out_img,
+                         b_res + n0 * img_bytes, b_x + n0 * img_bytes, b_raw + n0 * img_bytes, b_y + n0 * img_bytes,
+                         b_u0 + n0 * 4 * img_bytes, b_u1 + n0 * 16 * img_bytes, b_stats + (size_t)n0 * F * 2, stats_per_conv,
+                         nb, H, W, in_u8, out_u8, s);
+    if (rc) return rc;
+    if (concurrent && part > 0) {
+      FSR_CUDA(cudaEventRecord(g_join[part - 1], s));
+      FSR_CUDA(cudaStreamWaitEvent(st, g_join[part - 1], 0));
     }
   }
-  // upsampling x2 (model.py:39-40) and head (model.py:102-110) over the whole batch
-  if ((rc = fsr_conv3x3_c64(b_x, prm->up_w[0], b_u0, prm->up_b[0], nullptr, prm->up_alpha[0], N, H, W, 256, FSR_EPI_PS_PRELU, 0, 0.f, 0, dt, st))) return rc;
-  if ((rc = fsr_conv3x3_c64(b_u0, prm->up_w[1], b_u1, prm->up_b[1], nullptr, prm->up_alpha[1], N, 2 * H, 2 * W, 256, FSR_EPI_PS_PRELU, 0, 0.f, 0, dt, st))) return rc;
-  if ((rc = fsr_conv3x3_c64(b_u1, prm->head_w, y, prm->head_b, nullptr, nullptr, N, 4 * H, 4 * W, 16, FSR_EPI_HEAD_TANH, 0, 0.f, out_u8, dt, st))) return rc;
   return FSR_OK;
 }
 

@@ -186,6 +186,11 @@ size_t fsr_generator_workspace_bytes(int N, int H, int W, int n_filters, int n_l
 int fsr_generator_forward(const FsrGeneratorParams* prm, const void* x, void* y, void* workspace, size_t ws_bytes,
                           int N, int H, int W, int in_u8, int out_u8, int group, void* stream);
 
+/* Generator.forward can split the batch into `parts` sub-batches (default 1, env FSR_STREAMS) on internal side streams
+ * (fork/join by events on the caller's stream): the HBM-bound kernels of one sub-batch overlap the tensor-bound
+ * convolutions of the other.  1 = single stream. */
+int fsr_set_overlap_streams(int parts);
+
 /* ---- measurement hooks (bench.py): device-time single kernels INSIDE a running forward.
  * fsr_profile_enable(kernel_id) makes every later launch of that kernel (FSR_K_*) be bracketed by a
  * cudaEvent pair on its launch stream (at most FSR_PROFILE_MAX pairs are kept);
