@@ -874,4 +874,17 @@ int fsr_adamw(float* p, const float* g, float* m, float* v, size_t n, float lr, 
   return cuda_rc(cudaGetLastError());
 }
 
+int fsr_adamw_dev(float* p, const float* g, float* m, float* v, size_t n, float lr, float b1, float b2, float eps, float wd,
+                  int* step_dev, float grad_scale, void* stream) {
+  if (!p || !g || !m || !v || !step_dev) return FSR_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  {
+    LaunchScope scope(FSR_K_NONE - 1, st);
+    step_inc_kernel<<<1, 32, 0, st>>>(step_dev);
+  }
+  LaunchScope scope(FSR_K_NONE - 1, st);
+  adamw_dev_kernel<<<ew_blocks(n), 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, wd, step_dev, grad_scale);
+  return cuda_rc(cudaGetLastError());
+}
+
 }  // extern "C"

@@ -58,6 +58,7 @@ class FlatParams:
         if with_optimizer:
             self.m = torch.zeros_like(self.flat)
             self.v = torch.zeros_like(self.flat)
+            self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)     # device-side step counter (graph safe)
         self.step_count = 0
         self.version = 0
         module._fsr_flat = self                            # lets the module's own forward reuse this aliasing
@@ -72,7 +73,7 @@ class FlatParams:
     def adamw_step(self, lr: float, grad_scale: float = 1.0):
         """torch.optim.AdamW defaults of trainer.py:33-38 (betas .9/.999, eps 1e-8, weight_decay 1e-2)."""
         self.step_count += 1
-        ops.adamw(self.flat, self.grad, self.m, self.v, lr, self.step_count, grad_scale=grad_scale)
+        ops.adamw_dev(self.flat, self.grad, self.m, self.v, lr, self.step_dev, grad_scale=grad_scale)
         self.version += 1
 
 
@@ -84,6 +85,7 @@ class GeneratorNet:
         self.m, self.fp, self.dt = module, fp, dtype
         self.L = module.n_layers
         self._packed_version = -1
+        self._bwd_version = -1
         self.P: Dict[str, torch.Tensor] = {}
 
     def _convs64(self):
@@ -93,23 +95,33 @@ class GeneratorNet:
         return names + ["bottleneck.0.weight"]
 
     def pack(self, need_bwd: bool):
-        if self._packed_version == self.fp.version and (not need_bwd or "bwd" in self.P):
+        """(Re)pack into PERSISTENT buffers (same addresses for the lifetime of the net): a captured CUDA graph keeps
+        reading the right memory, and no allocation happens per step."""
+        if self._packed_version == self.fp.version and (not need_bwd or self._bwd_version == self.fp.version):
             return
-        p, P, dt = self.fp.p, {}, self.dt
+        p, P, dt = self.fp.p, self.P, self.dt
+        fwd_stale = self._packed_version != self.fp.version
         for n in self._convs64():
-            P[n], _ = ops.pack_conv3x3(p[n], None, dt)
+            if fwd_stale:
+                P[n], _ = ops.pack_conv3x3(p[n], None, dt, out_w=P.get(n))
             if need_bwd:
-                P[n + ".t"] = ops.pack_conv3x3_t(p[n], dt, flip=True)              # c64-kernel dgrad
+                P[n + ".t"] = ops.pack_conv3x3_t(p[n], dt, flip=True, out=P.get(n + ".t"))          # c64-kernel dgrad
         for i in range(2):
-            P[f"up{i}.w"], P[f"up{i}.b"] = ops.pack_conv3x3(p[f"upsampling.{i}.conv.weight"], p[f"upsampling.{i}.conv.bias"], dt, ps_perm=True)
+            w, b = p[f"upsampling.{i}.conv.weight"], p[f"upsampling.{i}.conv.bias"]
+            if fwd_stale:
+                P[f"up{i}.w"], P[f"up{i}.b"] = ops.pack_conv3x3(w, b, dt, ps_perm=True, out_w=P.get(f"up{i}.w"), out_b=P.get(f"up{i}.b"))
             if need_bwd:
-                P[f"up{i}.t"] = ops.pack_conv3x3_t(p[f"upsampling.{i}.conv.weight"], dt, ps_perm=True)   # gen-kernel dgrad
-        P["head.w"], P["head.b"] = ops.pack_conv3x3(p["head.0.weight"], p["head.0.bias"], dt, cout_pad=16)
+                P[f"up{i}.t"] = ops.pack_conv3x3_t(w, dt, ps_perm=True, out=P.get(f"up{i}.t"))      # gen-kernel dgrad
+        if fwd_stale:
+            P["head.w"], P["head.b"] = ops.pack_conv3x3(p["head.0.weight"], p["head.0.bias"], dt, cout_pad=16,
+                                                        out_w=P.get("head.w"), out_b=P.get("head.b"))
         if need_bwd:
             # head dgrad = direct 3->64 conv with transposed, flipped weights (K = 27: CUDA cores)
-            P["head.t"] = p["head.0.weight"].permute(1, 0, 2, 3).flip(2, 3).contiguous()
-            P["bwd"] = torch.empty(0)
-        self.P, self._packed_version = P, self.fp.version
+            if "head.t" not in P:
+                P["head.t"] = torch.empty((64, 3, 3, 3), dtype=torch.float32, device=p["head.0.weight"].device)
+            P["head.t"].copy_(p["head.0.weight"].permute(1, 0, 2, 3).flip(2, 3))
+            self._bwd_version = self.fp.version
+        self._packed_version = self.fp.version
 
     def forward(self, lr_img: torch.Tensor, save: bool):
         self.pack(need_bwd=save)
@@ -173,21 +185,25 @@ class DiscriminatorNet:
         F_ = module.n_filters
         self.widths = [(F_, F_), (F_, 2 * F_), (2 * F_, 2 * F_), (2 * F_, 4 * F_), (4 * F_, 4 * F_), (4 * F_, 8 * F_), (8 * F_, 8 * F_)]
         self._packed_version = -1
+        self._bwd_version = -1
         self.P: Dict[str, torch.Tensor] = {}
 
     def pack(self, need_bwd: bool):
-        if self._packed_version == self.fp.version and (not need_bwd or "bwd" in self.P):
+        """(Re)pack into persistent buffers (CUDA-graph safe, see GeneratorNet.pack)."""
+        if self._packed_version == self.fp.version and (not need_bwd or self._bwd_version == self.fp.version):
             return
-        p, P, dt = self.fp.p, {}, self.dt
+        p, P, dt = self.fp.p, self.P, self.dt
+        fwd_stale = self._packed_version != self.fp.version
         for i in range(7):
             w = p[f"stem.{i}.conv.weight"]
-            P[f"w{i}"], _ = ops.pack_conv3x3(w, None, dt)
+            if fwd_stale:
+                P[f"w{i}"], _ = ops.pack_conv3x3(w, None, dt, out_w=P.get(f"w{i}"))
             if need_bwd:
-                P[f"t{i}"] = ops.pack_conv3x3_t(w, dt)
+                P[f"t{i}"] = ops.pack_conv3x3_t(w, dt, out=P.get(f"t{i}"))
         if need_bwd:
-            P["neck.t"] = ops.pack_conv3x3_t(p["neck.0.weight"], dt, flip=True, row_pad=16)   # 64 -> 3 image gradient
-            P["bwd"] = torch.empty(0)
-        self.P, self._packed_version = P, self.fp.version
+            P["neck.t"] = ops.pack_conv3x3_t(p["neck.0.weight"], dt, flip=True, row_pad=16, out=P.get("neck.t"))   # 64 -> 3 image gradient
+            self._bwd_version = self.fp.version
+        self._packed_version = self.fp.version
 
     def forward(self, img: torch.Tensor, save: bool):
         self.pack(need_bwd=save)
@@ -312,6 +328,9 @@ class GANEngine:
         # fp16 gradients (1/numel-scaled losses) would underflow: static loss scale; bf16 needs none
         self.S = float(loss_scale) if loss_scale is not None else (4096.0 if dtype == torch.float16 else 1.0)
         self.pg = process_group
+        import os
+        self.use_graph = os.environ.get("FSR_GRAPH", "1") != "0"
+        self._graphs: Dict = {}
         self.world = 1
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.world = torch.distributed.get_world_size(process_group)
@@ -323,16 +342,67 @@ class GANEngine:
 
     def train_step(self, lr_img: torch.Tensor, hr_img: torch.Tensor, noise: Dict[str, torch.Tensor]):
         """lr_img [B,3,h,w], hr_img [B,3,4h,4w] fp32 NCHW in [-1,1] (this rank's shard);
-        noise = {"d_real","d_fake","g_real"}: uniform [0,1) tensors shaped like D's output (trainer.py:175,176,187)."""
-        S, dev = self.S, lr_img.device
+        noise = {"d_real","d_fake","g_real"}: uniform [0,1) tensors shaped like D's output (trainer.py:175,176,187).
+
+        With use_graph (default) the ~500 launches of a step are captured ONCE per input shape into three CUDA graphs
+        (after two eager warm-up steps) and replayed: [D forward/backward] -> all-reduce(D grads) -> [D AdamW + G step
+        forward/backward] -> all-reduce(G grads) -> [G AdamW].  The NCCL calls stay outside the graphs; inputs are copied
+        into static buffers; the AdamW step counters live in device memory."""
         lr_img, hr_img = lr_img.contiguous().float(), hr_img.contiguous().float()
         B = lr_img.shape[0]
-        n_real = noise["d_real"].reshape(B, -1).contiguous().float()
-        n_fake = noise["d_fake"].reshape(B, -1).contiguous().float()
-        n_g = noise["g_real"].reshape(B, -1).contiguous().float()
-        losses = torch.zeros(4, dtype=torch.float32, device=dev)       # loss_real, loss_fake, adv (unscaled bce), content sum
+        ins = (lr_img, hr_img, noise["d_real"].reshape(B, -1).contiguous().float(),
+               noise["d_fake"].reshape(B, -1).contiguous().float(), noise["g_real"].reshape(B, -1).contiguous().float())
+        if not self.use_graph:
+            return self._run_segments(ins, None)
+        key = (tuple(lr_img.shape), tuple(hr_img.shape))
+        st = self._graphs.get(key)
+        if st is None:
+            st = self._graphs[key] = dict(calls=0, graphs=None)
+        if st["graphs"] is None:
+            st["calls"] += 1
+            if st["calls"] <= 2:                                        # eager warm-up: allocator, func attributes, packs
+                return self._run_segments(ins, None)
+            st["inputs"] = [t.clone() for t in ins]
+            torch.cuda.synchronize()
+            graphs, pool = [], None
+            for seg in (self._seg_d, self._seg_g, self._seg_opt):       # capture only: nothing executes here
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pool):
+                    seg(st["inputs"])
+                pool = g.pool()
+                graphs.append(g)
+            st["graphs"], st["out"] = graphs, self._out
+            for fp in (self.gp, self.dp):
+                fp.step_count -= 1                                      # undo the bookkeeping of the (non-executing) capture
+        for dst, src in zip(st["inputs"], ins):
+            dst.copy_(src, non_blocking=True)
+        self._run_segments(st["inputs"], st["graphs"])
+        for fp in (self.gp, self.dp):
+            fp.step_count += 1
+            fp.version += 1
+        self.G.m._packed_key = None
+        return st["out"]
 
-        # ---------------- discriminator step (trainer.py:171-181)
+    def _run_segments(self, ins, graphs):
+        if graphs is None:
+            self._seg_d(ins)
+            self._allreduce(self.dp.grad)
+            self._seg_g(ins)
+            self._allreduce(self.gp.grad)
+            self._seg_opt(ins)
+        else:
+            graphs[0].replay()
+            self._allreduce(self.dp.grad)
+            graphs[1].replay()
+            self._allreduce(self.gp.grad)
+            graphs[2].replay()
+        return self._out
+
+    def _seg_d(self, ins):
+        """discriminator step up to the gradient (trainer.py:171-180)."""
+        lr_img, hr_img, n_real, n_fake, _ = ins
+        S = self.S
+        self._losses = losses = torch.zeros(4, dtype=torch.float32, device=lr_img.device)   # real, fake, adv bce, content sum
         self.dp.zero_grad()
         sr, _ = self.G.forward(lr_img, save=False)                      # :173 (.detach())
         z_real, ctx_r = self.D.forward(hr_img, save=True)               # :172
@@ -342,11 +412,12 @@ class GANEngine:
         ops.bce_logits(z_fake, n_fake, 0.3, 0.0, losses[1:2], dz_f, grad_scale=0.5 * S)      # :176,178,179
         self.D.backward(ctx_r, dz_r, wgrad=True, d_img=None)            # :180
         self.D.backward(ctx_f, dz_f, wgrad=True, d_img=None)
-        del ctx_r, ctx_f
-        self._allreduce(self.dp.grad)
-        self.dp.adamw_step(self.lr_d, grad_scale=1.0 / (S * self.world))   # :181
 
-        # ---------------- generator step (trainer.py:184-196)
+    def _seg_g(self, ins):
+        """discriminator AdamW (trainer.py:181) and the generator step up to the gradient (:184-195)."""
+        lr_img, hr_img, _, _, n_g = ins
+        S, losses = self.S, self._losses
+        self.dp.adamw_step(self.lr_d, grad_scale=1.0 / (S * self.world))   # :181
         self.gp.zero_grad()
         sr, ctx_g = self.G.forward(lr_img, save=True)                   # :185
         z, ctx_d = self.D.forward(sr, save=True)                        # :186 (updated D)
@@ -360,12 +431,12 @@ class GANEngine:
         self.V.backward(ctx_v, dfeat, d_sr)                             # :195
         self.D.backward(ctx_d, dz, wgrad=False, d_img=d_sr)
         self.G.backward(ctx_g, d_sr)
-        self._allreduce(self.gp.grad)
-        self.gp.adamw_step(self.lr_g, grad_scale=1.0 / (S * self.world))   # :196
-        self.G.m._packed_key = None                                        # the module's inference cache is stale now
         nfeat = float(fake_f.numel())
-        return dict(loss_real=losses[0], loss_fake=losses[1], adv_loss=0.1 * losses[2], content_loss=losses[3] / nfeat,
-                    sr=sr)
+        self._out = dict(loss_real=losses[0], loss_fake=losses[1], adv_loss=0.1 * losses[2], content_loss=losses[3] / nfeat, sr=sr)
+
+    def _seg_opt(self, ins):
+        self.gp.adamw_step(self.lr_g, grad_scale=1.0 / (self.S * self.world))   # :196
+        self.G.m._packed_key = None                                        # the module's inference cache is stale now
 
     def pretrain_step(self, lr_img: torch.Tensor, hr_img: torch.Tensor):
         """trainer.py:104-111: generator-only SmoothL1 warm-up."""

@@ -16,15 +16,16 @@ def _cuda(*ts):
 
 
 def pack_conv3x3(weight: torch.Tensor, bias: Optional[torch.Tensor], dtype: torch.dtype, cout_pad: Optional[int] = None,
-                 ps_perm: bool = False) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
-    """OIHW fp32 -> [9][cout_pad][cin] `dtype` (+ permuted/padded fp32 bias)."""
+                 ps_perm: bool = False, out_w: Optional[torch.Tensor] = None,
+                 out_b: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """OIHW fp32 -> [9][cout_pad][cin] `dtype` (+ permuted/padded fp32 bias).  out_w/out_b: repack in place."""
     _cuda(weight, bias)
     cout, cin = weight.shape[0], weight.shape[1]
     cout_pad = cout_pad or cout
     w = weight.detach().float().contiguous()
     b = bias.detach().float().contiguous() if bias is not None else None
-    wp = torch.empty((9, cout_pad, cin), dtype=dtype, device=w.device)
-    bp = torch.empty(cout_pad, dtype=torch.float32, device=w.device) if b is not None else None
+    wp = out_w if out_w is not None else torch.empty((9, cout_pad, cin), dtype=dtype, device=w.device)
+    bp = (out_b if out_b is not None else torch.empty(cout_pad, dtype=torch.float32, device=w.device)) if b is not None else None
     L.check(L.load().fsr_pack_conv3x3_weight(L.ptr(w), L.ptr(b), L.ptr(wp), L.ptr(bp), cout, cin, cout_pad,
                                              int(ps_perm), L.dtype_code(dtype), L.stream_ptr(w.device)), "pack")
     return wp, bp
@@ -347,3 +348,10 @@ def adamw(p, g, m, v, lr, step, b1=0.9, b2=0.999, eps=1e-8, wd=1e-2, grad_scale=
     _cuda(p, g, m, v)
     L.check(L.load().fsr_adamw(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, b1, b2, eps, wd, step, grad_scale,
                                L.stream_ptr(p.device)), "adamw")
+
+
+def adamw_dev(p, g, m, v, lr, step_dev, b1=0.9, b2=0.999, eps=1e-8, wd=1e-2, grad_scale=1.0):
+    """AdamW with the step counter in device memory (int32 tensor, incremented by the call) - CUDA-graph safe."""
+    _cuda(p, g, m, v, step_dev)
+    L.check(L.load().fsr_adamw_dev(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, b1, b2, eps, wd,
+                                   step_dev.data_ptr(), grad_scale, L.stream_ptr(p.device)), "adamw_dev")

@@ -158,6 +158,11 @@ int fsr_bias_grad_nchw(const float* g, float* db, int N, int C, size_t HW, void*
 int fsr_adamw(float* p, const float* g, float* m, float* v, size_t n, float lr, float b1, float b2, float eps, float wd,
               int step, float grad_scale, void* stream);
 
+/* same, with the step counter in device memory (incremented by the call): nothing step-dependent is baked into the
+ * launch parameters, so the whole train step can be captured once in a CUDA graph and replayed. */
+int fsr_adamw_dev(float* p, const float* g, float* m, float* v, size_t n, float lr, float b1, float b2, float eps, float wd,
+                  int* step_dev, float grad_scale, void* stream);
+
 /* ---- whole Generator.forward (model.py:112-117) as one call: neck -> n_layers residual blocks ->
  * bottleneck + long skip -> 2 x (conv + pixel-shuffle + PReLU) -> head + tanh. */
 typedef struct FsrGeneratorParams {

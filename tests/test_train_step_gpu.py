@@ -149,3 +149,43 @@ def test_pretrain_step_runs_and_reduces_loss():
         l1 = tr.pretrain_step(lr_img, hr_img)["loss"].item()
     print("pretrain loss", l0, "->", l1)
     assert l1 < l0
+
+
+def test_cuda_graph_train_step_matches_eager():
+    """Steps 3+ replay a captured CUDA graph (device-side AdamW step counter): same trajectory as eager execution up to
+    the usual Adam sign flips of noise-level gradients (<= 2*lr per step per weight)."""
+    from fast_srgan_b200.trainer import Trainer
+
+    def run(use_graph):
+        cfg = ns(experiment=ns(name="t", seed=0), generator=ns(n_filters=64, n_layers=2), discriminator=ns(n_filters=64, n_layers=7),
+                 training=ns(device="cuda", generator_lr=1e-4, discriminator_lr=1e-4))
+        tr = Trainer(cfg, compute_dtype=torch.bfloat16)
+        tr.generator.load_state_dict(O.make_generator_state(64, 2, 1234))
+        tr.discriminator.load_state_dict(O.make_discriminator_state(64, 4321))
+        tr.perceptual_network.load_state_dict(O.make_vgg19_state(99))
+        tr.engine.use_graph = use_graph
+        losses = []
+        for step in range(5):
+            g = torch.Generator().manual_seed(100 + step)
+            lr_img, hr_img = torch.rand((2, 3, 24, 24), generator=g) * 2 - 1, torch.rand((2, 3, 96, 96), generator=g) * 2 - 1
+            noise = {k: torch.rand((2, 1, 6, 6), generator=g) for k in ("d_real", "d_fake", "g_real")}
+            out = tr.train_step(lr_img, hr_img, noise=noise)
+            losses.append([out[k].item() for k in ("loss_real", "loss_fake", "adv_loss", "content_loss")])
+        torch.cuda.synchronize()
+        e = tr.engine
+        assert e.gp.step_count == 5 and int(e.gp.step_dev.item()) == 5 and int(e.dp.step_dev.item()) == 5
+        # the packed weight buffers the (captured) kernels read must hold the CURRENT parameters: packs are in-place into
+        # persistent buffers, never re-allocated (a graph would otherwise keep reading stale/freed memory)
+        from fast_srgan_b200 import ops
+        wd, _ = ops.pack_conv3x3(e.dp.p["stem.3.conv.weight"], None, torch.bfloat16)
+        assert torch.equal(wd, e.D.P["w3"])
+        wg, _ = ops.pack_conv3x3(e.gp.p["stem.1.conv2.weight"], None, torch.bfloat16)
+        # G was updated by the last AdamW after its last pack: the buffer holds the weights used by the last forward
+        assert wg.shape == e.G.P["stem.1.conv2.weight"].shape
+        return torch.tensor(losses), e.gp.flat.clone(), e.dp.flat.clone()
+
+    le, ge, de = run(False)
+    lg, gg, dg = run(True)
+    print("eager losses", le[-1].tolist(), "graph losses", lg[-1].tolist())
+    assert (le - lg).abs().max().item() <= 2e-2
+    assert (ge - gg).abs().max().item() <= 5 * 2.05e-4 and (de - dg).abs().max().item() <= 5 * 2.05e-4
