@@ -450,11 +450,11 @@ int fsr_neck_conv3x3(const void* x, const float* w, const float* bias, const flo
   if (act == FSR_ACT_PRELU && !alpha) return FSR_ERR_BAD_ARG;
   NeckParams p{x, w, bias, alpha, out, N, H, W, cout, act, slope, in_u8, vgg_norm};
   const size_t total = (size_t)N * H * W;
-  dim3 grid((unsigned)((total + 127) / 128), cout / 64);
+  dim3 grid((unsigned)((2 * total + 255) / 256), cout / 64);
   cudaStream_t st = (cudaStream_t)stream;
   LaunchScope scope(FSR_K_NECK, st);
-  if (dtype == FSR_BF16) neck_conv3x3_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>(p);
-  else neck_conv3x3_kernel<__half><<<grid, 128, 0, st>>>(p);
+  if (dtype == FSR_BF16) neck_conv3x3_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(p);
+  else neck_conv3x3_kernel<__half><<<grid, 256, 0, st>>>(p);
   return cuda_rc(cudaGetLastError());
 }
 
@@ -842,14 +842,15 @@ int fsr_wgrad_c3(const float* img, const void* act, float* out, int N, int H, in
 }
 
 int fsr_bias_grad(const void* g, float* db, size_t npix, int C, int ps_perm, int dtype, void* stream) {
-  if (!g || !db) return FSR_ERR_BAD_ARG;
+  if (!g || !db || C % 8 || 256 % (C / 8)) return FSR_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  int blocks = (int)((npix + 63) / 64);
+  int blocks = (int)((npix + 255) / 256);
   if (blocks > num_sms() * 4) blocks = num_sms() * 4;
   if (blocks < 1) blocks = 1;
+  const size_t sm = (size_t)C * sizeof(float);
   LaunchScope scope(FSR_K_NONE - 1, st);
-  FSR_T((bias_grad_kernel<__half><<<blocks, 256, 0, st>>>((const __half*)g, db, npix, C, ps_perm)),
-        (bias_grad_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)g, db, npix, C, ps_perm)));
+  FSR_T((bias_grad_kernel<__half><<<blocks, 256, sm, st>>>((const __half*)g, db, npix, C, ps_perm)),
+        (bias_grad_kernel<__nv_bfloat16><<<blocks, 256, sm, st>>>((const __nv_bfloat16*)g, db, npix, C, ps_perm)));
   return cuda_rc(cudaGetLastError());
 }
 

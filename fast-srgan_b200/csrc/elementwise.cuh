@@ -11,7 +11,7 @@
 namespace fsr {
 
 // ------------------------------------------------------------------ neck: direct 3->COUT conv
-// One thread = one output pixel x 64 output channels (blockIdx.y selects the 64-channel group).
+// Two threads = one output pixel x 64 output channels (blockIdx.y selects the 64-channel group).
 // Weights [27][64] fp32 in smem, read as broadcast float4.  Input: fp32 NCHW or uint8 NHWC
 // (uint8 path folds reference inference.py:50  x/127.5 - 1).  VGG mode folds model.py:21-22
 // ((x+1)/2 - mean)/std applied to in-image pixels only (zero padding comes AFTER the renorm).
@@ -29,7 +29,9 @@ struct NeckParams {
 };
 
 template <typename T>
-__global__ void __launch_bounds__(128) neck_conv3x3_kernel(const NeckParams p) {
+__global__ void __launch_bounds__(256, 3) neck_conv3x3_kernel(const NeckParams p) {
+  // two threads per output pixel, 32 output channels each (fewer registers -> more resident warps to hide the
+  // 27-element input gather); weights [27][64] fp32 in smem, read as broadcast float4
   __shared__ __align__(16) float sw[27 * 64];
   __shared__ float sb[64];
   const int cg = blockIdx.y;   // 64-channel group
@@ -41,7 +43,9 @@ __global__ void __launch_bounds__(128) neck_conv3x3_kernel(const NeckParams p) {
   __syncthreads();
   const float slope = (p.act == ACT_PRELU) ? __ldg(p.alpha) : p.slope;
   const size_t total = (size_t)p.N * p.H * p.W;
-  const size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t gt = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t pix = gt >> 1;
+  const int half = (int)(gt & 1);
   if (pix >= total) return;
   const int x = (int)(pix % p.W);
   const int y = (int)((pix / p.W) % p.H);
@@ -61,21 +65,21 @@ __global__ void __launch_bounds__(128) neck_conv3x3_kernel(const NeckParams p) {
           if (p.in_u8) {
             v = (float)reinterpret_cast<const uint8_t*>(p.x)[((size_t)(n * p.H + yy) * p.W + xx) * 3 + ci] / 127.5f - 1.0f;
           } else {
-            v = reinterpret_cast<const float*>(p.x)[((size_t)(n * 3 + ci) * p.H + yy) * p.W + xx];
+            v = __ldg(reinterpret_cast<const float*>(p.x) + ((size_t)(n * 3 + ci) * p.H + yy) * p.W + xx);
           }
           if (p.vgg_norm) v = ((v + 1.0f) / 2.0f - mean[ci]) / stdv[ci];
         }
         in[ci * 9 + r * 3 + s] = v;
       }
 
-  float acc[64];
+  float acc[32];
 #pragma unroll
-  for (int c = 0; c < 64; ++c) acc[c] = sb[c];
+  for (int c = 0; c < 32; ++c) acc[c] = sb[half * 32 + c];
 #pragma unroll
   for (int t = 0; t < 27; ++t) {
-    const float4* wr = reinterpret_cast<const float4*>(sw + t * 64);
+    const float4* wr = reinterpret_cast<const float4*>(sw + t * 64 + half * 32);
 #pragma unroll
-    for (int c4 = 0; c4 < 16; ++c4) {
+    for (int c4 = 0; c4 < 8; ++c4) {
       const float4 w4 = wr[c4];
       acc[4 * c4 + 0] = fmaf(in[t], w4.x, acc[4 * c4 + 0]);
       acc[4 * c4 + 1] = fmaf(in[t], w4.y, acc[4 * c4 + 1]);
@@ -83,9 +87,9 @@ __global__ void __launch_bounds__(128) neck_conv3x3_kernel(const NeckParams p) {
       acc[4 * c4 + 3] = fmaf(in[t], w4.w, acc[4 * c4 + 3]);
     }
   }
-  T* o = reinterpret_cast<T*>(p.out) + pix * p.cout + cg * 64;
+  T* o = reinterpret_cast<T*>(p.out) + pix * p.cout + cg * 64 + half * 32;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
+  for (int k = 0; k < 4; ++k) {
     uint4 pk;
     pk.x = Cvt<T>::pack2(apply_act(acc[8 * k + 0], p.act, slope), apply_act(acc[8 * k + 1], p.act, slope));
     pk.y = Cvt<T>::pack2(apply_act(acc[8 * k + 2], p.act, slope), apply_act(acc[8 * k + 3], p.act, slope));
