@@ -162,6 +162,48 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def bench_train_step(args, rank, world, dev, dist):
+    """GAN train step (trainer.py:168-196): G + D + VGG19 perceptual, 24x24 LR / 96x96 HR synthetic pairs, bf16 operands.
+    Per-GPU batch 64 at N=1 (BASELINE configs[2]); 32 per GPU for N>1 (configs[3]: global 256 on 8 GPUs), one NCCL
+    all-reduce per network per step.  Device-timed, max over ranks."""
+    import types
+    from fast_srgan_b200.trainer import Trainer
+    import srgan_oracle as O
+    ns = types.SimpleNamespace
+    B = 64 if world == 1 else 32
+    cfg = ns(experiment=ns(name="bench", seed=0), generator=ns(n_filters=NF, n_layers=NL), discriminator=ns(n_filters=64, n_layers=7),
+             training=ns(device=str(dev), generator_lr=1e-4, discriminator_lr=1e-4))
+    tr = Trainer(cfg, compute_dtype=torch.bfloat16)
+    tr.generator.load_state_dict(O.make_generator_state(NF, NL, seed=1234))
+    tr.discriminator.load_state_dict(O.make_discriminator_state(64, seed=4321))
+    tr.perceptual_network.load_state_dict(O.make_vgg19_state(seed=99))
+    g = torch.Generator().manual_seed(7 + rank)
+    lr = (torch.rand((B, 3, 24, 24), generator=g) * 2 - 1).to(dev)
+    hr = (torch.rand((B, 3, 96, 96), generator=g) * 2 - 1).to(dev)
+    noise = {k: torch.rand((B, 1, 6, 6), generator=g).to(dev) for k in ("d_real", "d_fake", "g_real")}
+    steps = max(5, min(args.steps, 20))
+    for _ in range(4):                               # 2 eager + graph capture + 1 replay
+        out = tr.train_step(lr, hr, noise=noise)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = tr.train_step(lr, hr, noise=noise)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    if dist is not None:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    return {"metric": "GAN train-step ms", "ms_per_step": ms, "per_gpu_batch": B, "global_batch": B * world, "steps": steps,
+            "samples_per_s": B * world / (ms / 1e3), "dtype": "bf16 operands, fp32 accumulate",
+            "needed_tflops_per_gpu": 2636e9 * B / 64.0 / (ms * 1e-3) / 1e12,
+            "content_loss": float(out["content_loss"])}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -171,6 +213,7 @@ def main():
     ap.add_argument("--dtype", default=os.environ.get("FSR_DTYPE", "fp16"), choices=["fp16", "bf16"])
     ap.add_argument("--l2-group", type=int, default=int(os.environ.get("FSR_L2_GROUP", "0")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the auxiliary GAN train-step measurement")
     ap.add_argument("--streams", type=int, default=int(os.environ.get("FSR_STREAMS", "1")),
                     help="sub-batches of the forward run concurrently on internal side streams (1 = single stream)")
     args = ap.parse_args()
@@ -295,6 +338,14 @@ def main():
     e2e_ms = max_over_ranks(wall_ms)    # host-visible completion of the last D2H, max over ranks
     e2e_fps = world * BATCH * args.steps / (e2e_ms / 1e3)
 
+    # ---------------- auxiliary: GAN train-step ms (second half of BASELINE's metric string; configs[2]/[3])
+    train_aux = None
+    if not args.no_train:
+        try:
+            train_aux = bench_train_step(args, rank, world, dev, dist)
+        except Exception as exc:                     # never let the auxiliary number break the headline line
+            train_aux = {"error": repr(exc)[:200]}
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -326,6 +377,7 @@ def main():
                 "d2h_bytes_per_step": BATCH * 16 * H * W * 3, "api": "Generator.super_resolve_u8 (uint8 NHWC host frames in/out)",
                 "ms_per_step": e2e_ms / args.steps},
         "roofline": roof,
+        "train_step": train_aux,
     }
     if not args.no_cpu_baseline and world == 1:
         cfps, cthreads, csample = cpu_generator_fps()
