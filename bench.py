@@ -159,7 +159,7 @@ def run_reference(args, rank, world):
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def bench_train_step(args, rank, world, dev, dist):
@@ -204,7 +204,28 @@ def bench_train_step(args, rank, world, dev, dist):
             "content_loss": float(out["content_loss"])}
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Route fd 1 to stderr while working (NCCL prints its version banner on stdout); emit() restores it so that the
+    ONE JSON line is the only thing on stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(line), flush=True)
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
@@ -383,9 +404,9 @@ def main():
         cfps, cthreads, csample = cpu_generator_fps()
         line["cpu_baseline"] = {"value": cfps, "unit": UNIT, "cores": cthreads, "kind": "port",
                                 "sample": csample + "; oracle port of model.py:112-117, fp32 oneDNN"}
-    print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+    emit(line)
 
 
 if __name__ == "__main__":
