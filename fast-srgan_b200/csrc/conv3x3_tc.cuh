@@ -48,6 +48,7 @@ struct ConvParams {
   const float* alpha;       // device pointer to the PReLU slope (ACT_PRELU)
   float slope;              // LeakyReLU slope (ACT_LRELU)
   int act;                  // ActMode (EPI_BIAS_ACT)
+  int ws;                   // 1: weight-stationary MMAs (B re-used from the collector across the two interleaved tiles)
   int out_u8;               // EPI_HEAD_TANH: 0 -> tanh, fp32 NCHW [N,3,H,W]; 1 -> tanh, uint8 NHWC [N,H,W,3];
                             //                2 -> linear (no tanh) fp32 NCHW store; 3 -> linear, accumulate (+=)
 };
@@ -71,7 +72,9 @@ struct ConvCfg {
   static constexpr int kThreads = 64 + 32 * kEpiWarps;
   static constexpr int kStagingBytes = kEpiWarps * 4096;
   static constexpr int kStages = (NS >= 128) ? (HALO1 ? 2 : 3) : (HALO1 ? 5 : 6);
-  static constexpr int kTmemCols = (2 * NS <= 32) ? 32 : (2 * NS <= 64 ? 64 : (2 * NS <= 128 ? 128 : 256));
+  static constexpr bool kPair = HALO1 && kStages >= 4;   // interleave the MMAs of two tiles (needs both tiles staged)
+  static constexpr int kAccs = kPair ? 4 : 2;
+  static constexpr int kTmemCols = (kAccs * NS <= 32) ? 32 : (kAccs * NS <= 64 ? 64 : (kAccs * NS <= 128 ? 128 : (kAccs * NS <= 256 ? 256 : 512)));
   static constexpr int kSmemBytes = kWBytes + kStages * Geo::kStageBytes + kStagingBytes + 1024 /*barriers+bias*/ + 1024 /*align*/;
   static_assert(kSmemBytes <= 232448, "exceeds the 227 KB per-CTA shared memory of sm_100");
 };
@@ -82,10 +85,30 @@ FSR_DEVINL float apply_act(float v, int act, float slope) {
   return v;
 }
 
+// Sum 64 per-lane values across the 32 lanes of a warp with a halving butterfly (32+16+8+4+2 = 62 shuffles):
+// afterwards lane L holds the totals of columns 2L and 2L+1.  Register-only: costs no shared-memory bandwidth
+// (the conv is bound by the smem data pipe).
+FSR_DEVINL void warp_reduce64(float (&v)[64], int lane) {
+#pragma unroll
+  for (int step = 0; step < 5; ++step) {
+    const int off = 16 >> step;
+    const int half = 32 >> step;
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float send = up ? v[i] : v[i + half];
+      const float keep = up ? v[i + half] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+}
+
 template <int NS, int EPI, typename T, bool HALO1>
 __global__ void __launch_bounds__(ConvCfg<NS, HALO1>::kThreads, 1)
 conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
-                   const ConvParams p) {
+                   const __grid_constant__ CUtensorMap tm_out, const ConvParams p) {
+  // NHWC outputs leave through a TMA store of the staged (swizzled) tile: no smem read-back, hardware edge clipping
+  constexpr bool kTmaStore = (EPI == EPI_RAW_STATS || EPI == EPI_BIAS_ACT);
   using Cfg = ConvCfg<NS, HALO1>;
   using Geo = ConvGeo<HALO1>;
   constexpr int TH = Geo::TH, TW = Geo::TW;
@@ -98,9 +121,9 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
   uint64_t* full_bar = bars;                       // [kStages]
   uint64_t* empty_bar = bars + Cfg::kStages;       // [kStages]
   uint64_t* w_bar = bars + 2 * Cfg::kStages;       // [1]
-  uint64_t* tfull_bar = w_bar + 1;                 // [2]
-  uint64_t* tempty_bar = tfull_bar + 2;            // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* tfull_bar = w_bar + 1;                 // [4]
+  uint64_t* tempty_bar = tfull_bar + 4;            // [4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 4);
   float* smem_bias = reinterpret_cast<float*>(tmem_slot + 4);   // [NS]
 
   const int warp = threadIdx.x >> 5;
@@ -119,11 +142,16 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     tma_prefetch_desc(&tm_w);
     for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     mbar_init(w_bar, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
     fence_mbar_init();
     fence_proxy_async();
   }
   if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  // accumulator ring: HALO1 issues the MMAs of TWO tiles interleaved (two independent accumulation chains keep the
+  // tensor pipe busy while each chain waits on its own previous MMA) -> 4 accumulators, tile `it` uses
+  // ((it>>1)&1)*2 + (it&1), reused every 4 tiles; HALO0 keeps the plain double buffer.
+  auto acc_of = [](int it) { return Cfg::kPair ? (((it >> 1) & 1) * 2 + (it & 1)) : (it & 1); };
+  auto phase_of = [](int it) { return (uint32_t)(Cfg::kPair ? ((it >> 2) & 1) : ((it >> 1) & 1)); };
   if (EPI != EPI_RAW_STATS && p.bias != nullptr) {
     for (int i = threadIdx.x; i < NS; i += blockDim.x) smem_bias[i] = p.bias[slice * NS + i];
   } else {
@@ -170,16 +198,27 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     tc_fence_after();
     int stage = 0; uint32_t phase = 0;
     int it = 0;
-    for (int t = t_begin; t < t_end; ++t, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
-      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * NS;
-      if constexpr (HALO1) {
-        mbar_wait(&full_bar[stage], phase);
+    if constexpr (HALO1) {
+      constexpr int kStep = Cfg::kPair ? 2 : 1;
+      for (int t = t_begin; t < t_end; t += kStep, it += kStep) {
+        const bool two = Cfg::kPair && (t + 1 < t_end);
+        const int acc_a = acc_of(it), acc_b = Cfg::kPair ? acc_of(it + 1) : acc_a;
+        const uint32_t ph = phase_of(it);
+        mbar_wait(&tempty_bar[acc_a], ph ^ 1);
+        if (two) mbar_wait(&tempty_bar[acc_b], ph ^ 1);
         tc_fence_after();
-        const uint32_t a_lo = a_lo0 + stage * (Geo::kStageBytes >> 4);
+        const int stage_a = stage;
+        const uint32_t phase_a = phase;
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        const int stage_b = stage;
+        const uint32_t phase_b = phase;
+        if (two) { if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; } }
+        mbar_wait(&full_bar[stage_a], phase_a);
+        if (two) mbar_wait(&full_bar[stage_b], phase_b);
+        tc_fence_after();
+        const uint32_t a_lo_a = a_lo0 + stage_a * (Geo::kStageBytes >> 4);
+        const uint32_t a_lo_b = a_lo0 + stage_b * (Geo::kStageBytes >> 4);
+        const uint32_t d_a = tmem_base + acc_a * NS, d_b = tmem_base + acc_b * NS;
         if (elect_one()) {
 #pragma unroll
           for (int r = 0; r < 3; ++r) {
@@ -192,18 +231,32 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
               const uint32_t hi = kSbo | (1u << 14) | (2u << 29);
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                const uint64_t adesc = desc_join(a_lo + (((r * (TW + 2) + s) * 128 + k * 32) >> 4), hi);
+                const uint32_t aoff = (uint32_t)(((r * (TW + 2) + s) * 128 + k * 32) >> 4);
                 const uint64_t bdesc = desc_join(b_lo0 + (((r * 3 + s) * (NS * 128) + k * 32) >> 4), kDescHiSw128);
-                umma_f16(d_tmem, adesc, bdesc, idesc, (s | r | k) != 0 ? 1u : 0u);
+                if (two && p.ws) {
+                  umma_f16_ws_fill(d_a, desc_join(a_lo_a + aoff, hi), bdesc, idesc, (s | r | k) != 0 ? 1u : 0u);
+                  umma_f16_ws_lastuse(d_b, desc_join(a_lo_b + aoff, hi), bdesc, idesc, (s | r | k) != 0 ? 1u : 0u);
+                } else {
+                  umma_f16(d_a, desc_join(a_lo_a + aoff, hi), bdesc, idesc, (s | r | k) != 0 ? 1u : 0u);
+                  if (two) umma_f16(d_b, desc_join(a_lo_b + aoff, hi), bdesc, idesc, (s | r | k) != 0 ? 1u : 0u);
+                }
               }
             }
           }
-          umma_commit(&empty_bar[stage]);
-          umma_commit(&tfull_bar[acc]);
+          umma_commit(&empty_bar[stage_a]);
+          if (two) umma_commit(&empty_bar[stage_b]);
+          umma_commit(&tfull_bar[acc_a]);
+          if (two) umma_commit(&tfull_bar[acc_b]);
         }
         __syncwarp();
-        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
-      } else {
+      }
+    } else {
+      for (int t = t_begin; t < t_end; ++t, ++it) {
+        const int acc = acc_of(it);
+        const uint32_t acc_phase = phase_of(it);
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * NS;
 #pragma unroll
         for (int s = 0; s < 3; ++s) {
           mbar_wait(&full_bar[stage], phase);
@@ -253,9 +306,9 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     };
     int it = 0;
     for (int t = t_begin; t < t_end; ++t, ++it) {
-      const int acc = it & 1;
-      if (Cfg::kEpiWarps == 8 && acc != egroup) continue;
-      const uint32_t acc_phase = (it >> 1) & 1;
+      if (Cfg::kEpiWarps == 8 && (it & 1) != egroup) continue;
+      const int acc = acc_of(it);
+      const uint32_t acc_phase = phase_of(it);
       const int n = t / tiles_per_img;
       const int rem = t - n * tiles_per_img;
       const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
@@ -335,69 +388,69 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
           }
           const int col0 = slice * NS + chunk * 64;   // first GEMM column of this chunk
 
-          // ---- registers -> swizzled smem (row = pixel, 8 x 16B chunks) -> coalesced global
+          // ---- registers -> swizzled smem (row = pixel, 8 x 16B chunks) -> global
+          if constexpr (kTmaStore) {
+            if (lane == 0) tma_store_wait_read();       // the previous TMA store has finished reading this buffer
+          }
           __syncwarp();
 #pragma unroll
           for (int k = 0; k < 8; ++k)
             st_shared_v4(stg + lane * 128 + ((k ^ (lane & 7)) << 4), pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
-          __syncwarp();
-          uint4 val[8];
+          if constexpr (kTmaStore) {
+            fence_proxy_async();                         // generic-proxy writes -> visible to the TMA (async proxy)
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_4d(&tm_out, smem_stg + ew * 4096, col0, x0, y0 + (q * 32) / TW, n);
+              tma_store_commit();
+            }
+          } else {
+            __syncwarp();
+            uint4 val[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int rrow = j * 4 + (lane >> 3);
-            val[j] = ld_shared_v4(stg + rrow * 128 + (((lane & 7) ^ (rrow & 7)) << 4));
-          }
+            for (int j = 0; j < 8; ++j) {
+              const int rrow = j * 4 + (lane >> 3);
+              val[j] = ld_shared_v4(stg + rrow * 128 + (((lane & 7) ^ (rrow & 7)) << 4));
+            }
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int rrow = j * 4 + (lane >> 3);
-            const int mm = q * 32 + rrow;
-            const int py = y0 + mm / TW, px = x0 + mm % TW;
-            if (interior || (py < p.H && px < p.W)) {
-              T* dst;
-              if constexpr (EPI == EPI_PS_PRELU) {
-                const int qq = col0 >> 6;               // GEMM column block = 2*i + j
-                const int oy = 2 * py + (qq >> 1), ox = 2 * px + (qq & 1);
-                dst = reinterpret_cast<T*>(p.out) + ((size_t)(n * 2 * p.H + oy) * (2 * p.W) + ox) * 64;
-              } else {
-                dst = reinterpret_cast<T*>(p.out) + ((size_t)(n * p.H + py) * p.W + px) * p.cout_total + col0;
+            for (int j = 0; j < 8; ++j) {
+              const int rrow = j * 4 + (lane >> 3);
+              const int mm = q * 32 + rrow;
+              const int py = y0 + mm / TW, px = x0 + mm % TW;
+              if (interior || (py < p.H && px < p.W)) {
+                T* dst;
+                if constexpr (EPI == EPI_PS_PRELU) {
+                  const int qq = col0 >> 6;               // GEMM column block = 2*i + j
+                  const int oy = 2 * py + (qq >> 1), ox = 2 * px + (qq & 1);
+                  dst = reinterpret_cast<T*>(p.out) + ((size_t)(n * 2 * p.H + oy) * (2 * p.W) + ox) * 64;
+                } else {
+                  dst = reinterpret_cast<T*>(p.out) + ((size_t)(n * p.H + py) * p.W + px) * p.cout_total + col0;
+                }
+                *reinterpret_cast<uint4*>(dst + (lane & 7) * 8) = val[j];
               }
-              *reinterpret_cast<uint4*>(dst + (lane & 7) * 8) = val[j];
             }
           }
 
           if constexpr (EPI == EPI_RAW_STATS) {
-            // InstanceNorm statistics (reference model.py:55,65,94,132) of the STORED (rounded) values:
-            // lane L owns channels 2L, 2L+1 = one 32-bit word per staged pixel row -> conflict-free
-            // column walk over the 32 rows of this warp; out-of-image rows are skipped (edge tiles).
-            const uint32_t colw = ((lane & 3) << 2);
-            if (interior) {
-              uint32_t w[32];
+            // InstanceNorm statistics (reference model.py:55,65,94,132) of the STORED (rounded) values, reduced in
+            // registers: a butterfly over the warp's 32 pixels leaves channels (2L, 2L+1) in lane L.
+            float v[64], sq[64];
 #pragma unroll
-              for (int rr = 0; rr < 32; ++rr)
-                w[rr] = ld_shared_u32(stg + rr * 128 + ((((lane >> 2) ^ (rr & 7))) << 4) + colw);
-#pragma unroll
-              for (int rr = 0; rr < 32; ++rr) {
-                const float2 f = Cvt<T>::unpack2(w[rr]);
-                st_s0 += f.x; st_q0 = fmaf(f.x, f.x, st_q0);
-                st_s1 += f.y; st_q1 = fmaf(f.y, f.y, st_q1);
-              }
-            } else {
-#pragma unroll 4
-              for (int rr = 0; rr < 32; ++rr) {
-                const int mm = q * 32 + rr;
-                const bool ok = (y0 + mm / TW < p.H) && (x0 + mm % TW < p.W);
-                const uint32_t w = ld_shared_u32(stg + rr * 128 + ((((lane >> 2) ^ (rr & 7))) << 4) + colw);
-                const float2 f = Cvt<T>::unpack2(w);
-                if (ok) {
-                  st_s0 += f.x; st_q0 = fmaf(f.x, f.x, st_q0);
-                  st_s1 += f.y; st_q1 = fmaf(f.y, f.y, st_q1);
-                }
-              }
+            for (int i = 0; i < 32; ++i) {
+              const float2 f = Cvt<T>::unpack2(pk[i]);
+              v[2 * i] = pvalid ? f.x : 0.f;
+              v[2 * i + 1] = pvalid ? f.y : 0.f;
+              sq[2 * i] = v[2 * i] * v[2 * i];
+              sq[2 * i + 1] = v[2 * i + 1] * v[2 * i + 1];
             }
+            warp_reduce64(v, lane);
+            warp_reduce64(sq, lane);
+            st_s0 += v[0]; st_q0 += sq[0];
+            st_s1 += v[1]; st_q1 += sq[1];
           }
         }
       }
     }
+    if (kTmaStore && lane == 0) tma_store_wait_all();
     if (EPI == EPI_RAW_STATS) flush_stats(st_n);
   }
 

@@ -28,10 +28,12 @@ struct NeckParams {
   int vgg_norm;
 };
 
-template <typename T>
-__global__ void __launch_bounds__(256, 3) neck_conv3x3_kernel(const NeckParams p) {
-  // two threads per output pixel, 32 output channels each (fewer registers -> more resident warps to hide the
-  // 27-element input gather); weights [27][64] fp32 in smem, read as broadcast float4
+template <typename T, int TPP>
+__global__ void __launch_bounds__(TPP == 2 ? 256 : 128, TPP == 2 ? 3 : 1) neck_conv3x3_kernel(const NeckParams p) {
+  // TPP threads per output pixel, 64/TPP output channels each.  TPP = 2 (fewer registers, more resident warps) wins on
+  // the small training images, TPP = 1 (one input gather per pixel) on large inference batches (measured).
+  // weights [27][64] fp32 in smem, read as broadcast float4
+  constexpr int CPT = 64 / TPP;
   __shared__ __align__(16) float sw[27 * 64];
   __shared__ float sb[64];
   const int cg = blockIdx.y;   // 64-channel group
@@ -44,8 +46,8 @@ __global__ void __launch_bounds__(256, 3) neck_conv3x3_kernel(const NeckParams p
   const float slope = (p.act == ACT_PRELU) ? __ldg(p.alpha) : p.slope;
   const size_t total = (size_t)p.N * p.H * p.W;
   const size_t gt = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t pix = gt >> 1;
-  const int half = (int)(gt & 1);
+  const size_t pix = gt / TPP;
+  const int half = (int)(gt % TPP);
   if (pix >= total) return;
   const int x = (int)(pix % p.W);
   const int y = (int)((pix / p.W) % p.H);
@@ -72,14 +74,14 @@ __global__ void __launch_bounds__(256, 3) neck_conv3x3_kernel(const NeckParams p
         in[ci * 9 + r * 3 + s] = v;
       }
 
-  float acc[32];
+  float acc[CPT];
 #pragma unroll
-  for (int c = 0; c < 32; ++c) acc[c] = sb[half * 32 + c];
+  for (int c = 0; c < CPT; ++c) acc[c] = sb[half * CPT + c];
 #pragma unroll
   for (int t = 0; t < 27; ++t) {
-    const float4* wr = reinterpret_cast<const float4*>(sw + t * 64 + half * 32);
+    const float4* wr = reinterpret_cast<const float4*>(sw + t * 64 + half * CPT);
 #pragma unroll
-    for (int c4 = 0; c4 < 8; ++c4) {
+    for (int c4 = 0; c4 < CPT / 4; ++c4) {
       const float4 w4 = wr[c4];
       acc[4 * c4 + 0] = fmaf(in[t], w4.x, acc[4 * c4 + 0]);
       acc[4 * c4 + 1] = fmaf(in[t], w4.y, acc[4 * c4 + 1]);
@@ -87,9 +89,9 @@ __global__ void __launch_bounds__(256, 3) neck_conv3x3_kernel(const NeckParams p
       acc[4 * c4 + 3] = fmaf(in[t], w4.w, acc[4 * c4 + 3]);
     }
   }
-  T* o = reinterpret_cast<T*>(p.out) + pix * p.cout + cg * 64 + half * 32;
+  T* o = reinterpret_cast<T*>(p.out) + pix * p.cout + cg * 64 + half * CPT;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
+  for (int k = 0; k < CPT / 8; ++k) {
     uint4 pk;
     pk.x = Cvt<T>::pack2(apply_act(acc[8 * k + 0], p.act, slope), apply_act(acc[8 * k + 1], p.act, slope));
     pk.y = Cvt<T>::pack2(apply_act(acc[8 * k + 2], p.act, slope), apply_act(acc[8 * k + 3], p.act, slope));

@@ -212,6 +212,9 @@ unsigned long long fsr_launch_count(void);
  * 1 = ONE halo tile per 16x8-pixel tile addressed through unaligned UMMA descriptors (2.6x less
  * L2->SM traffic, the default).  Environment FSR_HALO1=0 selects mode 0 at start-up. */
 int fsr_set_halo_mode(int single_halo_tile);
+/* 1: the 64-channel conv issues tcgen05.mma.ws (weight-stationary) pairs: the weight tile is read from smem once
+ * per two pixel tiles (collector buffer reuse).  Default on (environment FSR_WS=0 disables; -1 = environment default). */
+int fsr_set_ws_mode(int weight_stationary);
 
 #ifdef __cplusplus
 }

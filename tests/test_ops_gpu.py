@@ -10,15 +10,18 @@ DTYPES = [torch.float16, torch.bfloat16]
 EPS = {torch.float16: 2.0 ** -11, torch.bfloat16: 2.0 ** -8}   # half-ulp relative rounding of the stored output
 
 
-@pytest.fixture(autouse=True, params=[1, 0], ids=["halo1", "halo3"])
+@pytest.fixture(autouse=True, params=[(1, 0), (1, 1), (0, 0)], ids=["halo1", "halo1-ws", "halo3"])
 def _setup(request):
-    """No TF32 in the PyTorch reference; every test runs in both A-operand staging modes of the conv."""
+    """No TF32 in the PyTorch reference; every test runs in each A-operand staging mode of the conv and with the
+    weight-stationary (tcgen05.mma.ws, collector re-use) MMA pairing on and off."""
     from fast_srgan_b200 import _lib
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
-    _lib.load().fsr_set_halo_mode(request.param)
+    _lib.load().fsr_set_halo_mode(request.param[0])
+    _lib.load().fsr_set_ws_mode(request.param[1])
     yield
     _lib.load().fsr_set_halo_mode(1)
+    _lib.load().fsr_set_ws_mode(-1)
 
 
 def rnd(shape, seed, scale=1.0):

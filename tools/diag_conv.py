@@ -27,6 +27,7 @@ def nchw(x):
 from fast_srgan_b200 import _lib  # noqa: E402
 MODE = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 _lib.load().fsr_set_halo_mode(MODE)
+_lib.load().fsr_set_ws_mode(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
 print("halo mode", MODE, flush=True)
 g = torch.Generator().manual_seed(0)
 N, H, W = 1, 16, 32
