@@ -204,7 +204,7 @@ int launch_head(const void* x, const void* w_packed, ConvParams p, int dtype, cu
 }
 
 template <typename T>
-int conv_dispatch(const void* x, const void* w_packed, void* out, const float* bias, float* stats, const float* alpha,
+int conv_dispatch(const void* x, const void* w_packed, void* out, const float* bias, long long* stats, const float* alpha,
                   int N, int H, int W, int cout, int epilogue, int act, float slope, int out_u8, int dtype,
                   cudaStream_t st) {
   if (N <= 0 || H <= 0 || W <= 0) return FSR_ERR_BAD_SHAPE;
@@ -261,7 +261,7 @@ int launch_gen(const CUtensorMap* maps, const CUtensorMap& tmw, GenParams& p, cu
 }
 
 template <typename T>
-int gen_dispatch(const void* x, const void* w_packed, void* out, const float* bias, float* stats, const float* alpha,
+int gen_dispatch(const void* x, const void* w_packed, void* out, const float* bias, long long* stats, const float* alpha,
                  int N, int H, int W, int cin, int cout, int stride, int mode, int epilogue, int act, float slope,
                  int dtype, cudaStream_t st) {
   if (N <= 0 || H <= 0 || W <= 0 || cin % 64 || cout % 64) return FSR_ERR_BAD_SHAPE;
@@ -440,24 +440,24 @@ int fsr_pack_conv3x3_weight(const float* w_oihw, const float* bias, void* w_pack
   return cuda_rc(cudaGetLastError());
 }
 
-int fsr_conv3x3_c64(const void* x, const void* w_packed, void* out, const float* bias, float* stats,
+int fsr_conv3x3_c64(const void* x, const void* w_packed, void* out, const float* bias, int64_t* stats,
                     const float* alpha, int N, int H, int W, int cout, int epilogue, int act, float slope,
                     int out_u8, int dtype, void* stream) {
   if (!x || !w_packed || !out) return FSR_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == FSR_BF16)
-    return conv_dispatch<__nv_bfloat16>(x, w_packed, out, bias, stats, alpha, N, H, W, cout, epilogue, act, slope, out_u8, dtype, st);
-  return conv_dispatch<__half>(x, w_packed, out, bias, stats, alpha, N, H, W, cout, epilogue, act, slope, out_u8, dtype, st);
+    return conv_dispatch<__nv_bfloat16>(x, w_packed, out, bias, reinterpret_cast<long long*>(stats), alpha, N, H, W, cout, epilogue, act, slope, out_u8, dtype, st);
+  return conv_dispatch<__half>(x, w_packed, out, bias, reinterpret_cast<long long*>(stats), alpha, N, H, W, cout, epilogue, act, slope, out_u8, dtype, st);
 }
 
-int fsr_conv3x3_gen(const void* x, const void* w_packed, void* out, const float* bias, float* stats,
+int fsr_conv3x3_gen(const void* x, const void* w_packed, void* out, const float* bias, int64_t* stats,
                     const float* alpha, int N, int H, int W, int cin, int cout, int stride, int mode, int epilogue,
                     int act, float slope, int dtype, void* stream) {
   if (!x || !w_packed || !out) return FSR_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == FSR_BF16)
-    return gen_dispatch<__nv_bfloat16>(x, w_packed, out, bias, stats, alpha, N, H, W, cin, cout, stride, mode, epilogue, act, slope, dtype, st);
-  return gen_dispatch<__half>(x, w_packed, out, bias, stats, alpha, N, H, W, cin, cout, stride, mode, epilogue, act, slope, dtype, st);
+    return gen_dispatch<__nv_bfloat16>(x, w_packed, out, bias, reinterpret_cast<long long*>(stats), alpha, N, H, W, cin, cout, stride, mode, epilogue, act, slope, dtype, st);
+  return gen_dispatch<__half>(x, w_packed, out, bias, reinterpret_cast<long long*>(stats), alpha, N, H, W, cin, cout, stride, mode, epilogue, act, slope, dtype, st);
 }
 
 int fsr_neck_conv3x3(const void* x, const float* w, const float* bias, const float* alpha, void* out, int N, int H,
@@ -480,11 +480,11 @@ int fsr_neck_conv3x3(const void* x, const float* w, const float* bias, const flo
   return cuda_rc(cudaGetLastError());
 }
 
-int fsr_instnorm_apply(const void* raw, const float* stats, const void* residual, void* out, const float* alpha,
+int fsr_instnorm_apply(const void* raw, const int64_t* stats, const void* residual, void* out, const float* alpha,
                        int N, int HW, int C, int act, float slope, float eps, int dtype, void* stream) {
   if (!raw || !stats || !out || C % 8 || N <= 0 || HW <= 0) return FSR_ERR_BAD_ARG;
   if (act == FSR_ACT_PRELU && !alpha) return FSR_ERR_BAD_ARG;
-  InApplyParams p{raw, stats, residual, out, alpha, slope, act, HW, C, eps};
+  InApplyParams p{raw, reinterpret_cast<const long long*>(stats), residual, out, alpha, slope, act, HW, C, eps};
   const size_t nvec = (size_t)HW * (C / 8);
   int bpi = (int)((nvec + 256 * 4 - 1) / (256 * 4));   // ~4 vectors per thread
   const int cap = (num_sms() * 8 + N - 1) / N;
@@ -571,7 +571,7 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 
 size_t fsr_generator_workspace_bytes(int N, int H, int W, int n_filters, int n_layers) {
   const size_t P = align_up((size_t)N * H * W * n_filters * 2, 1024);
-  const size_t stats = align_up((size_t)(2 * n_layers + 1) * N * n_filters * 2 * sizeof(float), 1024);
+  const size_t stats = align_up((size_t)(2 * n_layers + 1) * N * n_filters * 2 * sizeof(int64_t), 1024);
   return 4 * P + 4 * P + 16 * P + stats + 4096;
 }
 
@@ -597,7 +597,7 @@ int fsr_set_overlap_streams(int parts) {
 }
 
 static int generator_chain(const FsrGeneratorParams* prm, const uint8_t* xin, uint8_t* yout, uint8_t* res, uint8_t* xb,
-                           uint8_t* raw, uint8_t* yb, uint8_t* u0, uint8_t* u1, float* stats, size_t stats_per_conv,
+                           uint8_t* raw, uint8_t* yb, uint8_t* u0, uint8_t* u1, int64_t* stats, size_t stats_per_conv,
                            int nb, int H, int W, int in_u8, int out_u8, cudaStream_t st) {
   const int F = 64, L = prm->n_layers, dt = prm->dtype;
   int rc;
@@ -606,8 +606,8 @@ static int generator_chain(const FsrGeneratorParams* prm, const uint8_t* xin, ui
     return rc;
   const uint8_t* cur = res;
   for (int l = 0; l < L; ++l) {   // ResidualBlock.forward (model.py:67-69)
-    float* s1 = stats + (size_t)(2 * l) * stats_per_conv;
-    float* s2 = stats + (size_t)(2 * l + 1) * stats_per_conv;
+    int64_t* s1 = stats + (size_t)(2 * l) * stats_per_conv;
+    int64_t* s2 = stats + (size_t)(2 * l + 1) * stats_per_conv;
     if ((rc = fsr_conv3x3_c64(cur, prm->stem_w1[l], raw, nullptr, s1, nullptr, nb, H, W, F, FSR_EPI_RAW_STATS, 0, 0.f, 0, dt, st))) return rc;
     if ((rc = fsr_instnorm_apply(raw, s1, nullptr, yb, prm->stem_alpha[l], nb, H * W, F, FSR_ACT_PRELU, 0.f, 1e-5f, dt, st))) return rc;
     if ((rc = fsr_conv3x3_c64(yb, prm->stem_w2[l], raw, nullptr, s2, nullptr, nb, H, W, F, FSR_EPI_RAW_STATS, 0, 0.f, 0, dt, st))) return rc;
@@ -615,7 +615,7 @@ static int generator_chain(const FsrGeneratorParams* prm, const uint8_t* xin, ui
     cur = xb;
   }
   {   // bottleneck + long skip (model.py:86-95, 115)
-    float* sb = stats + (size_t)(2 * L) * stats_per_conv;
+    int64_t* sb = stats + (size_t)(2 * L) * stats_per_conv;
     if ((rc = fsr_conv3x3_c64(cur, prm->bott_w, raw, nullptr, sb, nullptr, nb, H, W, F, FSR_EPI_RAW_STATS, 0, 0.f, 0, dt, st))) return rc;
     if ((rc = fsr_instnorm_apply(raw, sb, res, xb, nullptr, nb, H * W, F, FSR_ACT_NONE, 0.f, 1e-5f, dt, st))) return rc;
   }
@@ -640,9 +640,9 @@ int fsr_generator_forward(const FsrGeneratorParams* prm, const void* x, void* y,
   uint8_t* b_y = base + 3 * P;      // normalised + PReLU intermediate
   uint8_t* b_u0 = base + 4 * P;     // [N,2H,2W,64]
   uint8_t* b_u1 = base + 8 * P;     // [N,4H,4W,64]
-  float* b_stats = reinterpret_cast<float*>(base + 24 * P);
+  int64_t* b_stats = reinterpret_cast<int64_t*>(base + 24 * P);
   const size_t stats_per_conv = (size_t)N * F * 2;
-  FSR_CUDA(cudaMemsetAsync(b_stats, 0, (size_t)(2 * L + 1) * stats_per_conv * sizeof(float), st));
+  FSR_CUDA(cudaMemsetAsync(b_stats, 0, (size_t)(2 * L + 1) * stats_per_conv * sizeof(int64_t), st));
 
   // group > 0: that many images per sequential chunk (kept for A/B: L2-resident groups); else `parts` concurrent
   // sub-batches on side streams
@@ -798,12 +798,12 @@ int fsr_smooth_l1(const void* a, const void* b, size_t n, float* loss_acc, void*
   return cuda_rc(cudaGetLastError());
 }
 
-int fsr_instnorm_bwd(const void* raw, const float* stats, const void* dy, float* red, void* draw, const float* alpha,
+int fsr_instnorm_bwd(const void* raw, const int64_t* stats, const void* dy, float* red, void* draw, const float* alpha,
                      float* dalpha, int N, int HW, int C, int act, float slope, float eps, int dtype, void* stream) {
   if (!raw || !stats || !dy || !red || !draw || C % 8 || 256 % (C / 8)) return FSR_ERR_BAD_ARG;
   if (act == FSR_ACT_PRELU && !alpha) return FSR_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  InBwdParams p{raw, stats, dy, red, draw, alpha, dalpha, slope, act, HW, C, eps};
+  InBwdParams p{raw, reinterpret_cast<const long long*>(stats), dy, red, draw, alpha, dalpha, slope, act, HW, C, eps};
   const size_t nvec = (size_t)HW * (C / 8);
   int bpi = (int)((nvec + 256 * 8 - 1) / (256 * 8));
   const int cap = (num_sms() * 4 + N - 1) / N;

@@ -46,7 +46,7 @@ struct GenParams {
   void* out;                // NHWC T, pixel pitch cout_total
   long long out_img_stride; // elements between consecutive images of `out`
   const float* bias;        // [cout_total] or nullptr
-  float* stats;             // [N][cout_total][2] (EPI_RAW_STATS)
+  long long* stats;         // [N][cout_total][2] fixed-point int64 (EPI_RAW_STATS)
   const float* alpha;
   float slope;
   int act;
@@ -187,17 +187,17 @@ conv3x3_gen_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_const
     const int yy = m / TW, xx = m % TW;
     (void)yy; (void)xx;
     const float slope = (p.act == ACT_PRELU) ? __ldg(p.alpha) : p.slope;
-    float st_s0 = 0.f, st_q0 = 0.f, st_s1 = 0.f, st_q1 = 0.f;
+    long long st_s0 = 0, st_q0 = 0, st_s1 = 0, st_q1 = 0;     // fixed point, see conv3x3_tc.cuh
     int st_n = -1;
     auto flush_stats = [&](int img) {
       if (EPI == EPI_RAW_STATS && img >= 0) {
-        float* st = p.stats + ((size_t)img * p.cout_total + slice * NS + 2 * lane) * 2;
-        atomicAdd(st + 0, st_s0);
-        atomicAdd(st + 1, st_q0);
-        atomicAdd(st + 2, st_s1);
-        atomicAdd(st + 3, st_q1);
+        long long* st = p.stats + ((size_t)img * p.cout_total + slice * NS + 2 * lane) * 2;
+        stat_atomic_add(st + 0, st_s0);
+        stat_atomic_add(st + 1, st_q0);
+        stat_atomic_add(st + 2, st_s1);
+        stat_atomic_add(st + 3, st_q1);
       }
-      st_s0 = st_q0 = st_s1 = st_q1 = 0.f;
+      st_s0 = st_q0 = st_s1 = st_q1 = 0;
     };
     int it = 0;
     for (int t = t_begin; t < t_end; ++t, ++it) {
@@ -260,6 +260,7 @@ conv3x3_gen_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_const
       }
       if constexpr (EPI == EPI_RAW_STATS) {
         const uint32_t colw = ((lane & 3) << 2);
+        float t_s0 = 0.f, t_q0 = 0.f, t_s1 = 0.f, t_q1 = 0.f;      // this tile's partial sums (fixed order)
 #pragma unroll 4
         for (int rr = 0; rr < 32; ++rr) {
           const int mm = q * 32 + rr;
@@ -267,10 +268,12 @@ conv3x3_gen_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_const
           const uint32_t w = ld_shared_u32(stg + rr * 128 + ((((lane >> 2) ^ (rr & 7))) << 4) + colw);
           const float2 f = Cvt<T>::unpack2(w);
           if (ok) {
-            st_s0 += f.x; st_q0 = fmaf(f.x, f.x, st_q0);
-            st_s1 += f.y; st_q1 = fmaf(f.y, f.y, st_q1);
+            t_s0 += f.x; t_q0 = fmaf(f.x, f.x, t_q0);
+            t_s1 += f.y; t_q1 = fmaf(f.y, f.y, t_q1);
           }
         }
+        st_s0 += stat_fix(t_s0, kStatSumScale); st_q0 += stat_fix(t_q0, kStatSqScale);
+        st_s1 += stat_fix(t_s1, kStatSumScale); st_q1 += stat_fix(t_q1, kStatSqScale);
       }
     }
     if (EPI == EPI_RAW_STATS) flush_stats(st_n);

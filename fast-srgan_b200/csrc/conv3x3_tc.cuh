@@ -44,7 +44,7 @@ struct ConvParams {
   int num_tiles;            // N * tiles_y * tiles_x
   void* out;                // see ConvEpilogue
   const float* bias;        // [cout_total] in GEMM column order, or nullptr
-  float* stats;             // [N][cout_total][2] fp32 (sum, sumsq), EPI_RAW_STATS
+  long long* stats;         // [N][cout_total][2] fixed-point int64 (sum * 2^24, sumsq * 2^20), EPI_RAW_STATS
   const float* alpha;       // device pointer to the PReLU slope (ACT_PRELU)
   float slope;              // LeakyReLU slope (ACT_LRELU)
   int act;                  // ActMode (EPI_BIAS_ACT)
@@ -292,17 +292,19 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     if (EPI == EPI_PS_PRELU || (EPI == EPI_BIAS_ACT && p.act == ACT_PRELU)) prelu_a = __ldg(p.alpha);
     const float slope = (EPI == EPI_PS_PRELU || p.act == ACT_PRELU) ? prelu_a : p.slope;
     // InstanceNorm statistics of channels (2*lane, 2*lane+1) of the current image, carried across tiles
-    float st_s0 = 0.f, st_q0 = 0.f, st_s1 = 0.f, st_q1 = 0.f;
+    // (each TILE's partial sums are converted to fixed point before they are added up: the totals are independent of
+    //  how tiles are distributed over warps / CTAs / launches -> batch-size and run-to-run invariant)
+    long long st_s0 = 0, st_q0 = 0, st_s1 = 0, st_q1 = 0;
     int st_n = -1;
     auto flush_stats = [&](int img) {
       if (EPI == EPI_RAW_STATS && img >= 0) {
-        float* st = p.stats + ((size_t)img * p.cout_total + slice * NS + 2 * lane) * 2;
-        atomicAdd(st + 0, st_s0);
-        atomicAdd(st + 1, st_q0);
-        atomicAdd(st + 2, st_s1);
-        atomicAdd(st + 3, st_q1);
+        long long* st = p.stats + ((size_t)img * p.cout_total + slice * NS + 2 * lane) * 2;
+        stat_atomic_add(st + 0, st_s0);
+        stat_atomic_add(st + 1, st_q0);
+        stat_atomic_add(st + 2, st_s1);
+        stat_atomic_add(st + 3, st_q1);
       }
-      st_s0 = st_q0 = st_s1 = st_q1 = 0.f;
+      st_s0 = st_q0 = st_s1 = st_q1 = 0;
     };
     int it = 0;
     for (int t = t_begin; t < t_end; ++t, ++it) {
@@ -444,8 +446,8 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
             }
             warp_reduce64(v, lane);
             warp_reduce64(sq, lane);
-            st_s0 += v[0]; st_q0 += sq[0];
-            st_s1 += v[1]; st_q1 += sq[1];
+            st_s0 += stat_fix(v[0], kStatSumScale); st_q0 += stat_fix(sq[0], kStatSqScale);
+            st_s1 += stat_fix(v[1], kStatSumScale); st_q1 += stat_fix(sq[1], kStatSqScale);
           }
         }
       }

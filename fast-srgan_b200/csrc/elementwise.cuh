@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(TPP == 2 ? 256 : 128, TPP == 2 ? 3 : 1) neck_c
 // accumulated by the producing conv's epilogue.  grid = (blocks_per_image, N).
 struct InApplyParams {
   const void* raw;
-  const float* stats;
+  const long long* stats;  // [N][C][2] fixed-point (see stat_atomic_add)
   const void* residual;  // nullable
   void* out;
   const float* alpha;    // PReLU slope pointer
@@ -122,14 +122,8 @@ __global__ void __launch_bounds__(256) instnorm_apply_kernel(const InApplyParams
   float* s_mean = s_ms;
   float* s_rstd = s_ms + p.C;
   const int n = blockIdx.y;
-  const float inv_hw = 1.0f / (float)p.HW;
   for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
-    const float sum = p.stats[((size_t)n * p.C + c) * 2 + 0];
-    const float sq = p.stats[((size_t)n * p.C + c) * 2 + 1];
-    const float m = sum * inv_hw;
-    const float var = fmaxf(sq * inv_hw - m * m, 0.f);   // biased variance (InstanceNorm2d)
-    s_mean[c] = m;
-    s_rstd[c] = rsqrtf(var + p.eps);
+    stat_mean_rstd(p.stats + ((size_t)n * p.C + c) * 2, 1.0 / (double)p.HW, p.eps, s_mean[c], s_rstd[c]);
   }
   __syncthreads();
   const float slope = (p.act == ACT_PRELU) ? __ldg(p.alpha) : p.slope;

@@ -242,6 +242,23 @@ struct Cvt<__nv_bfloat16> {
   FSR_DEVINL static __nv_bfloat16 from_f(float v) { return __float2bfloat16_rn(v); }
 };
 
+// InstanceNorm statistics are accumulated as 64-bit FIXED-POINT integers: integer atomics are associative, so the
+// result does not depend on the order in which warps / CTAs arrive -> the forward pass is bitwise reproducible
+// (fp32 atomics made it differ run to run at 1e-7, which 16-bit rounding + kinked activations amplify chaotically).
+constexpr double kStatSumScale = 16777216.0;    // 2^24  (|sum|   < 5.5e11)
+constexpr double kStatSqScale = 1048576.0;      // 2^20  (sum sq  < 8.8e12)
+FSR_DEVINL long long stat_fix(float v, double scale) { return __double2ll_rn((double)v * scale); }
+FSR_DEVINL void stat_atomic_add(long long* dst, long long v) {
+  atomicAdd(reinterpret_cast<unsigned long long*>(dst), (unsigned long long)v);
+}
+FSR_DEVINL void stat_mean_rstd(const long long* st, double inv_count, float eps, float& mean, float& rstd) {
+  const double m = (double)st[0] / kStatSumScale * inv_count;
+  double var = (double)st[1] / kStatSqScale * inv_count - m * m;   // biased variance (InstanceNorm2d), in fp64
+  if (var < 0.0) var = 0.0;
+  mean = (float)m;
+  rstd = (float)(1.0 / sqrt(var + (double)eps));
+}
+
 FSR_DEVINL float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(256) smooth_l1_f32_kernel(const float* __restr
 // pass 1: per (n,c) sums S1 = sum g, S2 = sum g*xhat  (+ PReLU slope gradient sum_{xhat<0} dY*xhat)
 struct InBwdParams {
   const void* raw;       // conv output (pre-norm) NHWC
-  const float* stats;    // [N][C][2] sum, sumsq from the forward
+  const long long* stats; // [N][C][2] fixed-point sum, sumsq from the forward
   const void* dy;        // gradient w.r.t. the block output NHWC
   float* red;            // [N][C][2] S1, S2 (zeroed by the caller)
   void* draw;            // pass 2 output NHWC
@@ -254,10 +254,7 @@ __global__ void __launch_bounds__(256) instnorm_bwd_kernel(const InBwdParams p) 
   const int n = blockIdx.y;
   const float inv_hw = 1.0f / (float)p.HW;
   for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
-    const float sum = p.stats[((size_t)n * p.C + c) * 2 + 0], sq = p.stats[((size_t)n * p.C + c) * 2 + 1];
-    const float m = sum * inv_hw;
-    s_mean[c] = m;
-    s_rstd[c] = rsqrtf(fmaxf(sq * inv_hw - m * m, 0.f) + p.eps);
+    stat_mean_rstd(p.stats + ((size_t)n * p.C + c) * 2, 1.0 / (double)p.HW, p.eps, s_mean[c], s_rstd[c]);
     if (PASS == 1) { s_a[c] = 0.f; s_b[c] = 0.f; }
     else {
       s_a[c] = p.red[((size_t)n * p.C + c) * 2 + 0] * inv_hw;

@@ -9,6 +9,20 @@ import torch
 from . import _lib as L
 
 
+STAT_SUM_SCALE, STAT_SQ_SCALE = float(2 ** 24), float(2 ** 20)
+
+
+def stats_to_float(stats: torch.Tensor) -> torch.Tensor:
+    """[N,C,2] int64 fixed point (sum * 2^24, sumsq * 2^20) -> float64 (sum, sumsq)."""
+    scale = torch.tensor([STAT_SUM_SCALE, STAT_SQ_SCALE], dtype=torch.float64, device=stats.device)
+    return stats.double() / scale
+
+
+def stats_from_float(sums: torch.Tensor, sumsq: torch.Tensor) -> torch.Tensor:
+    """(sum, sumsq) [N,C] -> the kernels' [N,C,2] int64 fixed-point statistics buffer."""
+    return torch.stack([(sums.double() * STAT_SUM_SCALE).round(), (sumsq.double() * STAT_SQ_SCALE).round()], dim=-1).to(torch.int64).contiguous()
+
+
 def _cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
@@ -39,7 +53,7 @@ def conv3x3_c64_raw_stats(x: torch.Tensor, w_packed: torch.Tensor, stats: Option
     cout = w_packed.shape[1]
     out = torch.empty((N, H, W, cout), dtype=x.dtype, device=x.device)
     if stats is None:
-        stats = torch.zeros((N, cout, 2), dtype=torch.float32, device=x.device)
+        stats = torch.zeros((N, cout, 2), dtype=torch.int64, device=x.device)
     L.check(L.load().fsr_conv3x3_c64(x.data_ptr(), w_packed.data_ptr(), out.data_ptr(), None, stats.data_ptr(), None,
                                      N, H, W, cout, L.EPI_RAW_STATS, 0, 0.0, 0, L.dtype_code(x.dtype),
                                      L.stream_ptr(x.device)), "conv3x3 raw+stats")
@@ -184,7 +198,7 @@ def conv3x3_gen(x, w_packed, cout, stride=1, mode=0, epilogue=L.EPI_BIAS_ACT, bi
         H, W = 2 * H2, 2 * W2
         out = torch.empty((N, 4, H2, W2, cout), dtype=x.dtype, device=x.device)
     if epilogue == L.EPI_RAW_STATS and stats is None:
-        stats = torch.zeros((N, cout, 2), dtype=torch.float32, device=x.device)
+        stats = torch.zeros((N, cout, 2), dtype=torch.int64, device=x.device)
     L.check(L.load().fsr_conv3x3_gen(x.data_ptr(), w_packed.data_ptr(), out.data_ptr(), L.ptr(bias), L.ptr(stats), L.ptr(alpha),
                                      N, H, W, cin, cout, stride, mode, epilogue, act, slope, dt, L.stream_ptr(x.device)),
             "conv3x3_gen")

@@ -52,14 +52,15 @@ int fsr_pack_conv3x3_weight(const float* w_oihw, const float* bias, void* w_pack
  * conv1/conv2), :87-93 (bottleneck), :103-108 (head).
  *   x        [N,H,W,64] NHWC dtype        w_packed  from fsr_pack_conv3x3_weight
  *   epilogue FSR_EPI_*:
- *     RAW_STATS : out [N,H,W,cout] dtype, stats [N,cout,2] fp32 += (sum, sumsq)   (caller zeroes stats)
+ *     RAW_STATS : out [N,H,W,cout] dtype, stats [N,cout,2] int64 FIXED POINT += (sum * 2^24, sumsq * 2^20); caller zeroes
+ *                 (integer atomics are order independent: the forward pass is bitwise reproducible)
  *     BIAS_ACT  : out [N,H,W,cout] dtype = act(conv + bias)
  *     PS_PRELU  : cout = 256: out [N,2H,2W,64] dtype = PReLU(PixelShuffle2(conv + bias)); alpha = device ptr
  *     HEAD_TANH : cout_pad = 16 (3 real): out fp32 [N,3,H,W] (out_u8=0) or uint8 [N,H,W,3] (out_u8=1);
  *                 out_u8=2|3: no tanh, fp32 NCHW store | accumulate (the 64->3 data gradients of the
  *                 3-channel first layers: VGG conv1_1, Discriminator.neck)
  */
-int fsr_conv3x3_c64(const void* x, const void* w_packed, void* out, const float* bias, float* stats,
+int fsr_conv3x3_c64(const void* x, const void* w_packed, void* out, const float* bias, int64_t* stats,
                     const float* alpha, int N, int H, int W, int cout, int epilogue, int act, float slope,
                     int out_u8, int dtype, void* stream);
 
@@ -72,7 +73,7 @@ int fsr_conv3x3_c64(const void* x, const void* w_packed, void* out, const float*
  *   mode 1, stride 1: x = dY [N,H,W,cin=Cout_fwd]; w packed with transpose=1 -> out = dX [N,H,W,cout=Cin_fwd]
  *   mode 1, stride 2: x = dY [N,H/2,W/2,cin]; out = dX in parity-plane layout [N][4][H/2][W/2][cout]
  * epilogue: FSR_EPI_RAW_STATS (out + InstanceNorm sum/sumsq) or FSR_EPI_BIAS_ACT. */
-int fsr_conv3x3_gen(const void* x, const void* w_packed, void* out, const float* bias, float* stats,
+int fsr_conv3x3_gen(const void* x, const void* w_packed, void* out, const float* bias, int64_t* stats,
                     const float* alpha, int N, int H, int W, int cin, int cout, int stride, int mode, int epilogue,
                     int act, float slope, int dtype, void* stream);
 
@@ -87,8 +88,8 @@ int fsr_neck_conv3x3(const void* x, const float* w, const float* bias, const flo
 /* InstanceNorm2d(affine=False, eps) normalise from conv-epilogue statistics, fused with the following
  * activation and residual add: out = act((raw-mean)*rstd) (+ residual).
  * Replaces model.py:55-56 (bn1+relu1), :65+:69 (bn2 + skip), :94+:115 (bottleneck IN + long skip),
- * :132-133 (SimpleBlock bn + LeakyReLU).  raw/out/residual NHWC dtype [N,HW,C]; stats [N,C,2] fp32. */
-int fsr_instnorm_apply(const void* raw, const float* stats, const void* residual, void* out, const float* alpha,
+ * :132-133 (SimpleBlock bn + LeakyReLU).  raw/out/residual NHWC dtype [N,HW,C]; stats [N,C,2] int64 fixed point. */
+int fsr_instnorm_apply(const void* raw, const int64_t* stats, const void* residual, void* out, const float* alpha,
                        int N, int HW, int C, int act, float slope, float eps, int dtype, void* stream);
 
 /* torch.nn.PixelShuffle(2) (model.py:36) on NHWC: in [N,H,W,4C] (reference channel order) -> out [N,2H,2W,C]. */
@@ -138,7 +139,7 @@ int fsr_smooth_l1(const void* a, const void* b, size_t n, float* loss_acc, void*
 
 /* InstanceNorm2d (+PReLU|LeakyReLU) backward (model.py:55-56,65,94,132-133): from the conv output `raw`, its forward
  * statistics and dY, writes dRaw; PReLU slope gradient accumulated into dalpha.  red = [N][C][2] fp32 scratch. */
-int fsr_instnorm_bwd(const void* raw, const float* stats, const void* dy, float* red, void* draw, const float* alpha,
+int fsr_instnorm_bwd(const void* raw, const int64_t* stats, const void* dy, float* red, void* draw, const float* alpha,
                      float* dalpha, int N, int HW, int C, int act, float slope, float eps, int dtype, void* stream);
 /* activation backward from the stored post-activation tensor (neck PReLU / LeakyReLU). */
 int fsr_act_bwd(const void* y, const void* dy, void* dv, size_t n_elems, const float* alpha, float slope, int act,

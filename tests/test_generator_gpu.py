@@ -50,8 +50,8 @@ def test_generator_vs_oracle_shapes(shape, L):
 
 
 def test_generator_l2_groups_identical():
-    """Processing the residual chain in L2-sized image groups changes nothing but the (unordered)
-    fp32 atomic accumulation order of the InstanceNorm statistics: results agree to <= 5e-4."""
+    """Processing the residual chain in L2-sized image groups must not change a single bit (InstanceNorm statistics
+    are accumulated with order-independent fixed-point integer atomics)."""
     g, _ = make(64, 3, torch.float16)
     x = seeded((5, 3, 24, 40), 5).cuda()
     with torch.no_grad():
@@ -59,7 +59,7 @@ def test_generator_l2_groups_identical():
         a = g(x).clone()
         g.l2_group = 2
         b = g(x).clone()
-    assert (a - b).abs().max().item() <= 1e-3
+    assert torch.equal(a, b)
 
 
 def test_generator_uint8_pipeline():
@@ -82,5 +82,5 @@ def test_generator_batch_independence_fullsize():
     with torch.no_grad():
         full = g(x)
         single = g(x[1:2])
-    assert (full[1:2] - single).abs().max().item() <= 1e-3   # fp32 atomics order only
+    assert torch.equal(full[1:2], single)                   # bitwise: integer (fixed-point) statistics atomics
     assert torch.isfinite(full).all() and full.abs().max().item() <= 1.0

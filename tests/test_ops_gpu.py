@@ -56,10 +56,15 @@ def test_conv3x3_raw_stats(dt, shape):
     assert (got - ref).abs().max().item() <= 2 * EPS[dt] * scale + 1e-5
     # InstanceNorm statistics are accumulated (fp32) over the STORED, rounded outputs: exact w.r.t. those
     # (up to fp32 summation order), and within rounding noise of the fp32 conv
+    assert stats.dtype == torch.int64                      # fixed point: order-independent integer atomics
+    stats_i = stats
+    stats = ops.stats_to_float(stats).float()
     s_got = torch.stack([got.sum((2, 3)), (got * got).sum((2, 3))], dim=-1)
     assert torch.allclose(stats, s_got, rtol=1e-4, atol=1e-3)
     s_ref = torch.stack([ref.sum((2, 3)), (ref * ref).sum((2, 3))], dim=-1)
     assert torch.allclose(stats, s_ref, rtol=4 * EPS[dt], atol=4 * EPS[dt] * scale * (H * W) ** 0.5 + 1e-3)
+    raw2, stats2 = ops.conv3x3_c64_raw_stats(x, wp)        # bitwise reproducible run to run
+    assert torch.equal(raw2, raw) and torch.equal(stats2, stats_i)
 
 
 @pytest.mark.parametrize("dt", DTYPES)
@@ -150,7 +155,7 @@ def test_instnorm_apply(dt, mode):
     N, H, W, C = 2, 13, 21, 64
     raw = nhwc(rnd((N, C, H, W), 17, 3.0) + 0.7, dt)
     rf = nchw_f32(raw)
-    stats = torch.stack([rf.sum((2, 3)), (rf * rf).sum((2, 3))], dim=-1).contiguous()
+    stats = ops.stats_from_float(rf.sum((2, 3)), (rf * rf).sum((2, 3)))
     alpha = torch.tensor([0.3], device="cuda")
     res = nhwc(rnd((N, C, H, W), 18), dt)
     ref = F.instance_norm(rf, eps=1e-5)

@@ -189,3 +189,37 @@ def test_cuda_graph_train_step_matches_eager():
     print("eager losses", le[-1].tolist(), "graph losses", lg[-1].tolist())
     assert (le - lg).abs().max().item() <= 2e-2
     assert (ge - gg).abs().max().item() <= 5 * 2.05e-4 and (de - dg).abs().max().item() <= 5 * 2.05e-4
+
+
+def test_gradients_shard_exactly_over_batch():
+    """Size-independent property behind the multi-GPU path: every op is per-sample, losses are batch means,
+    so grad(full batch) == mean over shards of grad(shard).  Checked on the discriminator step at BASELINE-like size."""
+    from fast_srgan_b200.trainer import Trainer
+    cfg = ns(experiment=ns(name="t", seed=0), generator=ns(n_filters=64, n_layers=2), discriminator=ns(n_filters=64, n_layers=7),
+             training=ns(device="cuda", generator_lr=1e-4, discriminator_lr=1e-4))
+    tr = Trainer(cfg, compute_dtype=torch.bfloat16)
+    tr.generator.load_state_dict(O.make_generator_state(64, 2, 1234))
+    tr.discriminator.load_state_dict(O.make_discriminator_state(64, 4321))
+    tr.perceptual_network.load_state_dict(O.make_vgg19_state(99))
+    e = tr.engine
+    B = 16
+    g = torch.Generator().manual_seed(77)
+    lr = (torch.rand((B, 3, 24, 24), generator=g) * 2 - 1).cuda()
+    hr = (torch.rand((B, 3, 96, 96), generator=g) * 2 - 1).cuda()
+    n1, n2, n3 = (torch.rand((B, 36), generator=g).cuda() for _ in range(3))
+
+    def d_grad(sl):
+        e._seg_d((lr[sl].contiguous(), hr[sl].contiguous(), n1[sl].contiguous(), n2[sl].contiguous(), n3[sl].contiguous()))
+        torch.cuda.synchronize()
+        return e.dp.grad.clone()
+
+    full = d_grad(slice(0, B))
+    halves = 0.5 * (d_grad(slice(0, B // 2)) + d_grad(slice(B // 2, B)))
+    rel = ((full - halves).norm() / full.norm()).item()
+    again = d_grad(slice(0, B))
+    noise = ((full - again).norm() / full.norm()).item()
+    print("full-batch vs mean-of-shards D gradient: rel-L2", rel, " run-to-run", noise)
+    # the forward is bitwise reproducible and batch-size invariant (fixed-point statistics); the backward's fp32
+    # atomics (split-K weight gradients, InstanceNorm-backward sums) reorder sums, which flips a few bf16 roundings of
+    # the propagated gradient: measured 2e-3 run to run, and sharding adds nothing on top of that
+    assert noise <= 6e-3 and rel <= max(2.0 * noise, 6e-3)
