@@ -168,15 +168,12 @@ def bench_train_step(args, rank, world, dev, dist):
     all-reduce per network per step.  Device-timed, max over ranks."""
     import types
     from fast_srgan_b200.trainer import Trainer
-    import srgan_oracle as O
     ns = types.SimpleNamespace
     B = 64 if world == 1 else 32
     cfg = ns(experiment=ns(name="bench", seed=0), generator=ns(n_filters=NF, n_layers=NL), discriminator=ns(n_filters=64, n_layers=7),
              training=ns(device=str(dev), generator_lr=1e-4, discriminator_lr=1e-4))
-    tr = Trainer(cfg, compute_dtype=torch.bfloat16)
-    tr.generator.load_state_dict(O.make_generator_state(NF, NL, seed=1234))
-    tr.discriminator.load_state_dict(O.make_discriminator_state(64, seed=4321))
-    tr.perceptual_network.load_state_dict(O.make_vgg19_state(seed=99))
+    torch.manual_seed(1234)                       # same random init on every rank (replicas must start identical)
+    tr = Trainer(cfg, compute_dtype=torch.bfloat16)   # G, D: torch default init; VGG19: torchvision's init (no ImageNet download)
     g = torch.Generator().manual_seed(7 + rank)
     lr = (torch.rand((B, 3, 24, 24), generator=g) * 2 - 1).to(dev)
     hr = (torch.rand((B, 3, 96, 96), generator=g) * 2 - 1).to(dev)
@@ -259,12 +256,9 @@ def main():
     import types
     from fast_srgan_b200 import _lib as L
     from fast_srgan_b200.model import Generator
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import srgan_oracle as O   # only for deterministic random-init weights (not on the timed path)
-
     dt = torch.float16 if args.dtype == "fp16" else torch.bfloat16
+    torch.manual_seed(1234)                       # reference configs/config.yaml:3; random-init weights (torch default init)
     gen = Generator(types.SimpleNamespace(n_filters=NF, n_layers=NL), compute_dtype=dt)
-    gen.load_state_dict(O.make_generator_state(NF, NL, seed=1234))
     gen = gen.to(dev).eval()
     gen.l2_group = args.l2_group
     lib = L.load()

@@ -55,6 +55,7 @@ _SIGS = {
     "fsr_bias_grad_nchw": (_i, [_fp, _fp, _i, _i, _sz, _vp]),
     "fsr_adamw": (_i, [_fp, _fp, _fp, _fp, _sz, _f, _f, _f, _f, _f, _i, _f, _vp]),
     "fsr_adamw_dev": (_i, [_fp, _fp, _fp, _fp, _sz, _f, _f, _f, _f, _f, _vp, _f, _vp]),
+    "fsr_conv3x3_head": (_i, [_vp, _vp, _vp, _fp, _i, _i, _i, _i, _i, _i, _vp]),
     "fsr_neck_conv3x3": (_i, [_vp, _fp, _fp, _fp, _vp, _i, _i, _i, _i, _i, _f, _i, _i, _i, _vp]),
     "fsr_instnorm_apply": (_i, [_vp, _fp, _vp, _vp, _fp, _i, _i, _i, _i, _f, _f, _i, _vp]),
     "fsr_pixel_shuffle2": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),

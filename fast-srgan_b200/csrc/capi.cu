@@ -181,7 +181,7 @@ int launch_conv_mode(const void* x, const void* w_packed, int w_rows, const Conv
 
 // 3-output-channel conv as 1x1 GEMM + shift-add epilogue (conv3x3_head.cuh)
 template <typename T>
-int launch_head(const void* x, const void* w_packed, ConvParams p, int dtype, cudaStream_t st) {
+int launch_head(const void* x, const void* w_packed, ConvParams p, int dtype, cudaStream_t st, int cin = 64) {
   auto kern = conv3x3_head_kernel<T>;
   static bool attr_done = false;
   if (!attr_done) {
@@ -192,13 +192,14 @@ int launch_head(const void* x, const void* w_packed, ConvParams p, int dtype, cu
   p.tiles_y = (p.H + HeadCfg::TH - 1) / HeadCfg::TH;
   p.num_tiles = p.N * p.tiles_x * p.tiles_y;
   CUtensorMap tmx;
-  int rc = make_act_map(&tmx, x, p.N, p.H, p.W, 64, HeadCfg::BW, HeadCfg::BH, dtype);
+  if (cin % 64 || cin > 64 * HeadCfg::kMaxKC) return FSR_ERR_BAD_SHAPE;
+  int rc = make_act_map(&tmx, x, p.N, p.H, p.W, cin, HeadCfg::BW, HeadCfg::BH, dtype);
   if (rc) return rc;
   int grid = num_sms();
   if (grid > p.num_tiles) grid = p.num_tiles;
   {
     LaunchScope scope(FSR_K_CONV_HEAD, st);
-    kern<<<grid, HeadCfg::kThreads, HeadCfg::kSmemBytes, st>>>(tmx, reinterpret_cast<const T*>(w_packed), p);
+    kern<<<grid, HeadCfg::kThreads, HeadCfg::kSmemBytes, st>>>(tmx, reinterpret_cast<const T*>(w_packed), p, cin);
   }
   return cuda_rc(cudaGetLastError());
 }
@@ -268,8 +269,12 @@ int gen_dispatch(const void* x, const void* w_packed, void* out, const float* bi
   if (stride != 1 && stride != 2) return FSR_ERR_BAD_ARG;
   if (stride == 2 && ((H | W) & 1)) return FSR_ERR_BAD_SHAPE;
   if (epilogue == FSR_EPI_RAW_STATS && !stats) return FSR_ERR_BAD_ARG;
-  if (epilogue != FSR_EPI_RAW_STATS && epilogue != FSR_EPI_BIAS_ACT) return FSR_ERR_BAD_ARG;
+  if (epilogue != FSR_EPI_RAW_STATS && epilogue != FSR_EPI_BIAS_ACT && epilogue != FSR_EPI_PS_PRELU) return FSR_ERR_BAD_ARG;
   GenParams p{};
+  if (epilogue == FSR_EPI_PS_PRELU) {          // UpSamplingBlock with F != 64: bias + PReLU + pixel-shuffle scatter
+    if (stride != 1 || mode != 0 || cout % 256 || !alpha) return FSR_ERR_BAD_ARG;
+    p.ps = 1; act = FSR_ACT_PRELU; epilogue = FSR_EPI_BIAS_ACT;
+  }
   p.N = N; p.cin = cin; p.cout_total = cout; p.num_slices = cout / 64;
   p.bias = bias; p.stats = stats; p.alpha = alpha; p.slope = slope; p.act = act;
   CUtensorMap maps[4], tmw;
@@ -295,7 +300,7 @@ int gen_dispatch(const void* x, const void* w_packed, void* out, const float* bi
         K.taps[r * 3 + s2].wrow = r * 3 + s2;
         K.taps[r * 3 + s2].a_off = mode == 0 ? r * 10 + s2 : (2 - r) * 10 + (2 - s2);
       }
-    return finish(H, W, out, (long long)H * W * cout, true);
+    return finish(H, W, out, p.ps ? (long long)4 * H * W * (cout / 4) : (long long)H * W * cout, true);
   }
   if (mode == 0) {
     // stride-2 forward: x is in parity-plane layout [N][4][H2][W2][cin]; input row 2y+r-1:
@@ -458,6 +463,16 @@ int fsr_conv3x3_gen(const void* x, const void* w_packed, void* out, const float*
   if (dtype == FSR_BF16)
     return gen_dispatch<__nv_bfloat16>(x, w_packed, out, bias, reinterpret_cast<long long*>(stats), alpha, N, H, W, cin, cout, stride, mode, epilogue, act, slope, dtype, st);
   return gen_dispatch<__half>(x, w_packed, out, bias, reinterpret_cast<long long*>(stats), alpha, N, H, W, cin, cout, stride, mode, epilogue, act, slope, dtype, st);
+}
+
+int fsr_conv3x3_head(const void* x, const void* w_packed, void* out, const float* bias, int N, int H, int W, int cin,
+                     int out_mode, int dtype, void* stream) {
+  if (!x || !w_packed || !out || out_mode < 0 || out_mode > 3) return FSR_ERR_BAD_ARG;
+  ConvParams p{};
+  p.N = N; p.H = H; p.W = W; p.out = out; p.bias = bias; p.out_u8 = out_mode; p.cout_total = 16; p.num_slices = 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == FSR_BF16) return launch_head<__nv_bfloat16>(x, w_packed, p, dtype, st, cin);
+  return launch_head<__half>(x, w_packed, p, dtype, st, cin);
 }
 
 int fsr_neck_conv3x3(const void* x, const float* w, const float* bias, const float* alpha, void* out, int N, int H,

@@ -50,6 +50,8 @@ struct GenParams {
   const float* alpha;
   float slope;
   int act;
+  int ps;                   // 1: PixelShuffle(2) scatter store (UpSamplingBlock with F != 64): GEMM columns are packed
+                            //    (2i+j)*F + c, out = [N, 2Ho, 2Wo, F = cout_total/4]
 };
 
 template <int MAXTAPS>
@@ -253,8 +255,16 @@ conv3x3_gen_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_const
         const int mm = q * 32 + rrow;
         const int py = y0 + mm / TW, px = x0 + mm % TW;
         if (interior || (py < p.Ho && px < p.Wo)) {
-          T* dst = reinterpret_cast<T*>(p.out) + (size_t)n * p.out_img_stride +
-                   ((size_t)py * p.Wo + px) * p.cout_total + col0;
+          T* dst;
+          if (p.ps) {
+            const int F = p.cout_total >> 2;
+            const int qq = col0 / F, c0 = col0 - qq * F;
+            dst = reinterpret_cast<T*>(p.out) + (size_t)n * p.out_img_stride +
+                  ((size_t)(2 * py + (qq >> 1)) * (2 * p.Wo) + 2 * px + (qq & 1)) * F + c0;
+          } else {
+            dst = reinterpret_cast<T*>(p.out) + (size_t)n * p.out_img_stride +
+                  ((size_t)py * p.Wo + px) * p.cout_total + col0;
+          }
           *reinterpret_cast<uint4*>(dst + (lane & 7) * 8) = val[j];
         }
       }

@@ -17,7 +17,8 @@ struct HeadCfg {
   static constexpr int kHaloRows = BW * BH;                 // 180
   static constexpr int kStageBytes = 23552;                 // 184 rows, 1024-aligned
   static constexpr int kStages = 5;
-  static constexpr int kWBytes = 32 * 128;                  // B tile: 32 rows (tap*3+c) x 64 ch
+  static constexpr int kMaxKC = 8;                          // Cin <= 512
+  static constexpr int kWBytes = kMaxKC * 32 * 128;         // B tiles: per 64-channel chunk 32 rows (tap*3+c) x 64 ch
   static constexpr int kZPitch = 33;                        // floats per halo pixel (odd -> conflict-free column reads)
   static constexpr int kZBytes = ((kHaloRows * kZPitch * 4 + 1023) / 1024) * 1024;   // 24576
   static constexpr int kEpiWarps = 8;
@@ -40,8 +41,9 @@ FSR_DEVINL float ld_shared_f32(uint32_t addr) {
 
 template <typename T>
 __global__ void __launch_bounds__(HeadCfg::kThreads, 1)
-conv3x3_head_kernel(const __grid_constant__ CUtensorMap tm_x, const T* __restrict__ w_packed /*[9][16][64]*/,
-                    const ConvParams p) {
+conv3x3_head_kernel(const __grid_constant__ CUtensorMap tm_x, const T* __restrict__ w_packed /*[9][16][cin]*/,
+                    const ConvParams p, const int cin) {
+  const int KC = cin >> 6;
   using Cfg = HeadCfg;
   constexpr int TH = Cfg::TH, TW = Cfg::TW;
   extern __shared__ uint8_t smem_raw[];
@@ -72,14 +74,14 @@ conv3x3_head_kernel(const __grid_constant__ CUtensorMap tm_x, const T* __restric
   }
   if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
   // B tile: row j = tap*3 + c  <-  w_packed[tap][c][0..63]; 128B-swizzled like a TMA write (chunk ^= row & 7)
-  for (int i = threadIdx.x; i < 32 * 8; i += blockDim.x) {
-    const int row = i >> 3, ch = i & 7;
+  for (int i = threadIdx.x; i < KC * 32 * 8; i += blockDim.x) {
+    const int kc = i >> 8, row = (i >> 3) & 31, ch = i & 7;
     uint4 v = make_uint4(0, 0, 0, 0);
     if (row < 27) {
       const int tap = row / 3, c = row % 3;
-      v = *reinterpret_cast<const uint4*>(w_packed + ((size_t)tap * 16 + c) * 64 + ch * 8);
+      v = *reinterpret_cast<const uint4*>(w_packed + ((size_t)tap * 16 + c) * cin + kc * 64 + ch * 8);
     }
-    *reinterpret_cast<uint4*>(smem_w + row * 128 + ((ch ^ (row & 7)) << 4)) = v;
+    *reinterpret_cast<uint4*>(smem_w + kc * 4096 + row * 128 + ((ch ^ (row & 7)) << 4)) = v;
   }
   if (threadIdx.x < 4) smem_bias[threadIdx.x] = (p.bias != nullptr && threadIdx.x < 3) ? p.bias[threadIdx.x] : 0.f;
   fence_proxy_async();        // generic-proxy smem writes (B tile) -> visible to the tensor core (async proxy)
@@ -95,13 +97,15 @@ conv3x3_head_kernel(const __grid_constant__ CUtensorMap tm_x, const T* __restric
       const int n = t / tiles_per_img;
       const int rem = t - n * tiles_per_img;
       const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
-      mbar_wait(&empty_bar[stage], phase ^ 1);
-      if (elect_one()) {
-        mbar_arrive_expect_tx(&full_bar[stage], Cfg::kHaloRows * 128);
-        tma_load_4d(smem_a + stage * Cfg::kStageBytes, &tm_x, &full_bar[stage], 0, tx * TW - 1, ty * TH - 1, n);
+      for (int kc = 0; kc < KC; ++kc) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kHaloRows * 128);
+          tma_load_4d(smem_a + stage * Cfg::kStageBytes, &tm_x, &full_bar[stage], kc * 64, tx * TW - 1, ty * TH - 1, n);
+        }
+        __syncwarp();
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
-      __syncwarp();
-      if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
@@ -115,24 +119,27 @@ conv3x3_head_kernel(const __grid_constant__ CUtensorMap tm_x, const T* __restric
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
-      mbar_wait(&full_bar[stage], phase);
-      tc_fence_after();
-      const uint32_t a_lo = a_lo0 + stage * (Cfg::kStageBytes >> 4);
-      if (elect_one()) {
+      for (int kc = 0; kc < KC; ++kc) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t a_lo = a_lo0 + stage * (Cfg::kStageBytes >> 4);
+        const uint32_t b_lo = b_lo0 + kc * (4096 >> 4);
+        if (elect_one()) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {          // halo rows [0,128) and [128,256) (rows >= 180 are never read back)
+          for (int h = 0; h < 2; ++h) {          // halo rows [0,128) and [128,256) (rows >= 180 are never read back)
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t adesc = desc_join(a_lo + ((h * 128 * 128 + k * 32) >> 4), kDescHiSw128);
-            const uint64_t bdesc = desc_join(b_lo0 + ((k * 32) >> 4), kDescHiSw128);
-            umma_f16(tmem_base + acc * 64 + h * 32, adesc, bdesc, idesc, k != 0 ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t adesc = desc_join(a_lo + ((h * 128 * 128 + k * 32) >> 4), kDescHiSw128);
+              const uint64_t bdesc = desc_join(b_lo + ((k * 32) >> 4), kDescHiSw128);
+              umma_f16(tmem_base + acc * 64 + h * 32, adesc, bdesc, idesc, (k | kc) != 0 ? 1u : 0u);
+            }
           }
+          umma_commit(&empty_bar[stage]);
+          if (kc == KC - 1) umma_commit(&tfull_bar[acc]);
         }
-        umma_commit(&empty_bar[stage]);
-        umma_commit(&tfull_bar[acc]);
+        __syncwarp();
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
-      __syncwarp();
-      if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
     }
   } else {
     // =============================== epilogue: Z -> smem, shift-add, tanh, store ===============================

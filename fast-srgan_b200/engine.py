@@ -82,6 +82,9 @@ class GeneratorNet:
     """model.py:72-117 forward (saving activations) and backward."""
 
     def __init__(self, module, fp: FlatParams, dtype: torch.dtype):
+        if module.n_filters != 64:
+            raise RuntimeError("the training engine (backward kernels) is built for generator.n_filters == 64; "
+                               "other widths are supported for inference only")
         self.m, self.fp, self.dt = module, fp, dtype
         self.L = module.n_layers
         self._packed_version = -1

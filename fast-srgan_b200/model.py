@@ -124,47 +124,65 @@ class Generator(torch.nn.Module):
                   ("head", self.head[0])]
         return convs
 
+    def _effective_weights(self):
+        """fp32 OIHW tensors padded with zero channels up to a multiple of 64 (the kernels work on 64-channel = 128-byte
+        pixel rows).  Zero channels stay exactly zero through conv / InstanceNorm ((0-0)*rsqrt(0+eps)) / PReLU / pixel
+        shuffle, so the result equals the unpadded network; for n_filters = 32 this costs 4x the ideal FLOPs (reported
+        as such in the config sweep)."""
+        F_, Fp = self.n_filters, self.padded_filters
+
+        def pad(t, o, i=None):
+            t = t.detach().float()
+            shape = list(t.shape)
+            shape[0] = o
+            if i is not None:
+                shape[1] = i
+            out = torch.zeros(shape, dtype=torch.float32, device=t.device)
+            out[tuple(slice(0, d) for d in t.shape)] = t
+            return out
+
+        eff = {}
+        for name, conv in self._conv_list():
+            w, b = conv.weight, conv.bias
+            if name == "neck":
+                eff[name] = (pad(w, Fp), pad(b, Fp))
+            elif name.startswith("up"):
+                eff[name] = (pad(w, 4 * Fp, Fp), pad(b, 4 * Fp))        # reference channel 4c+q keeps its index (c < F)
+            elif name == "head":
+                eff[name] = (pad(w, 3, Fp), b.detach().float())
+            else:
+                eff[name] = (pad(w, Fp, Fp), None)
+        return eff
+
     def _pack(self):
         """(Re)pack OIHW fp32 parameters into the kernel layout when they changed."""
         dev = self.neck[0].weight.device
         key = (str(dev), self.compute_dtype) + tuple((c.weight._version, c.weight.data_ptr()) for _, c in self._conv_list())
         if key == self._packed_key:
             return
-        if self.n_filters != 64:
-            raise RuntimeError("this build of libfsr_b200 supports generator.n_filters == 64 only")
-        lib, dt = L.load(), L.dtype_code(self.compute_dtype)
-        st = L.stream_ptr(dev)
+        from . import ops
+        Fp, dt = self.padded_filters, self.compute_dtype
         pk: Dict[str, torch.Tensor] = {}
-
-        def pack(name, conv, cout_pad, ps):
-            cout, cin = conv.weight.shape[0], conv.weight.shape[1]
-            w = conv.weight.detach().float().contiguous()
-            b = conv.bias.detach().float().contiguous() if conv.bias is not None else None
-            wp = torch.empty(9 * cout_pad * cin, dtype=self.compute_dtype, device=dev)
-            bp = torch.empty(cout_pad, dtype=torch.float32, device=dev) if b is not None else None
-            L.check(lib.fsr_pack_conv3x3_weight(L.ptr(w), L.ptr(b), L.ptr(wp), L.ptr(bp), cout, cin, cout_pad, ps, dt, st),
-                    f"pack {name}")
-            pk[name + ".w"] = wp
-            if bp is not None:
-                pk[name + ".b"] = bp
-
-        for name, conv in self._conv_list():
+        for name, (w, b) in self._effective_weights().items():
             if name == "neck":
-                pk["neck.w"] = conv.weight.detach().float().contiguous()
-                pk["neck.b"] = conv.bias.detach().float().contiguous()
+                pk["neck.w"], pk["neck.b"] = w.contiguous(), b.contiguous()
             elif name.startswith("up"):
-                pack(name, conv, 256, 1)
+                pk[name + ".w"], pk[name + ".b"] = ops.pack_conv3x3(w, b, dt, ps_perm=True)
             elif name == "head":
-                pack(name, conv, 16, 0)
+                pk[name + ".w"], pk[name + ".b"] = ops.pack_conv3x3(w, b, dt, cout_pad=16)
             else:
-                pack(name, conv, 64, 0)
+                pk[name + ".w"], _ = ops.pack_conv3x3(w, None, dt)
         self._packed, self._packed_key = pk, key
+
+    @property
+    def padded_filters(self) -> int:
+        return (self.n_filters + 63) // 64 * 64
 
     def _params_struct(self) -> "L.FsrGeneratorParams":
         self._pack()
         pk = self._packed
         P = L.FsrGeneratorParams()
-        P.n_filters, P.n_layers, P.dtype = self.n_filters, self.n_layers, L.dtype_code(self.compute_dtype)
+        P.n_filters, P.n_layers, P.dtype = self.padded_filters, self.n_layers, L.dtype_code(self.compute_dtype)
         P.neck_w, P.neck_b = pk["neck.w"].data_ptr(), pk["neck.b"].data_ptr()
         P.neck_alpha = self.neck[1].weight.data_ptr()
         for i, blk in enumerate(self.stem):
@@ -179,8 +197,27 @@ class Generator(torch.nn.Module):
         P.head_w, P.head_b = pk["head.w"].data_ptr(), pk["head.b"].data_ptr()
         return P
 
+    def _forward_wide(self, x: torch.Tensor, out: torch.Tensor, in_u8: int, out_u8: int):
+        """n_filters > 64 (multiples of 64 after padding): the same graph on the general-channel kernels."""
+        from . import ops
+        self._pack()
+        pk, dt, Fp = self._packed, self.compute_dtype, self.padded_filters
+        a0 = ops.neck_conv3x3(x, pk["neck.w"], pk["neck.b"], dt, act=L.ACT_PRELU, alpha=self.neck[1].weight)
+        cur = a0
+        for i, blk in enumerate(self.stem):
+            raw, st = ops.conv3x3_gen(cur, pk[f"s{i}a.w"], Fp, epilogue=L.EPI_RAW_STATS)
+            y = ops.instnorm_apply(raw, st, act=L.ACT_PRELU, alpha=blk.relu1.weight)
+            raw, st = ops.conv3x3_gen(y, pk[f"s{i}b.w"], Fp, epilogue=L.EPI_RAW_STATS)
+            cur = ops.instnorm_apply(raw, st, residual=cur)
+        raw, st = ops.conv3x3_gen(cur, pk["bott.w"], Fp, epilogue=L.EPI_RAW_STATS)
+        cur = ops.instnorm_apply(raw, st, residual=a0)
+        for i in range(2):
+            cur = ops.conv3x3_gen(cur, pk[f"up{i}.w"], 4 * Fp, epilogue=L.EPI_PS_PRELU, bias=pk[f"up{i}.b"],
+                                  alpha=self.upsampling[i].relu.weight)
+        return ops.conv3x3_head(cur, pk["head.w"], pk["head.b"], out_mode=out_u8, out=out)
+
     def _workspace(self, N, H, W, dev):
-        need = L.load().fsr_generator_workspace_bytes(N, H, W, self.n_filters, self.n_layers)
+        need = L.load().fsr_generator_workspace_bytes(N, H, W, self.padded_filters, self.n_layers)
         if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
             self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
         return self._ws, need
@@ -188,6 +225,10 @@ class Generator(torch.nn.Module):
     def _run(self, x: torch.Tensor, out: torch.Tensor, N, H, W, in_u8, out_u8):
         if self.n_layers > L.FSR_MAX_LAYERS:
             raise RuntimeError(f"n_layers > {L.FSR_MAX_LAYERS} not supported")
+        if self.padded_filters > 512:
+            raise RuntimeError("generator.n_filters > 512 is not supported by this build")
+        if self.padded_filters != 64:
+            return self._forward_wide(x, out, in_u8, out_u8)
         P = self._params_struct()
         ws, need = self._workspace(N, H, W, x.device)
         rc = L.load().fsr_generator_forward(P, x.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel(), N, H, W,

@@ -188,7 +188,10 @@ def conv3x3_gen(x, w_packed, cout, stride=1, mode=0, epilogue=L.EPI_BIAS_ACT, bi
     cin = x.shape[-1]
     if stride == 1:
         N, H, W, _ = x.shape
-        out = torch.empty((N, H, W, cout), dtype=x.dtype, device=x.device)
+        if epilogue == L.EPI_PS_PRELU:
+            out = torch.empty((N, 2 * H, 2 * W, cout // 4), dtype=x.dtype, device=x.device)
+        else:
+            out = torch.empty((N, H, W, cout), dtype=x.dtype, device=x.device)
     elif mode == 0:
         N, _, H2, W2, _ = x.shape
         H, W = 2 * H2, 2 * W2
@@ -369,3 +372,15 @@ def adamw_dev(p, g, m, v, lr, step_dev, b1=0.9, b2=0.999, eps=1e-8, wd=1e-2, gra
     _cuda(p, g, m, v, step_dev)
     L.check(L.load().fsr_adamw_dev(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, b1, b2, eps, wd,
                                    step_dev.data_ptr(), grad_scale, L.stream_ptr(p.device)), "adamw_dev")
+
+
+def conv3x3_head(x, w_packed, bias_packed, out_mode: int = 0, out=None):
+    """Generator.head for any channel count (cin multiple of 64): x NHWC [N,H,W,cin], w_packed [9][16][cin]."""
+    _cuda(x, w_packed, bias_packed)
+    N, H, W, C = x.shape
+    if out is None:
+        out = torch.empty((N, H, W, 3), dtype=torch.uint8, device=x.device) if out_mode == 1 else \
+            torch.empty((N, 3, H, W), dtype=torch.float32, device=x.device)
+    L.check(L.load().fsr_conv3x3_head(x.data_ptr(), w_packed.data_ptr(), out.data_ptr(), L.ptr(bias_packed), N, H, W, C,
+                                      out_mode, L.dtype_code(x.dtype), L.stream_ptr(x.device)), "conv3x3 head")
+    return out

@@ -72,10 +72,16 @@ int fsr_conv3x3_c64(const void* x, const void* w_packed, void* out, const float*
  *   mode 0, stride 2: x in parity-plane layout [N][4][H/2][W/2][cin] -> out [N,H/2,W/2,cout] NHWC
  *   mode 1, stride 1: x = dY [N,H,W,cin=Cout_fwd]; w packed with transpose=1 -> out = dX [N,H,W,cout=Cin_fwd]
  *   mode 1, stride 2: x = dY [N,H/2,W/2,cin]; out = dX in parity-plane layout [N][4][H/2][W/2][cout]
- * epilogue: FSR_EPI_RAW_STATS (out + InstanceNorm sum/sumsq) or FSR_EPI_BIAS_ACT. */
+ * epilogue: FSR_EPI_RAW_STATS (out + InstanceNorm sum/sumsq), FSR_EPI_BIAS_ACT, or FSR_EPI_PS_PRELU (mode 0, stride 1,
+ * cout = 4F packed with ps_perm: bias + PReLU + PixelShuffle(2) -> out [N,2H,2W,F]; the UpSamplingBlock for F != 64). */
 int fsr_conv3x3_gen(const void* x, const void* w_packed, void* out, const float* bias, int64_t* stats,
                     const float* alpha, int N, int H, int W, int cin, int cout, int stride, int mode, int epilogue,
                     int act, float slope, int dtype, void* stream);
+
+/* Conv2d(cin -> 3, k3, p1) (+ tanh): Generator.head for any n_filters (model.py:102-110), cin multiple of 64 (<= 512),
+ * w_packed [9][16][cin] (3 real rows).  out_mode: 0 tanh -> fp32 NCHW, 1 tanh -> uint8 NHWC, 2|3 linear store|accumulate. */
+int fsr_conv3x3_head(const void* x, const void* w_packed, void* out, const float* bias, int N, int H, int W, int cin,
+                     int out_mode, int dtype, void* stream);
 
 /* Conv2d(3 -> cout, k3, p1) + bias + activation, direct (HBM-bound; K = 27 is no tensor-core shape).
  * Replaces model.py:75-78 (Generator.neck, PReLU) and :143-146 (Discriminator.neck, LeakyReLU 0.2);

@@ -62,3 +62,19 @@ def test_cpu_input_raises():
     with pytest.raises(RuntimeError):
         with torch.no_grad():
             g(torch.zeros(1, 3, 8, 8))
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    """No CPU / PyTorch fallback: without the built .so the product path raises instead of computing elsewhere."""
+    from fast_srgan_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libfsr_b200.so")
+    with pytest.raises(RuntimeError, match="no CPU"):
+        _lib.load()
+
+
+def test_product_package_never_imports_the_oracle():
+    import glob
+    for f in glob.glob(os.path.join(ROOT, "fast-srgan_b200", "*.py")):
+        src = open(f).read()
+        assert "srgan_oracle" not in src and "import oracle" not in src, f

@@ -84,3 +84,29 @@ def test_generator_batch_independence_fullsize():
         single = g(x[1:2])
     assert torch.equal(full[1:2], single)                   # bitwise: integer (fixed-point) statistics atomics
     assert torch.isfinite(full).all() and full.abs().max().item() <= 1.0
+
+
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+def test_generator_f32_vs_reference_golden(golden, dt):
+    """n_filters = 32 (BASELINE config #5): zero-padded to 64-channel rows; must equal the unpadded reference network."""
+    g, sd = make(32, 2, dt)
+    x = seeded((2, 3, 9, 13), 7)
+    with torch.no_grad():
+        y = g(x.cuda()).cpu()
+    err = np.abs(y.numpy() - golden["g32x2_y"]).max()
+    print(f"generator F=32 {dt} vs reference golden: max-abs {err:.3e}")
+    assert err <= TOL[dt]
+
+
+@pytest.mark.parametrize("F,L,shape", [(128, 2, (2, 3, 24, 40)), (128, 4, (1, 3, 37, 21)), (32, 8, (1, 3, 45, 80))])
+def test_generator_other_widths_vs_oracle(F, L, shape):
+    """n_filters = 128 runs on the general-channel kernels (res convs, pixel-shuffle epilogue, K-looped head)."""
+    g, sd = make(F, L, torch.float16)
+    x = seeded(shape, 17)
+    with torch.no_grad():
+        y = g(x.cuda()).cpu()
+        ref = O.generator_forward(sd, x)
+        u8 = g.super_resolve_u8(((x.permute(0, 2, 3, 1) + 1) * 127.5).round().clamp(0, 255).to(torch.uint8).cuda()).cpu()
+    err = (y - ref).abs().max().item()
+    print(f"generator F={F} L={L} {shape}: max-abs {err:.3e}")
+    assert y.shape == ref.shape and err <= 1e-3 and u8.shape == (shape[0], 4 * shape[2], 4 * shape[3], 3)
