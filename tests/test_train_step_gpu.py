@@ -55,8 +55,19 @@ def test_vgg_forward(golden, dt, tol):
     assert y.shape == ref.shape and err <= tol
 
 
+_ORACLE_CACHE = {}
+
+
 def _oracle_step(B, storage=None):
-    """fp64 oracle of one step; storage=dtype additionally rounds every stored tensor like a 16-bit engine would."""
+    """fp64 oracle of one step; storage=dtype additionally rounds every stored tensor like a 16-bit engine would.
+    (cached: the CPU fp64 step is the slowest part of the GPU test-suite)"""
+    if (B, storage) not in _ORACLE_CACHE:
+        _ORACLE_CACHE[(B, storage)] = _oracle_step_uncached(B, storage)
+    res, og, od, lr_img, hr_img, noise = _ORACLE_CACHE[(B, storage)]
+    return res, {k: v.clone() for k, v in og.items()}, {k: v.clone() for k, v in od.items()}, lr_img, hr_img, noise
+
+
+def _oracle_step_uncached(B, storage=None):
     import contextlib
     c = lambda sd: {k: v.double().clone() for k, v in sd.items()}
     og, od, ov = c(O.make_generator_state(64, 8, 1234)), c(O.make_discriminator_state(64, 4321)), c(O.make_vgg19_state(99))
