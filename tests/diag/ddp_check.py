@@ -1,4 +1,4 @@
-"""torchrun --nproc-per-node 2 tools/ddp_check.py : N-rank sharded train_step == 1-rank full-batch train_step.
+"""torchrun --nproc-per-node 2 tests/diag/ddp_check.py : N-rank sharded train_step == 1-rank full-batch train_step.
 Each rank also runs the FULL batch alone (no collective) and compares parameters after the step."""
 import os
 import sys
@@ -7,7 +7,7 @@ import types
 import torch
 import torch.distributed as dist
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import srgan_oracle as O  # noqa: E402

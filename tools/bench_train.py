@@ -10,8 +10,6 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "oracle"))
-import srgan_oracle as O  # noqa: E402
 from fast_srgan_b200 import _lib as L  # noqa: E402
 from fast_srgan_b200 import distributed as D  # noqa: E402
 from fast_srgan_b200.trainer import Trainer  # noqa: E402
@@ -27,10 +25,8 @@ torch.cuda.set_device(local)
 ns = types.SimpleNamespace
 cfg = ns(experiment=ns(name="b", seed=0), generator=ns(n_filters=64, n_layers=8), discriminator=ns(n_filters=64, n_layers=7),
          training=ns(device=f"cuda:{local}", generator_lr=1e-4, discriminator_lr=1e-4))
+torch.manual_seed(1234)     # torch default init, identical on every rank
 tr = Trainer(cfg, compute_dtype=torch.float16 if args.dtype == "fp16" else torch.bfloat16)
-tr.generator.load_state_dict(O.make_generator_state(64, 8, 1234))
-tr.discriminator.load_state_dict(O.make_discriminator_state(64, 4321))
-tr.perceptual_network.load_state_dict(O.make_vgg19_state(99))
 B = args.batch
 g = torch.Generator().manual_seed(rank)
 lr = (torch.rand((B, 3, 24, 24), generator=g) * 2 - 1).cuda()

@@ -7,8 +7,6 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "oracle"))
-import srgan_oracle as O  # noqa: E402
 from fast_srgan_b200.model import Generator  # noqa: E402
 
 iters = int(sys.argv[1]) if len(sys.argv) > 1 else 2
@@ -16,7 +14,6 @@ batch = int(sys.argv[2]) if len(sys.argv) > 2 else 32
 h, w = (int(sys.argv[3]), int(sys.argv[4])) if len(sys.argv) > 4 else (180, 320)
 dt = torch.bfloat16 if os.environ.get("FSR_DTYPE", "fp16") == "bf16" else torch.float16
 g = Generator(types.SimpleNamespace(n_filters=64, n_layers=8), compute_dtype=dt)
-g.load_state_dict(O.make_generator_state(64, 8, seed=1234))
 g = g.cuda().eval()
 x = (torch.rand((batch, 3, h, w)) * 2 - 1).cuda()
 with torch.no_grad():

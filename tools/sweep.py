@@ -11,8 +11,6 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "oracle"))
-import srgan_oracle as O  # noqa: E402
 from fast_srgan_b200.model import Generator  # noqa: E402
 
 peak = 1425.0
@@ -23,7 +21,6 @@ print("| n_filters | n_layers | input | GFLOP/frame | ms/batch(32) | frames/s | 
 print("|---|---|---|---|---|---|---|---|")
 for F, L in [(f, l) for f in (32, 64, 128) for l in (4, 8, 12, 16)]:
     g = Generator(types.SimpleNamespace(n_filters=F, n_layers=L), compute_dtype=torch.float16)
-    g.load_state_dict(O.make_generator_state(F, L, seed=1))
     g = g.cuda().eval()
     for (h, w) in ((90, 160), (180, 320)):
         x = (torch.rand((B, 3, h, w)) * 2 - 1).cuda()
