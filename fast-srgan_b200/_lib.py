@@ -66,6 +66,7 @@ _SIGS = {
     "fsr_launch_count": (C.c_ulonglong, []),
     "fsr_set_halo_mode": (_i, [_i]),
     "fsr_set_ws_mode": (_i, [_i]),
+    "fsr_set_small_mma": (_i, [_i]),
     "fsr_set_overlap_streams": (_i, [_i]),
     "fsr_generator_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "fsr_generator_forward": (_i, [C.POINTER(FsrGeneratorParams), _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _i, _vp]),

@@ -6,6 +6,7 @@
 #include "conv3x3_wgrad.cuh"
 #include "train_kernels.cuh"
 #include "elementwise.cuh"
+#include "small_mma.cuh"
 
 #include <cudaTypedefs.h>
 #include <atomic>
@@ -134,6 +135,15 @@ int ws_mode() {
     g_ws = (e && e[0] == '0') ? 0 : 1;   // default on: B200-measured ~5 % on the 64->64 conv, bit-identical results
   }
   return g_ws;
+}
+
+int g_small_mma = -1;   // 3-channel-sided convs (neck / wgrad_c3): 1 = mma.sync tensor-core kernels (small_mma.cuh), 0 = CUDA cores
+int small_mma_mode() {
+  if (g_small_mma < 0) {
+    const char* e = getenv("FSR_SMALL_MMA");
+    g_small_mma = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_small_mma;
 }
 
 template <int NS, int EPI, typename T, bool HALO1>
@@ -483,6 +493,15 @@ int fsr_neck_conv3x3(const void* x, const float* w, const float* bias, const flo
   const size_t total = (size_t)N * H * W;
   cudaStream_t st = (cudaStream_t)stream;
   LaunchScope scope(FSR_K_NECK, st);
+  if (small_mma_mode()) {            // one warp per 16-pixel row strip, >= 4 strips per warp, <= 3 blocks per SM
+    const long long strips = (long long)N * H * ((W + 15) / 16);
+    long long bx = (strips + 4 * kNeckWarps - 1) / (4 * kNeckWarps);
+    if (bx > (long long)num_sms() * 3) bx = (long long)num_sms() * 3;
+    dim3 grid((unsigned)bx, cout / 64);
+    if (dtype == FSR_BF16) neck_conv3x3_mma_kernel<__nv_bfloat16><<<grid, kNeckWarps * 32, 0, st>>>(p);
+    else neck_conv3x3_mma_kernel<__half><<<grid, kNeckWarps * 32, 0, st>>>(p);
+    return cuda_rc(cudaGetLastError());
+  }
   if (total > (size_t)1 << 20) {     // large frames/batches: one thread per pixel
     dim3 grid((unsigned)((total + 127) / 128), cout / 64);
     if (dtype == FSR_BF16) neck_conv3x3_kernel<__nv_bfloat16, 1><<<grid, 128, 0, st>>>(p);
@@ -573,6 +592,11 @@ unsigned long long fsr_launch_count(void) { return g_launches.load(); }
 
 int fsr_set_ws_mode(int weight_stationary) {
   g_ws = weight_stationary < 0 ? -1 : (weight_stationary ? 1 : 0);   // -1: back to the environment default
+  return FSR_OK;
+}
+
+int fsr_set_small_mma(int on) {
+  g_small_mma = on < 0 ? -1 : (on ? 1 : 0);   // -1: back to the environment default (FSR_SMALL_MMA)
   return FSR_OK;
 }
 
@@ -878,6 +902,16 @@ int fsr_wgrad_c3(const float* img, const void* act, float* out, int N, int H, in
   if (bx < 1) bx = 1;
   dim3 grid(bx, C64 / 64);
   LaunchScope scope(FSR_K_NONE - 1, st);
+  if (small_mma_mode()) {
+    if (total >= ((size_t)1 << 31) - 16) return FSR_ERR_BAD_SHAPE;
+    const long long steps = (long long)((total + 15) / 16);
+    long long mb = (steps + 8 * kWgc3Warps - 1) / (8 * kWgc3Warps);      // >= 8 steps per warp
+    if (mb > (long long)num_sms() * 3) mb = (long long)num_sms() * 3;
+    dim3 mgrid((unsigned)mb, C64 / 64);
+    FSR_T((wgrad_c3_mma_kernel<__half><<<mgrid, kWgc3Warps * 32, 0, st>>>(img, (const __half*)act, out, N, H, W, C64, flip, layout)),
+          (wgrad_c3_mma_kernel<__nv_bfloat16><<<mgrid, kWgc3Warps * 32, 0, st>>>(img, (const __nv_bfloat16*)act, out, N, H, W, C64, flip, layout)));
+    return cuda_rc(cudaGetLastError());
+  }
   FSR_T((wgrad_c3_kernel<__half><<<grid, 224, 0, st>>>(img, (const __half*)act, out, N, H, W, C64, flip, layout)),
         (wgrad_c3_kernel<__nv_bfloat16><<<grid, 224, 0, st>>>(img, (const __nv_bfloat16*)act, out, N, H, W, C64, flip, layout)));
   return cuda_rc(cudaGetLastError());

@@ -223,6 +223,11 @@ int fsr_set_halo_mode(int single_halo_tile);
  * per two pixel tiles (collector buffer reuse).  Default on (environment FSR_WS=0 disables; -1 = environment default). */
 int fsr_set_ws_mode(int weight_stationary);
 
+/* 1 (default): the 3-channel-sided convs (fsr_neck_conv3x3, fsr_wgrad_c3) run on warp-level tensor-core MMAs
+ * (mma.sync m16n8k16, fp32 operand split hi+lo: fp32-input accuracy); 0: the CUDA-core kernels (A/B and tests);
+ * -1: environment default (FSR_SMALL_MMA). */
+int fsr_set_small_mma(int on);
+
 #ifdef __cplusplus
 }
 #endif
