@@ -7,6 +7,7 @@
 #include "train_kernels.cuh"
 #include "elementwise.cuh"
 #include "small_mma.cuh"
+#include "aux_kernels.cuh"
 
 #include <cudaTypedefs.h>
 #include <atomic>
@@ -961,6 +962,44 @@ int fsr_adamw_dev(float* p, const float* g, float* m, float* v, size_t n, float 
   }
   LaunchScope scope(FSR_K_NONE - 1, st);
   adamw_dev_kernel<<<ew_blocks(n), 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, wd, step_dev, grad_scale);
+  return cuda_rc(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------ section-8 "next" rows: validation metrics, data path
+int fsr_psnr_ssim(const float* pred, const float* target, int N, int C, int H, int W, float scale, float shift,
+                  float data_range, const float* taps11_host, double* sse, double* ssim_sum, void* stream) {
+  if (!pred || !target || !taps11_host || !sse || !ssim_sum) return FSR_ERR_BAD_ARG;
+  if (N <= 0 || C <= 0 || H < 11 || W < 11 || (long long)N * C > 65535) return FSR_ERR_BAD_SHAPE;
+  MetricParams p{};
+  p.pred = pred; p.target = target; p.N = N; p.C = C; p.H = H; p.W = W; p.scale = scale; p.shift = shift;
+  p.c1 = (0.01f * data_range) * (0.01f * data_range);
+  p.c2 = (0.03f * data_range) * (0.03f * data_range);
+  for (int i = 0; i < 11; ++i) p.g[i] = taps11_host[i];
+  p.sse = sse; p.ssim_sum = ssim_sum;
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid((unsigned)((W - 10 + 15) / 16), (unsigned)((H - 10 + 15) / 16), (unsigned)(N * C));
+  LaunchScope scope(FSR_K_NONE - 1, st);
+  psnr_ssim_kernel<<<grid, 256, 0, st>>>(p);
+  return cuda_rc(cudaGetLastError());
+}
+
+int fsr_crop_resize_aa(const uint8_t* cache, const int64_t* img_off, const int32_t* img_h, const int32_t* img_w,
+                       const int32_t* samples, int B, int lr_size, int scale, const int32_t* tap_min,
+                       const int32_t* tap_size, const float* tap_w, int K, float* lr, float* hr, void* stream) {
+  if (!cache || !img_off || !img_h || !img_w || !samples || !tap_min || !tap_size || !tap_w || !lr || !hr) return FSR_ERR_BAD_ARG;
+  if (B <= 0 || lr_size <= 0 || scale <= 0 || K <= 0) return FSR_ERR_BAD_SHAPE;
+  const size_t hr_size = (size_t)lr_size * scale;
+  const size_t smem = (hr_size * hr_size + 15) / 16 * 16 + hr_size * lr_size * sizeof(float);
+  if (smem > 200 * 1024) return FSR_ERR_BAD_SHAPE;
+  static size_t s_attr = 48 * 1024;
+  if (smem > s_attr) {
+    FSR_CUDA(cudaFuncSetAttribute(crop_resize_aa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    s_attr = smem;
+  }
+  CropResizeParams p{cache, (const long long*)img_off, img_h, img_w, samples, tap_min, tap_size, tap_w, lr, hr, B, lr_size, scale, K};
+  cudaStream_t st = (cudaStream_t)stream;
+  LaunchScope scope(FSR_K_NONE - 1, st);
+  crop_resize_aa_kernel<<<dim3((unsigned)B, 3), 256, smem, st>>>(p);
   return cuda_rc(cudaGetLastError());
 }
 

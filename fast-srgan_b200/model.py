@@ -243,9 +243,9 @@ class Generator(torch.nn.Module):
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         self._require_cuda(x)
-        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
-            from .autograd import generator_forward_train   # training path (hand-written backward kernels)
-            return generator_forward_train(self, x)
+        if torch.is_grad_enabled() and x.requires_grad:
+            raise RuntimeError("autograd through fast_srgan_b200 modules is not supported: use Trainer.train_step / "
+                               "pretrain_step (hand-written backward kernels, trainer.py:104-111, 168-196)")
         x = x.contiguous().float()
         N, C, H, W = x.shape
         if C != 3:

@@ -5,8 +5,10 @@
   pretrain_step(lr, hr)           - one iteration of trainer.py:104-111
   pretrain(...) / train(...)      - the loops of trainer.py:89-141 / :158-233 over a dataloader
   save_checkpoints(step)          - the four files of trainer.py:143-156
-TensorBoard / torchmetrics logging (trainer.py:17,46-78,198-233) is observability, not compute: scalars
-are returned to the caller instead (out of scope).
+  calculate_metrics_over_dataset(dl) - SSIM / PSNR over a validation loader, trainer.py:53-69, on the fused CUDA
+                                    metric kernel (metrics.py) instead of torchmetrics
+TensorBoard logging (trainer.py:17,70-78,198-233) is observability, not compute: scalars are returned to the
+caller / collected in `self.history` instead (out of scope).
 Multi-GPU: construct under torchrun after torch.distributed.init_process_group("nccl"); each rank feeds its
 own shard of the mini-batch, gradients are summed with one NCCL all-reduce per network per step.
 """
@@ -18,6 +20,7 @@ from typing import Dict, Optional
 import torch
 
 from .engine import GANEngine
+from .metrics import ValidationMetrics
 from .model import VGG19, Discriminator, Generator
 
 
@@ -39,6 +42,8 @@ class Trainer:
         self._engine: Optional[GANEngine] = None
         self._noise_gen = torch.Generator(device=dev)
         self._noise_gen.manual_seed(int(getattr(getattr(config, "experiment", None), "seed", 0) or 0))
+        self.metrics = ValidationMetrics(dev, data_range=1.0)          # trainer.py:46-51
+        self.history: list = []                                        # (phase, step, dict) instead of the SummaryWriter
 
     @property
     def engine(self) -> GANEngine:
@@ -65,16 +70,47 @@ class Trainer:
     def pretrain_step(self, lr_images: torch.Tensor, hr_images: torch.Tensor):
         return self.engine.pretrain_step(lr_images.to(self.device, non_blocking=True), hr_images.to(self.device, non_blocking=True))
 
+    @torch.no_grad()
+    def calculate_metrics_over_dataset(self, dataloader, phase: str = "GAN", step: int = 0) -> Dict[str, float]:
+        """trainer.py:53-69 `_calculate_metrics_over_dataset`: generator in eval mode over the whole loader,
+        sr = (1 + G(lr))/2 against (1 + hr)/2; returns {"ssim": mean per-image SSIM, "psnr": PSNR of the pooled MSE}."""
+        was_training = self.generator.training
+        self.generator.eval()
+        self.metrics.reset()
+        for lr_images, hr_images in dataloader:
+            lr_images = lr_images.to(self.device, non_blocking=True)
+            hr_images = hr_images.to(self.device, non_blocking=True)
+            self.metrics.update(self.generator(lr_images), hr_images, rescale=True)   # trainer.py:64-66
+        out = self.metrics.compute()
+        res = {"ssim": out["ssim"], "psnr": out["psnr"]}
+        self.history.append((phase, step, res))
+        self.generator.train(was_training)
+        return res
+
+    def _every(self, name: str, step: int) -> bool:
+        n = int(getattr(self.config.training, name, 0) or 0)
+        return n > 0 and step % n == 0
+
     def pretrain(self, train_dataloader, val_dataloader=None):
+        if val_dataloader is not None:
+            self.calculate_metrics_over_dataset(val_dataloader, "Pretrain", 0)            # trainer.py:95
         last = None
-        for lr_images, hr_images in train_dataloader:                  # trainer.py:99-111
+        for step, (lr_images, hr_images) in enumerate(train_dataloader, start=1):          # trainer.py:99-111
             last = self.pretrain_step(lr_images, hr_images)
+            if val_dataloader is not None and self._every("checkpoint_iter", step):
+                self.calculate_metrics_over_dataset(val_dataloader, "Pretrain", step)     # trainer.py:126
         return last
 
     def train(self, train_dataloader, val_dataloader=None):
+        if val_dataloader is not None:
+            self.calculate_metrics_over_dataset(val_dataloader, "GAN", 0)                 # trainer.py:159
         last = None
-        for lr_images, hr_images in train_dataloader:                  # trainer.py:165-196
+        for step, (lr_images, hr_images) in enumerate(train_dataloader, start=1):          # trainer.py:165-196
             last = self.train_step(lr_images, hr_images)
+            if self._every("checkpoint_iter", step):
+                if val_dataloader is not None:
+                    self.calculate_metrics_over_dataset(val_dataloader, "GAN", step)      # trainer.py:231
+                self.save_checkpoints(step)                                               # trainer.py:232
         return last
 
     def save_checkpoints(self, step: int):

@@ -223,6 +223,27 @@ int fsr_set_halo_mode(int single_halo_tile);
  * per two pixel tiles (collector buffer reuse).  Default on (environment FSR_WS=0 disables; -1 = environment default). */
 int fsr_set_ws_mode(int weight_stationary);
 
+/* ---- rows SURVEY.md section 8 marks "next" --------------------------------------------------------------------
+ * Validation metrics.  Replaces the torchmetrics objects of trainer.py:46-51 as used at trainer.py:60-68
+ * (PeakSignalNoiseRatio / StructuralSimilarityIndexMeasure, data_range given, 11x11 gaussian sigma 1.5, reduction
+ * "none"): ONE fused pass over pred / target (fp32 NCHW, device), each mapped v -> scale*v + shift first
+ * (trainer.py:64-66: scale = shift = 0.5).  Accumulates (+=, double, device): sse[0] = sum (p-t)^2 over everything,
+ * ssim_sum[n] = sum of image n's SSIM map over C x (H-10) x (W-10) valid window positions.  The caller forms
+ * PSNR = 10 log10(dr^2 * numel / sse) and SSIM_n = ssim_sum[n] / (C (H-10)(W-10)).  taps11_host: 11 normalised gaussian
+ * taps in HOST memory (copied into the launch parameters).  H, W >= 11, N*C <= 65535. */
+int fsr_psnr_ssim(const float* pred, const float* target, int N, int C, int H, int W, float scale, float shift,
+                  float data_range, const float* taps11_host, double* sse, double* ssim_sum, void* stream);
+
+/* Data path.  Replaces NumpyImagesDataset.__getitem__ (dataloader.py:24-38) for a whole batch on a device-resident
+ * uint8 image cache: sample b = (image index, crop_y, crop_x) -> hr[b] = crop/127.5 - 1 (fp32 NCHW [B,3,hr,hr],
+ * hr = lr_size*scale) and lr[b] = antialiased-bicubic(crop -> lr_size x lr_size)/127.5 - 1 (torch
+ * `_upsample_bicubic2d_aa`, what v2.Resize(antialias=True, BICUBIC) runs on a float tensor).  cache: uint8 CHW images back
+ * to back, img_off/img_h/img_w per image; tap_min/tap_size/tap_w[lr_size][K]: the per-output-index tap table of the
+ * hr -> lr resize (device memory; same table for rows and columns).  Out-of-range crops are clamped into the image. */
+int fsr_crop_resize_aa(const uint8_t* cache, const int64_t* img_off, const int32_t* img_h, const int32_t* img_w,
+                       const int32_t* samples, int B, int lr_size, int scale, const int32_t* tap_min,
+                       const int32_t* tap_size, const float* tap_w, int K, float* lr, float* hr, void* stream);
+
 /* 1 (default): the 3-channel-sided convs (fsr_neck_conv3x3, fsr_wgrad_c3) run on warp-level tensor-core MMAs
  * (mma.sync m16n8k16, fp32 operand split hi+lo: fp32-input accuracy); 0: the CUDA-core kernels (A/B and tests);
  * -1: environment default (FSR_SMALL_MMA). */
