@@ -496,11 +496,20 @@ int fsr_neck_conv3x3(const void* x, const float* w, const float* bias, const flo
   LaunchScope scope(FSR_K_NECK, st);
   if (small_mma_mode()) {            // one warp per 16-pixel row strip, >= 4 strips per warp, <= 3 blocks per SM
     const long long strips = (long long)N * H * ((W + 15) / 16);
+    if (strips >= ((long long)1 << 31) - 1) return FSR_ERR_BAD_SHAPE;
     long long bx = (strips + 4 * kNeckWarps - 1) / (4 * kNeckWarps);
     if (bx > (long long)num_sms() * 3) bx = (long long)num_sms() * 3;
     dim3 grid((unsigned)bx, cout / 64);
-    if (dtype == FSR_BF16) neck_conv3x3_mma_kernel<__nv_bfloat16><<<grid, kNeckWarps * 32, 0, st>>>(p);
-    else neck_conv3x3_mma_kernel<__half><<<grid, kNeckWarps * 32, 0, st>>>(p);
+#define FSR_NECK_MMA(T)                                                                                       \
+  do {                                                                                                        \
+    if (in_u8) neck_conv3x3_mma_kernel<T, true, false><<<grid, kNeckWarps * 32, 0, st>>>(p);                  \
+    else if (vgg_norm) neck_conv3x3_mma_kernel<T, false, true><<<grid, kNeckWarps * 32, 0, st>>>(p);          \
+    else neck_conv3x3_mma_kernel<T, false, false><<<grid, kNeckWarps * 32, 0, st>>>(p);                       \
+  } while (0)
+    if (in_u8 && vgg_norm) return FSR_ERR_BAD_ARG;
+    if (dtype == FSR_BF16) FSR_NECK_MMA(__nv_bfloat16);
+    else FSR_NECK_MMA(__half);
+#undef FSR_NECK_MMA
     return cuda_rc(cudaGetLastError());
   }
   if (total > (size_t)1 << 20) {     // large frames/batches: one thread per pixel

@@ -49,9 +49,39 @@ FSR_DEVINL void split2(float v0, float v1, uint32_t& hi, uint32_t& lo) {
 // Column c of n-tile j is output channel 16*(c>>1) + 2j + (c&1): every lane then owns 16 CONTIGUOUS channels of its two
 // pixels and stores them as two 16-byte vectors (a warp writes whole 128-byte pixel rows).
 constexpr int kNeckWarps = 4;
-template <typename T>
+
+// One lane's share (6 of the 162 values) of the 3 x 3 x 18 input strip of (image n, row y, columns x0-1 .. x0+16):
+// branch-free predicated loads, so that all six are in flight together (a first version with the uint8 / renormalise /
+// bounds logic as branches serialised the six load latencies: 245 us at b32 180x320).
+template <bool IN_U8, bool VGG>
+FSR_DEVINL void neck_load_strip(const NeckParams& p, int n, int y, int x0, int lane, float (&v)[6]) {
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const int e = lane + 32 * i;
+    const int ci = e / 54, r = (e % 54) / 18, c = e % 18;
+    const int yy = y + r - 1, xx = x0 + c - 1;
+    const bool ok = e < 162 && yy >= 0 && yy < p.H && xx >= 0 && xx < p.W;
+    float val;
+    if (IN_U8) {
+      const size_t idx = ok ? ((size_t)(n * p.H + yy) * p.W + xx) * 3 + ci : 0;
+      const uint8_t u = __ldg(reinterpret_cast<const uint8_t*>(p.x) + idx);
+      val = (float)u / 127.5f - 1.0f;                                         // inference.py:50
+    } else {
+      const size_t idx = ok ? ((size_t)(n * 3 + ci) * p.H + yy) * p.W + xx : 0;
+      val = __ldg(reinterpret_cast<const float*>(p.x) + idx);
+    }
+    if (VGG) {   // model.py:21-22 (same operation order as the CUDA-core kernel)
+      const float mu = ci == 0 ? 0.485f : (ci == 1 ? 0.456f : 0.406f);
+      const float sd = ci == 0 ? 0.229f : (ci == 1 ? 0.224f : 0.225f);
+      val = ((val + 1.0f) / 2.0f - mu) / sd;
+    }
+    v[i] = ok ? val : 0.f;   // zero outside the image: the conv's padding comes after any renormalisation
+  }
+}
+
+template <typename T, bool IN_U8, bool VGG>
 __global__ void __launch_bounds__(kNeckWarps * 32, 3) neck_conv3x3_mma_kernel(const NeckParams p) {
-  __shared__ float s_strip[kNeckWarps][3 * 3 * 18 + 2];
+  __shared__ float s_strip[kNeckWarps][3 * 3 * 18 + 30];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int cg = blockIdx.y;
@@ -68,9 +98,9 @@ __global__ void __launch_bounds__(kNeckWarps * 32, 3) neck_conv3x3_mma_kernel(co
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int k = 16 * ks + 8 * h + 2 * t;
-        const float w0 = k < 27 ? __ldg(wr + k) : 0.f;
-        const float w1 = k + 1 < 27 ? __ldg(wr + k + 1) : 0.f;
-        split2<__half>(w0, w1, bh[ks][j][h], bl[ks][j][h]);
+        const float w0 = __ldg(wr + (k < 27 ? k : 0));
+        const float w1 = __ldg(wr + (k + 1 < 27 ? k + 1 : 0));
+        split2<__half>(k < 27 ? w0 : 0.f, k + 1 < 27 ? w1 : 0.f, bh[ks][j][h], bl[ks][j][h]);
       }
   }
   // ---- per-lane im2col offsets into the strip: k = (ci, r, s) -> ci*54 + r*18 + s (k >= 27: B row is zero, any finite A)
@@ -88,36 +118,25 @@ __global__ void __launch_bounds__(kNeckWarps * 32, 3) neck_conv3x3_mma_kernel(co
   const float slope = (p.act == ACT_PRELU) ? __ldg(p.alpha) : p.slope;
 
   const int tx = (p.W + 15) >> 4;
-  const long long nstrips = (long long)p.N * p.H * tx;
-  const long long warps_total = (long long)gridDim.x * kNeckWarps;
-  for (long long sidx = (long long)blockIdx.x * kNeckWarps + wib; sidx < nstrips; sidx += warps_total) {
-    const int xt = (int)(sidx % tx);
-    const int y = (int)((sidx / tx) % p.H);
-    const int n = (int)(sidx / ((long long)tx * p.H));
-    const int x0 = xt << 4;
-    // stage the 3 x 3 x 18 input strip (zero outside the image: the conv's padding comes after any renormalisation)
+  const int rows = p.N * p.H;                    // host guarantees N*H*tx < 2^31
+  const int nstrips = rows * tx;
+  const int stride = gridDim.x * kNeckWarps;
+  int sidx = blockIdx.x * kNeckWarps + wib;
+  float v[6];
+  if (sidx < nstrips) {
+    const int row = sidx / tx;
+    neck_load_strip<IN_U8, VGG>(p, row / p.H, row % p.H, (sidx - row * tx) << 4, lane, v);
+  }
+  for (; sidx < nstrips; sidx += stride) {
+    const int row = sidx / tx;
+    const int n = row / p.H, y = row - n * p.H, x0 = (sidx - row * tx) << 4;
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      const int e = lane + 32 * i;
-      if (e < 162) {
-        const int ci = e / 54, r = (e % 54) / 18, c = e % 18;
-        const int yy = y + r - 1, xx = x0 + c - 1;
-        float v = 0.f;
-        if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) {
-          if (p.in_u8)
-            v = (float)__ldg(reinterpret_cast<const uint8_t*>(p.x) + ((size_t)(n * p.H + yy) * p.W + xx) * 3 + ci) / 127.5f - 1.0f;
-          else
-            v = __ldg(reinterpret_cast<const float*>(p.x) + ((size_t)(n * 3 + ci) * p.H + yy) * p.W + xx);
-          if (p.vgg_norm) {   // model.py:21-22 (same operation order as the CUDA-core kernel)
-            const float mu = ci == 0 ? 0.485f : (ci == 1 ? 0.456f : 0.406f);
-            const float sd = ci == 0 ? 0.229f : (ci == 1 ? 0.224f : 0.225f);
-            v = ((v + 1.0f) / 2.0f - mu) / sd;
-          }
-        }
-        strip[e] = v;
-      }
-    }
+    for (int i = 0; i < 6; ++i) strip[lane + 32 * i] = v[i];       // 192 slots (162 used)
     __syncwarp();
+    if (sidx + stride < nstrips) {   // next strip's loads fly during this strip's MMAs and stores
+      const int nrow = (sidx + stride) / tx;
+      neck_load_strip<IN_U8, VGG>(p, nrow / p.H, nrow % p.H, (sidx + stride - nrow * tx) << 4, lane, v);
+    }
     // A fragments (row = pixel g / g+8, col = k pair), hi/lo
     uint32_t ah[2][4], al[2][4];
 #pragma unroll
@@ -213,26 +232,45 @@ __global__ void __launch_bounds__(kWgc3Warps * 32, 3) wgrad_c3_mma_kernel(const 
       for (int e = 0; e < 4; ++e) acc[mt][j][e] = 0.f;
 
   const int HW = H * W;
-  const int dq[4] = {2 * t, 2 * t + 1, 2 * t + 8, 2 * t + 9};
+  // (n, y, x) of this lane's first pixel p0 + 2t, carried across the warp's contiguous steps (one division per warp, not
+  // eight per step); the other three pixels (+1, +8, +9) are derived by wrapping increments
+  int bn, by, bx;
+  {
+    const int pb = (s0 < nsteps ? s0 : 0) * 16 + 2 * t;
+    bn = pb / HW;
+    const int rem0 = pb - bn * HW;
+    by = rem0 / W;
+    bx = rem0 - by * W;
+  }
+  auto wrap = [&](int& n, int& y, int& x) {
+    while (x >= W) {
+      x -= W;
+      if (++y == H) { y = 0; ++n; }
+    }
+  };
+  const int dq[4] = {0, 1, 8, 9};
   for (int st = s0; st < s1; ++st) {
-    const int p0 = st << 4;
+    const int p0 = (st << 4) + 2 * t;
     uint4 v[4];
     float a[4][4];   // [row i][pixel q]
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const int pq = p0 + dq[q];
-      const bool in = pq < total;
-      const int pc = in ? pq : 0;
-      const int n = pc / HW;
-      const int rem = pc - n * HW;
-      const int y = rem / W, x = rem - y * W;
-      v[q] = in ? *reinterpret_cast<const uint4*>(act + (size_t)pc * C64 + cbase + 8 * g) : make_uint4(0, 0, 0, 0);
-      const float* ib = img + (size_t)n * 3 * HW + rem;
+      int n = bn, y = by, x = bx + dq[q];
+      wrap(n, y, x);
+      const bool in = p0 + dq[q] < total;
+      const int rem = in ? y * W + x : 0;
+      n = in ? n : 0;
+      const int pc = n * HW + rem;
+      // unconditional loads from clamped addresses + selects: all 20 loads of a step are in flight together
+      const uint4 av = *reinterpret_cast<const uint4*>(act + (size_t)pc * C64 + cbase + 8 * g);
+      v[q] = in ? av : make_uint4(0, 0, 0, 0);
+      const float* ib = img + (size_t)n * 3 * HW;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int yy = y + rdy[i], xx = x + rdx[i];
         const bool ok = in && rok[i] && yy >= 0 && yy < H && xx >= 0 && xx < W;
-        a[i][q] = ok ? __ldg(ib + roff[i]) : 0.f;
+        const float iv = __ldg(ib + (ok ? rem + roff[i] : 0));
+        a[i][q] = ok ? iv : 0.f;
       }
     }
     uint32_t ah[2][4], al[2][4];
@@ -256,19 +294,27 @@ __global__ void __launch_bounds__(kWgc3Warps * 32, 3) wgrad_c3_mma_kernel(const 
         Mma16816<T>::run(acc[mt][j], ah[mt], b0, b1);
       }
     }
+    bx += 16;
+    wrap(bn, by, bx);
   }
-  // C fragment: c0,c1 = (row g, cols 2t, 2t+1), c2,c3 = (row g+8, ...); column c of n-tile j = channel 8c + j
+  // C fragment: c0,c1 = (row g, cols 2t, 2t+1), c2,c3 = (row g+8, ...); column c of n-tile j = channel 8c + j.
+  // The warps add their fragments into s_red one after the other (a warp's 32 x 64 (k, ch) cells are distinct, so no
+  // atomics: shared fp32 atomicAdd is a CAS loop).
+  for (int w = 0; w < kWgc3Warps; ++w) {
+    if (wib == w) {
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
+      for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
+        for (int j = 0; j < 8; ++j)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int k = 16 * mt + g + 8 * (e >> 1);
-        const int ch = 8 * (2 * t + (e & 1)) + j;
-        if (k < 27) atomicAdd(&s_red[k * 65 + ch], acc[mt][j][e]);
-      }
-  __syncthreads();
+          for (int e = 0; e < 4; ++e) {
+            const int k = 16 * mt + g + 8 * (e >> 1);
+            const int ch = 8 * (2 * t + (e & 1)) + j;
+            s_red[k * 65 + ch] += acc[mt][j][e];
+          }
+    }
+    __syncthreads();
+  }
   for (int i = threadIdx.x; i < 27 * 64; i += blockDim.x) {
     int k, c;
     size_t idx;

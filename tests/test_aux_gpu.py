@@ -102,10 +102,11 @@ def test_gpu_crop_loader_shards_like_one_process():
     for lr, hr in loader:
         assert lr.shape == (16, 3, 24, 24) and hr.shape == (16, 3, 96, 96) and lr.is_cuda
         assert hr.min().item() >= -1.0 and hr.max().item() <= 1.0
-        # LR is the antialiased downscale of HR: box-averaging HR 4x4 correlates > 0.9 with it
+        # LR is the antialiased downscale of HR: the 4x4 box average of HR correlates strongly with it even on white
+        # noise (0.88 measured; an unrelated crop would give ~0)
         box = torch.nn.functional.avg_pool2d(hr, 4)
         c = torch.corrcoef(torch.stack([box.flatten(), lr.flatten()]))[0, 1].item()
-        assert c > 0.9
+        assert c > 0.8
         n += 1
     assert n == 4
     idx_full = list(one)
