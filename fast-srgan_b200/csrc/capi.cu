@@ -2,6 +2,7 @@
 #include "../../include/fsr_b200.h"
 #include "conv3x3_tc.cuh"
 #include "conv3x3_gen.cuh"
+#include "conv3x3_gen_ws.cuh"
 #include "conv3x3_head.cuh"
 #include "conv3x3_wgrad.cuh"
 #include "train_kernels.cuh"
@@ -252,19 +253,40 @@ int conv_dispatch(const void* x, const void* w_packed, void* out, const float* b
 
 
 // ------------------------------------------------------------------ general conv (conv3x3_gen.cuh)
+int g_gen_ws = -1;   // general conv: 1 = weight-stationary over 4-tile groups (conv3x3_gen_ws.cuh), 0 = per-tile weight streaming
+int gen_ws_mode() {
+  if (g_gen_ws < 0) {
+    const char* e = getenv("FSR_GEN_WS");
+    g_gen_ws = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_gen_ws;
+}
+
 template <int EPI, typename T, int MAXTAPS>
 int launch_gen(const CUtensorMap* maps, const CUtensorMap& tmw, GenParams& p, cudaStream_t st) {
   using Cfg = GenCfg<MAXTAPS>;
+  int ctas_per_slice = num_sms() / p.num_slices;
+  if (ctas_per_slice < 1) ctas_per_slice = 1;
+  if (ctas_per_slice > p.num_tiles) ctas_per_slice = p.num_tiles;
+  const int grid = ctas_per_slice * p.num_slices;
+  if (gen_ws_mode()) {
+    using WCfg = GenWsCfg<MAXTAPS>;
+    auto wkern = conv3x3_gen_ws_kernel<EPI, T, MAXTAPS>;
+    static bool wattr_done = false;
+    if (!wattr_done) {
+      FSR_CUDA(cudaFuncSetAttribute(wkern, cudaFuncAttributeMaxDynamicSharedMemorySize, WCfg::kSmemBytes));
+      wattr_done = true;
+    }
+    LaunchScope scope(FSR_K_CONV_GEN, st);
+    wkern<<<grid, WCfg::kThreads, WCfg::kSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], tmw, p);
+    return cuda_rc(cudaGetLastError());
+  }
   auto kern = conv3x3_gen_kernel<EPI, T, MAXTAPS>;
   static bool attr_done = false;
   if (!attr_done) {
     FSR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_done = true;
   }
-  int ctas_per_slice = num_sms() / p.num_slices;
-  if (ctas_per_slice < 1) ctas_per_slice = 1;
-  if (ctas_per_slice > p.num_tiles) ctas_per_slice = p.num_tiles;
-  const int grid = ctas_per_slice * p.num_slices;
   {
     LaunchScope scope(FSR_K_CONV_GEN, st);
     kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], tmw, p);
@@ -602,6 +624,11 @@ unsigned long long fsr_launch_count(void) { return g_launches.load(); }
 
 int fsr_set_ws_mode(int weight_stationary) {
   g_ws = weight_stationary < 0 ? -1 : (weight_stationary ? 1 : 0);   // -1: back to the environment default
+  return FSR_OK;
+}
+
+int fsr_set_gen_ws(int on) {
+  g_gen_ws = on < 0 ? -1 : (on ? 1 : 0);   // -1: back to the environment default (FSR_GEN_WS)
   return FSR_OK;
 }
 

@@ -303,8 +303,23 @@ __global__ void __launch_bounds__(256) instnorm_bwd_kernel(const InBwdParams p) 
     if (PASS == 2) draw[i] = make_uint4(ou[0], ou[1], ou[2], ou[3]);
   }
   if (PASS == 1) {
+    // block reduction without shared atomics (fp32 shared atomicAdd is a CAS loop; 32 threads per channel contended):
+    // lanes with equal (lane % vpp) hold the same channel group when vpp divides 32 -> xor-shuffle over the other lane
+    // bits, then one lane per group adds; for vpp > 32 (C > 256) every lane owns a distinct group already.
+    const int lane = threadIdx.x & 31;
+    if (vpp <= 32) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { atomicAdd(&s_a[c0 + k], a1[k]); atomicAdd(&s_b[c0 + k], a2[k]); }
+      for (int k = 0; k < 8; ++k) {
+        for (int o = 16; o >= vpp; o >>= 1) {
+          a1[k] += __shfl_xor_sync(0xffffffffu, a1[k], o);
+          a2[k] += __shfl_xor_sync(0xffffffffu, a2[k], o);
+        }
+      }
+    }
+    if (vpp > 32 || lane < vpp) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { atomicAdd(&s_a[c0 + k], a1[k]); atomicAdd(&s_b[c0 + k], a2[k]); }
+    }
     __syncthreads();
     for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
       atomicAdd(&p.red[((size_t)n * p.C + c) * 2 + 0], s_a[c]);

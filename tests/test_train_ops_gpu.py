@@ -9,11 +9,16 @@ EPS = {torch.float16: 2.0 ** -11, torch.bfloat16: 2.0 ** -8}
 DT = [torch.float16, torch.bfloat16]
 
 
-@pytest.fixture(autouse=True)
-def _setup():
+@pytest.fixture(autouse=True, params=[1, 0], ids=["gen-ws", "gen-stream"])
+def _setup(request):
+    """Every test runs with the general conv weight-stationary over 4-tile groups (conv3x3_gen_ws.cuh) and with the
+    per-tile weight-streaming kernel (conv3x3_gen.cuh)."""
+    from fast_srgan_b200 import _lib
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
+    _lib.load().fsr_set_gen_ws(request.param)
     yield
+    _lib.load().fsr_set_gen_ws(-1)
 
 
 def rnd(shape, seed, scale=1.0):
