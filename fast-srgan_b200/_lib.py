@@ -68,6 +68,8 @@ _SIGS = {
     "fsr_set_ws_mode": (_i, [_i]),
     "fsr_set_small_mma": (_i, [_i]),
     "fsr_set_gen_ws": (_i, [_i]),
+    "fsr_set_fuse_in": (_i, [_i]),
+    "fsr_conv3x3_c64_in": (_i, [_vp, _vp, _fp, _f, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "fsr_psnr_ssim": (_i, [_fp, _fp, _i, _i, _i, _i, _f, _f, _f, _vp, _vp, _vp, _vp]),
     "fsr_crop_resize_aa": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _fp, _fp, _vp]),
     "fsr_set_overlap_streams": (_i, [_i]),

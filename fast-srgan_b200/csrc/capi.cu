@@ -139,6 +139,15 @@ int ws_mode() {
   return g_ws;
 }
 
+int g_fuse_in = -1;   // Generator.forward: 1 = the res-block's first InstanceNorm + PReLU is applied inside conv2's load path
+int fuse_in_mode() {
+  if (g_fuse_in < 0) {
+    const char* e = getenv("FSR_FUSE_IN");
+    g_fuse_in = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_fuse_in;
+}
+
 int g_small_mma = -1;   // 3-channel-sided convs (neck / wgrad_c3): 1 = mma.sync tensor-core kernels (small_mma.cuh), 0 = CUDA cores
 int small_mma_mode() {
   if (g_small_mma < 0) {
@@ -148,11 +157,11 @@ int small_mma_mode() {
   return g_small_mma;
 }
 
-template <int NS, int EPI, typename T, bool HALO1>
+template <int NS, int EPI, typename T, bool HALO1, bool XF = false>
 int launch_conv(const void* x, const void* w_packed, int w_rows, ConvParams p, int dtype, cudaStream_t st) {
   using Cfg = ConvCfg<NS, HALO1>;
   using Geo = ConvGeo<HALO1>;
-  auto kern = conv3x3_c64_kernel<NS, EPI, T, HALO1>;
+  auto kern = conv3x3_c64_kernel<NS, EPI, T, HALO1, XF>;
   static bool attr_done = false;   // per template instantiation
   if (!attr_done) {
     FSR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -180,7 +189,7 @@ int launch_conv(const void* x, const void* w_packed, int w_rows, ConvParams p, i
                     : EPI == EPI_HEAD_TANH ? FSR_K_CONV_HEAD : FSR_K_CONV_BIAS_ACT;
   {
     LaunchScope scope(kid, st);
-    kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tmx, tmw, tmo, p);
+    kern<<<grid, XF ? Cfg::kThreadsXf : Cfg::kThreads, Cfg::kSmemBytes, st>>>(tmx, tmw, tmo, p);
   }
   return cuda_rc(cudaGetLastError());
 }
@@ -488,6 +497,25 @@ int fsr_conv3x3_c64(const void* x, const void* w_packed, void* out, const float*
   return conv_dispatch<__half>(x, w_packed, out, bias, reinterpret_cast<long long*>(stats), alpha, N, H, W, cout, epilogue, act, slope, out_u8, dtype, st);
 }
 
+int fsr_conv3x3_c64_in(const void* x_raw, const int64_t* in_stats, const float* in_alpha, float in_eps, const void* w_packed,
+                       void* out, int64_t* stats, int N, int H, int W, int dtype, void* stream) {
+  if (!x_raw || !in_stats || !in_alpha || !w_packed || !out || !stats || x_raw == out) return FSR_ERR_BAD_ARG;
+  if (N <= 0 || H <= 0 || W <= 0) return FSR_ERR_BAD_SHAPE;
+  if (!halo_mode()) return FSR_ERR_BAD_ARG;      // exists for the single-halo-tile staging only
+  cudaStream_t st = (cudaStream_t)stream;
+  ConvParams p{};
+  p.N = N; p.H = H; p.W = W; p.out = out; p.stats = reinterpret_cast<long long*>(stats);
+  p.cout_total = 64; p.num_slices = 1;
+  p.in_stats = reinterpret_cast<const long long*>(in_stats); p.in_alpha = in_alpha; p.in_eps = in_eps;
+  if (dtype == FSR_BF16) return launch_conv<64, EPI_RAW_STATS, __nv_bfloat16, true, true>(x_raw, w_packed, 9 * 64, p, dtype, st);
+  return launch_conv<64, EPI_RAW_STATS, __half, true, true>(x_raw, w_packed, 9 * 64, p, dtype, st);
+}
+
+int fsr_set_fuse_in(int on) {
+  g_fuse_in = on < 0 ? -1 : (on ? 1 : 0);   // -1: back to the environment default (FSR_FUSE_IN)
+  return FSR_OK;
+}
+
 int fsr_conv3x3_gen(const void* x, const void* w_packed, void* out, const float* bias, int64_t* stats,
                     const float* alpha, int N, int H, int W, int cin, int cout, int stride, int mode, int epilogue,
                     int act, float slope, int dtype, void* stream) {
@@ -685,9 +713,15 @@ static int generator_chain(const FsrGeneratorParams* prm, const uint8_t* xin, ui
     int64_t* s1 = stats + (size_t)(2 * l) * stats_per_conv;
     int64_t* s2 = stats + (size_t)(2 * l + 1) * stats_per_conv;
     if ((rc = fsr_conv3x3_c64(cur, prm->stem_w1[l], raw, nullptr, s1, nullptr, nb, H, W, F, FSR_EPI_RAW_STATS, 0, 0.f, 0, dt, st))) return rc;
-    if ((rc = fsr_instnorm_apply(raw, s1, nullptr, yb, prm->stem_alpha[l], nb, H * W, F, FSR_ACT_PRELU, 0.f, 1e-5f, dt, st))) return rc;
-    if ((rc = fsr_conv3x3_c64(yb, prm->stem_w2[l], raw, nullptr, s2, nullptr, nb, H, W, F, FSR_EPI_RAW_STATS, 0, 0.f, 0, dt, st))) return rc;
-    if ((rc = fsr_instnorm_apply(raw, s2, cur, xb, nullptr, nb, H * W, F, FSR_ACT_NONE, 0.f, 1e-5f, dt, st))) return rc;
+    if (fuse_in_mode() && halo_mode()) {
+      // bn1 + relu1 (model.py:55-56) applied to the halo tile inside conv2's load path: one HBM round trip less per block
+      if ((rc = fsr_conv3x3_c64_in(raw, s1, prm->stem_alpha[l], 1e-5f, prm->stem_w2[l], yb, s2, nb, H, W, dt, st))) return rc;
+      if ((rc = fsr_instnorm_apply(yb, s2, cur, xb, nullptr, nb, H * W, F, FSR_ACT_NONE, 0.f, 1e-5f, dt, st))) return rc;
+    } else {
+      if ((rc = fsr_instnorm_apply(raw, s1, nullptr, yb, prm->stem_alpha[l], nb, H * W, F, FSR_ACT_PRELU, 0.f, 1e-5f, dt, st))) return rc;
+      if ((rc = fsr_conv3x3_c64(yb, prm->stem_w2[l], raw, nullptr, s2, nullptr, nb, H, W, F, FSR_EPI_RAW_STATS, 0, 0.f, 0, dt, st))) return rc;
+      if ((rc = fsr_instnorm_apply(raw, s2, cur, xb, nullptr, nb, H * W, F, FSR_ACT_NONE, 0.f, 1e-5f, dt, st))) return rc;
+    }
     cur = xb;
   }
   {   // bottleneck + long skip (model.py:86-95, 115)

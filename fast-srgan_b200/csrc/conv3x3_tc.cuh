@@ -51,6 +51,11 @@ struct ConvParams {
   int ws;                   // 1: weight-stationary MMAs (B re-used from the collector across the two interleaved tiles)
   int out_u8;               // EPI_HEAD_TANH: 0 -> tanh, fp32 NCHW [N,3,H,W]; 1 -> tanh, uint8 NHWC [N,H,W,3];
                             //                2 -> linear (no tanh) fp32 NCHW store; 3 -> linear, accumulate (+=)
+  // XF (fused input transform): the conv input is the RAW output of the previous conv; its InstanceNorm + PReLU
+  // (model.py:55-56) is applied to the staged halo tile in shared memory before the MMAs read it
+  const long long* in_stats;  // [N][64][2] fixed-point statistics of the input tensor
+  const float* in_alpha;      // PReLU slope (device pointer)
+  float in_eps;
 };
 
 template <bool HALO1>
@@ -64,12 +69,15 @@ struct ConvGeo {
   static constexpr int kTxBytes = kBoxW * kBoxH * 128;               // bytes one fill delivers
 };
 
+constexpr int kXfWarps = 2;   // input-transform warps of the XF variant (register budget: 384 threads x 168 registers)
+
 template <int NS, bool HALO1>
 struct ConvCfg {
   using Geo = ConvGeo<HALO1>;
   static constexpr int kWBytes = 9 * NS * 128;
   static constexpr int kEpiWarps = (NS >= 128) ? 4 : 8;
   static constexpr int kThreads = 64 + 32 * kEpiWarps;
+  static constexpr int kThreadsXf = kThreads + 32 * kXfWarps;
   static constexpr int kStagingBytes = kEpiWarps * 4096;
   static constexpr int kStages = (NS >= 128) ? (HALO1 ? 2 : 3) : (HALO1 ? 5 : 6);
   static constexpr bool kPair = HALO1 && kStages >= 4;   // interleave the MMAs of two tiles (needs both tiles staged)
@@ -103,8 +111,8 @@ FSR_DEVINL void warp_reduce64(float (&v)[64], int lane) {
   }
 }
 
-template <int NS, int EPI, typename T, bool HALO1>
-__global__ void __launch_bounds__(ConvCfg<NS, HALO1>::kThreads, 1)
+template <int NS, int EPI, typename T, bool HALO1, bool XF = false>
+__global__ void __launch_bounds__(XF ? ConvCfg<NS, HALO1>::kThreadsXf : ConvCfg<NS, HALO1>::kThreads, 1)
 conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                    const __grid_constant__ CUtensorMap tm_out, const ConvParams p) {
   // NHWC outputs leave through a TMA store of the staged (swizzled) tile: no smem read-back, hardware edge clipping
@@ -123,8 +131,12 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
   uint64_t* w_bar = bars + 2 * Cfg::kStages;       // [1]
   uint64_t* tfull_bar = w_bar + 1;                 // [4]
   uint64_t* tempty_bar = tfull_bar + 4;            // [4]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 4);
+  uint64_t* xfull_bar = tempty_bar + 4;            // [kStages] (XF: the stage's halo tile has been transformed)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xfull_bar + Cfg::kStages);
   float* smem_bias = reinterpret_cast<float*>(tmem_slot + 4);   // [NS]
+  static_assert(!XF || (HALO1 && NS == 64), "the fused input transform exists for the single-halo-tile 64->64 conv");
+  // the MMA warp consumes a stage once it is `ready`: filled by TMA, and in the XF variant transformed in place
+  uint64_t* ready_bar = XF ? xfull_bar : full_bar;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -140,7 +152,9 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_x);
     tma_prefetch_desc(&tm_w);
-    for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < Cfg::kStages; ++i) {
+      mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); mbar_init(&xfull_bar[i], kXfWarps);
+    }
     mbar_init(w_bar, 1);
     for (int i = 0; i < 4; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
     fence_mbar_init();
@@ -213,8 +227,8 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         const int stage_b = stage;
         const uint32_t phase_b = phase;
         if (two) { if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; } }
-        mbar_wait(&full_bar[stage_a], phase_a);
-        if (two) mbar_wait(&full_bar[stage_b], phase_b);
+        mbar_wait(&ready_bar[stage_a], phase_a);
+        if (two) mbar_wait(&ready_bar[stage_b], phase_b);
         tc_fence_after();
         const uint32_t a_lo_a = a_lo0 + stage_a * (Geo::kStageBytes >> 4);
         const uint32_t a_lo_b = a_lo0 + stage_b * (Geo::kStageBytes >> 4);
@@ -278,6 +292,66 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
           __syncwarp();
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
+      }
+    }
+  } else if (XF && warp >= 2 + Cfg::kEpiWarps) {
+    // =============================== input-transform warps (XF) ===============================
+    // y = PReLU((raw - mean[n,c]) * rstd[n,c]) applied IN PLACE to the TMA-written halo tile (rows = 180 halo pixels of
+    // 128 B; the 16-byte chunk of channel group g sits at chunk g ^ (row & 7): 128B swizzle on absolute address bits,
+    // stage bases are 1024-B aligned).  Same fp32 operations as instnorm_apply_kernel -> bit-identical activations.
+    // Rows outside the image stay zero (the conv's zero padding comes AFTER the normalisation).
+    if constexpr (XF) {
+      const int tid = threadIdx.x - (64 + 32 * Cfg::kEpiWarps);      // 0 .. 32*kXfWarps-1
+      const int g = tid & 7, r_first = tid >> 3;
+      constexpr int kRowStep = 4 * kXfWarps;
+      const float slope = __ldg(p.in_alpha);
+      const double inv_hw = 1.0 / (double)(p.H * p.W);
+      float mean[8], rstd[8];
+      int cur_n = -1;
+      int stage = 0; uint32_t phase = 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        const int n = t / tiles_per_img;
+        const int rem = t - n * tiles_per_img;
+        const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+        const int x0 = tx * TW, y0 = ty * TH;
+        if (n != cur_n) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            stat_mean_rstd(p.in_stats + ((size_t)n * 64 + 8 * g + k) * 2, inv_hw, p.in_eps, mean[k], rstd[k]);
+          cur_n = n;
+        }
+        const bool inside = (y0 >= 1) && (x0 >= 1) && (y0 + TH + 1 <= p.H) && (x0 + TW + 1 <= p.W);   // whole halo box in the image
+        mbar_wait(&full_bar[stage], phase);
+        const uint32_t base = smem_u32(smem_a + stage * Geo::kStageBytes);
+#pragma unroll 4
+        for (int r = r_first; r < Geo::kBoxW * Geo::kBoxH; r += kRowStep) {
+          bool ok = inside;
+          if (!inside) {
+            const int by = r / Geo::kBoxW, bx = r - by * Geo::kBoxW;
+            const int gy = y0 - 1 + by, gx = x0 - 1 + bx;
+            ok = gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
+          }
+          if (ok) {
+            const uint32_t addr = base + (uint32_t)r * 128u + (uint32_t)((g ^ (r & 7)) << 4);
+            const uint4 v = ld_shared_v4(addr);
+            const uint32_t vu[4] = {v.x, v.y, v.z, v.w};
+            uint32_t ou[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 f = Cvt<T>::unpack2(vu[k]);
+              float a = (f.x - mean[2 * k]) * rstd[2 * k];
+              float b = (f.y - mean[2 * k + 1]) * rstd[2 * k + 1];
+              a = apply_act(a, ACT_PRELU, slope);
+              b = apply_act(b, ACT_PRELU, slope);
+              ou[k] = Cvt<T>::pack2(a, b);
+            }
+            st_shared_v4(addr, ou[0], ou[1], ou[2], ou[3]);
+          }
+        }
+        fence_proxy_async();                 // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&xfull_bar[stage]);
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
     }
   } else {

@@ -60,6 +60,22 @@ def conv3x3_c64_raw_stats(x: torch.Tensor, w_packed: torch.Tensor, stats: Option
     return out, stats
 
 
+def conv3x3_c64_in(raw_in: torch.Tensor, stats_in: torch.Tensor, alpha: torch.Tensor, w_packed: torch.Tensor, eps: float = 1e-5,
+                   stats: Optional[torch.Tensor] = None):
+    """conv3x3(PReLU(InstanceNorm(raw_in))) with the normalisation fused into the conv's load path (model.py:55-64):
+    raw_in NHWC [N,H,W,64] + its fixed-point statistics -> (raw NHWC [N,H,W,64], stats int64 [N,64,2])."""
+    _cuda(raw_in, stats_in, alpha, w_packed)
+    N, H, W, C = raw_in.shape
+    assert C == 64 and raw_in.is_contiguous() and w_packed.shape[1] == 64
+    out = torch.empty((N, H, W, 64), dtype=raw_in.dtype, device=raw_in.device)
+    if stats is None:
+        stats = torch.zeros((N, 64, 2), dtype=torch.int64, device=raw_in.device)
+    L.check(L.load().fsr_conv3x3_c64_in(raw_in.data_ptr(), stats_in.data_ptr(), alpha.data_ptr(), eps, w_packed.data_ptr(),
+                                        out.data_ptr(), stats.data_ptr(), N, H, W, L.dtype_code(raw_in.dtype),
+                                        L.stream_ptr(raw_in.device)), "conv3x3 fused IN+PReLU input")
+    return out, stats
+
+
 def conv3x3_c64_bias_act(x, w_packed, bias, act: int = L.ACT_NONE, slope: float = 0.0, alpha=None):
     _cuda(x, w_packed, bias)
     N, H, W, C = x.shape

@@ -244,6 +244,18 @@ int fsr_crop_resize_aa(const uint8_t* cache, const int64_t* img_off, const int32
                        const int32_t* samples, int B, int lr_size, int scale, const int32_t* tap_min,
                        const int32_t* tap_size, const float* tap_w, int K, float* lr, float* hr, void* stream);
 
+/* The second conv of a ResidualBlock with the block's first InstanceNorm + PReLU fused into its load path:
+ *   out, stats = conv3x3(PReLU(InstanceNorm(x_raw)))       (model.py:55-56 folded into :57-64)
+ * x_raw [N,H,W,64] = RAW output of conv1 with its fixed-point statistics in_stats [N,64,2] (as written by
+ * fsr_conv3x3_c64 RAW_STATS), in_alpha = PReLU slope (device), in_eps = InstanceNorm eps.  The normalised activation is
+ * never written to HBM: the staged halo tile is transformed in shared memory (same fp32 operations as
+ * fsr_instnorm_apply -> bit-identical results).  out must not alias x_raw.  Single-halo-tile mode only. */
+int fsr_conv3x3_c64_in(const void* x_raw, const int64_t* in_stats, const float* in_alpha, float in_eps, const void* w_packed,
+                       void* out, int64_t* stats, int N, int H, int W, int dtype, void* stream);
+/* 1 (default): fsr_generator_forward uses fsr_conv3x3_c64_in for every residual block; 0: separate normalise pass;
+ * -1: environment default (FSR_FUSE_IN). */
+int fsr_set_fuse_in(int on);
+
 /* 1 (default): fsr_conv3x3_gen runs weight-stationary over groups of four 128-pixel tiles (one weight fill per K step
  * and group instead of per tile: 2.3x less L2->smem traffic, same results bit for bit); 0: per-tile weight streaming;
  * -1: environment default (FSR_GEN_WS). */
