@@ -386,7 +386,7 @@ def main():
                    "parallelism": f"{world} independent replicas (frames shard, no collective)",
                    "l2": "activations streamed per step (>5 GB) exceed the 126 MB L2; no explicit flush",
                    "l2_group": args.l2_group, "overlap_streams": args.streams,
-                   "switches": {k: os.environ.get(k, "default(1)") for k in ("FSR_FUSE_IN", "FSR_GEN_WS", "FSR_SMALL_MMA", "FSR_WS", "FSR_HALO1")}},
+                   "switches": {k: os.environ.get(k, "default") for k in ("FSR_FUSE_IN", "FSR_GEN_WS", "FSR_SMALL_MMA", "FSR_WS", "FSR_HALO1")}},
         "whole_model_tflops": total_flops / (ms_step * 1e-3) / 1e12 * 1.0,
         "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": e2e_fps, "unit": UNIT, "h2d_bytes_per_step": BATCH * H * W * 3,
