@@ -69,7 +69,7 @@ struct ConvGeo {
   static constexpr int kTxBytes = kBoxW * kBoxH * 128;               // bytes one fill delivers
 };
 
-constexpr int kXfWarps = 2;   // input-transform warps of the XF variant (register budget: 384 threads x 168 registers)
+constexpr int kXfWarps = 4;   // input-transform warps of the XF variant (448 threads: 146 registers per thread)
 
 template <int NS, bool HALO1>
 struct ConvCfg {
@@ -323,30 +323,38 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         const bool inside = (y0 >= 1) && (x0 >= 1) && (y0 + TH + 1 <= p.H) && (x0 + TW + 1 <= p.W);   // whole halo box in the image
         mbar_wait(&full_bar[stage], phase);
         const uint32_t base = smem_u32(smem_a + stage * Geo::kStageBytes);
-#pragma unroll 4
-        for (int r = r_first; r < Geo::kBoxW * Geo::kBoxH; r += kRowStep) {
+        // branch-free, fully unrolled: all of a thread's 16-byte chunks are loaded before the first is transformed
+        // (two warps with a branch per row needed 6.6 k cycles per tile against a 2.9 k-cycle tile period)
+        constexpr int kRows = Geo::kBoxW * Geo::kBoxH;                    // 180
+        constexpr int kIters = (kRows + kRowStep - 1) / kRowStep;         // 12 with 4 warps
+        uint4 v[kIters];
+#pragma unroll
+        for (int j = 0; j < kIters; ++j) {
+          const int r = min(r_first + j * kRowStep, kRows - 1);
+          v[j] = ld_shared_v4(base + (uint32_t)r * 128u + (uint32_t)((g ^ (r & 7)) << 4));
+        }
+#pragma unroll
+        for (int j = 0; j < kIters; ++j) {
+          const int r = r_first + j * kRowStep;
           bool ok = inside;
           if (!inside) {
             const int by = r / Geo::kBoxW, bx = r - by * Geo::kBoxW;
             const int gy = y0 - 1 + by, gx = x0 - 1 + bx;
             ok = gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
           }
-          if (ok) {
-            const uint32_t addr = base + (uint32_t)r * 128u + (uint32_t)((g ^ (r & 7)) << 4);
-            const uint4 v = ld_shared_v4(addr);
-            const uint32_t vu[4] = {v.x, v.y, v.z, v.w};
-            uint32_t ou[4];
+          const uint32_t vu[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+          uint32_t ou[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const float2 f = Cvt<T>::unpack2(vu[k]);
-              float a = (f.x - mean[2 * k]) * rstd[2 * k];
-              float b = (f.y - mean[2 * k + 1]) * rstd[2 * k + 1];
-              a = apply_act(a, ACT_PRELU, slope);
-              b = apply_act(b, ACT_PRELU, slope);
-              ou[k] = Cvt<T>::pack2(a, b);
-            }
-            st_shared_v4(addr, ou[0], ou[1], ou[2], ou[3]);
+          for (int k = 0; k < 4; ++k) {
+            const float2 f = Cvt<T>::unpack2(vu[k]);
+            float a = (f.x - mean[2 * k]) * rstd[2 * k];
+            float b = (f.y - mean[2 * k + 1]) * rstd[2 * k + 1];
+            a = apply_act(a, ACT_PRELU, slope);
+            b = apply_act(b, ACT_PRELU, slope);
+            ou[k] = ok ? Cvt<T>::pack2(a, b) : vu[k];                     // rows outside the image stay zero
           }
+          if (r < kRows)
+            st_shared_v4(base + (uint32_t)r * 128u + (uint32_t)((g ^ (r & 7)) << 4), ou[0], ou[1], ou[2], ou[3]);
         }
         fence_proxy_async();                 // generic-proxy writes -> visible to the tensor core's async-proxy reads
         __syncwarp();
@@ -509,17 +517,25 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
           if constexpr (EPI == EPI_RAW_STATS) {
             // InstanceNorm statistics (reference model.py:55,65,94,132) of the STORED (rounded) values, reduced in
             // registers: a butterfly over the warp's 32 pixels leaves channels (2L, 2L+1) in lane L.
-            float v[64], sq[64];
+            float v[64];
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               const float2 f = Cvt<T>::unpack2(pk[i]);
               v[2 * i] = pvalid ? f.x : 0.f;
               v[2 * i + 1] = pvalid ? f.y : 0.f;
-              sq[2 * i] = v[2 * i] * v[2 * i];
-              sq[2 * i + 1] = v[2 * i + 1] * v[2 * i + 1];
             }
             warp_reduce64(v, lane);
+            const float sum0 = v[0], sum1 = v[1];
+            if constexpr (XF) asm volatile("" ::: "memory");   // XF runs at 146 registers: keep the two butterflies apart
+            float sq[64];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float2 f = Cvt<T>::unpack2(pk[i]);
+              sq[2 * i] = pvalid ? f.x * f.x : 0.f;
+              sq[2 * i + 1] = pvalid ? f.y * f.y : 0.f;
+            }
             warp_reduce64(sq, lane);
+            v[0] = sum0; v[1] = sum1;
             st_s0 += stat_fix(v[0], kStatSumScale); st_q0 += stat_fix(sq[0], kStatSqScale);
             st_s1 += stat_fix(v[1], kStatSumScale); st_q1 += stat_fix(sq[1], kStatSqScale);
           }
