@@ -323,26 +323,21 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         const bool inside = (y0 >= 1) && (x0 >= 1) && (y0 + TH + 1 <= p.H) && (x0 + TW + 1 <= p.W);   // whole halo box in the image
         mbar_wait(&full_bar[stage], phase);
         const uint32_t base = smem_u32(smem_a + stage * Geo::kStageBytes);
-        // branch-free, fully unrolled: all of a thread's 16-byte chunks are loaded before the first is transformed
-        // (two warps with a branch per row needed 6.6 k cycles per tile against a 2.9 k-cycle tile period)
+        // ROLLED loop (two rows in flight per thread): a fully unrolled, branch-free version measured no faster than two
+        // warps with a branch per row (358 us either way) while the kernel's SASS grew to 64 KB and 27 % of the stall samples
+        // became `no_instructions` - the transform's code footprint, not its arithmetic, is what has to stay small.
         constexpr int kRows = Geo::kBoxW * Geo::kBoxH;                    // 180
-        constexpr int kIters = (kRows + kRowStep - 1) / kRowStep;         // 12 with 4 warps
-        uint4 v[kIters];
-#pragma unroll
-        for (int j = 0; j < kIters; ++j) {
-          const int r = min(r_first + j * kRowStep, kRows - 1);
-          v[j] = ld_shared_v4(base + (uint32_t)r * 128u + (uint32_t)((g ^ (r & 7)) << 4));
-        }
-#pragma unroll
-        for (int j = 0; j < kIters; ++j) {
-          const int r = r_first + j * kRowStep;
+#pragma unroll 2
+        for (int r = r_first; r < kRows; r += kRowStep) {
+          const uint32_t addr = base + (uint32_t)r * 128u + (uint32_t)((g ^ (r & 7)) << 4);
+          const uint4 v = ld_shared_v4(addr);
           bool ok = inside;
           if (!inside) {
             const int by = r / Geo::kBoxW, bx = r - by * Geo::kBoxW;
             const int gy = y0 - 1 + by, gx = x0 - 1 + bx;
             ok = gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
           }
-          const uint32_t vu[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+          const uint32_t vu[4] = {v.x, v.y, v.z, v.w};
           uint32_t ou[4];
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
@@ -353,8 +348,7 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
             b = apply_act(b, ACT_PRELU, slope);
             ou[k] = ok ? Cvt<T>::pack2(a, b) : vu[k];                     // rows outside the image stay zero
           }
-          if (r < kRows)
-            st_shared_v4(base + (uint32_t)r * 128u + (uint32_t)((g ^ (r & 7)) << 4), ou[0], ou[1], ou[2], ou[3]);
+          st_shared_v4(addr, ou[0], ou[1], ou[2], ou[3]);
         }
         fence_proxy_async();                 // generic-proxy writes -> visible to the tensor core's async-proxy reads
         __syncwarp();

@@ -252,8 +252,8 @@ int fsr_crop_resize_aa(const uint8_t* cache, const int64_t* img_off, const int32
  * fsr_instnorm_apply -> bit-identical results).  out must not alias x_raw.  Single-halo-tile mode only. */
 int fsr_conv3x3_c64_in(const void* x_raw, const int64_t* in_stats, const float* in_alpha, float in_eps, const void* w_packed,
                        void* out, int64_t* stats, int N, int H, int W, int dtype, void* stream);
-/* 1: fsr_generator_forward uses fsr_conv3x3_c64_in for every residual block; 0 (default): separate normalise pass;
- * -1: environment default (FSR_FUSE_IN=1 enables). */
+/* 1 (default): fsr_generator_forward uses fsr_conv3x3_c64_in for every residual block; 0: separate normalise pass;
+ * -1: environment default (FSR_FUSE_IN=0 disables). */
 int fsr_set_fuse_in(int on);
 
 /* 1 (default): fsr_conv3x3_gen runs weight-stationary over groups of four 128-pixel tiles (one weight fill per K step
