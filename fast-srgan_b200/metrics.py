@@ -60,16 +60,25 @@ class ValidationMetrics:
         self._ssim.append(sums / float(C * (H - KERNEL_SIZE + 1) * (W - KERNEL_SIZE + 1)))
         self._numel += sr.numel()
 
+    @staticmethod
+    def pool(stat: torch.Tensor, data_range: float, sync: bool = True) -> Dict[str, float]:
+        """stat = [sum of squared errors, element count, sum of per-image SSIM, image count] (float64, any device) ->
+        pooled metrics; summed over ranks first when torch.distributed is initialised (what torchmetrics'
+        dist_reduce_fx = "sum" / "cat" followed by .mean() amounts to)."""
+        if sync and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(stat)
+        sse, numel, ssum, n_img = (float(v) for v in stat.tolist())
+        mse = sse / numel
+        psnr = float("inf") if mse == 0.0 else 10.0 * math.log10(data_range ** 2 / mse)
+        return {"ssim": ssum / n_img, "psnr": psnr}
+
     def compute(self, sync: bool = True) -> Dict[str, float]:
-        """Pools over ranks when torch.distributed is initialised (torchmetrics' dist_reduce_fx: sum / cat)."""
+        """{"ssim": mean per-image SSIM, "psnr": PSNR of the pooled MSE, "ssim_per_image": this rank's values}."""
         if not self._ssim:
             raise RuntimeError("compute() before any update()")
         ssim = torch.cat(self._ssim)
         stat = torch.stack([self._sse[0], torch.tensor(float(self._numel), dtype=torch.float64, device=self.device),
                             ssim.sum(), torch.tensor(float(ssim.numel()), dtype=torch.float64, device=self.device)])
-        if sync and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(stat)
-        sse, numel, ssum, n_img = (float(v) for v in stat.tolist())
-        mse = sse / numel
-        psnr = float("inf") if mse == 0.0 else 10.0 * math.log10(self.data_range ** 2 / mse)
-        return {"ssim": ssum / n_img, "psnr": psnr, "ssim_per_image": ssim}
+        out = self.pool(stat, self.data_range, sync)
+        out["ssim_per_image"] = ssim
+        return out

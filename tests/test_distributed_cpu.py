@@ -73,3 +73,51 @@ def test_shard_ranges():
         assert False
     except ValueError:
         pass
+
+
+def _aux_worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import aux_oracle as A
+    from fast_srgan_b200 import distributed as D
+    from fast_srgan_b200.data import ShardedReplacementSampler
+    from fast_srgan_b200.metrics import ValidationMetrics
+    torch.set_num_threads(2)
+    D.init_from_env("gloo")
+    # (1) data path: every rank draws the same global index stream and keeps its slice of each global batch
+    mine = list(ShardedReplacementSampler(37, 8 * 5 + 3, 8, seed=11, rank=rank, world=world))
+    gathered = [None] * world
+    dist.all_gather_object(gathered, [b.tolist() for b in mine])
+    ref = A.replacement_sample_indices(37, 43, 11)
+    ok_sampler = all(sum((gathered[r][b] for r in range(world)), []) == ref[8 * b:8 * b + 8].tolist() for b in range(5))
+    # (2) validation metrics: each rank's partial sums (its shard of the validation set) pooled by one all-reduce
+    g = torch.Generator().manual_seed(5)
+    sr = torch.rand((4, 3, 24, 28), generator=g) * 2 - 1
+    hr = torch.rand((4, 3, 24, 28), generator=g) * 2 - 1
+    a, b = (1 + D.shard_batch(sr, rank, world)) / 2, (1 + D.shard_batch(hr, rank, world)) / 2
+    ss = A.ssim_per_image(a, b)
+    stat = torch.tensor([float(((a - b).double() ** 2).sum()), float(a.numel()), float(ss.double().sum()), float(ss.numel())],
+                        dtype=torch.float64)
+    out = ValidationMetrics.pool(stat, 1.0, sync=True)
+    ssim_ref, psnr_ref = A.validation_metrics([sr], [hr])
+    ret[rank] = (ok_sampler, abs(out["ssim"] - ssim_ref), abs(out["psnr"] - psnr_ref))
+    dist.destroy_process_group()
+
+
+def test_two_rank_sampler_shards_and_metric_pooling():
+    """SURVEY 8e for the f3 / f4 rows: W ranks at B/W see exactly one process's batches; pooled PSNR / SSIM equal the
+    single-process values (torchmetrics' sum / cat reductions)."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    port = 31000 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_aux_worker, args=(r, world, port, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    assert len(ret) == world
+    for ok, d_ssim, d_psnr in ret.values():
+        assert ok and d_ssim <= 1e-6 and d_psnr <= 1e-6
