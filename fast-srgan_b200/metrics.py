@@ -54,9 +54,12 @@ class ValidationMetrics:
         sums = torch.zeros(N, dtype=torch.float64, device=sr.device)
         s = 0.5 if rescale else 1.0
         b = 0.5 if rescale else 0.0
-        L.check(L.load().fsr_psnr_ssim(sr.data_ptr(), hr.data_ptr(), N, C, H, W, s, b, self.data_range,
-                                       ctypes.cast(self._taps, ctypes.c_void_p), self._sse.data_ptr(), sums.data_ptr(),
-                                       L.stream_ptr(sr.device)), "psnr/ssim")
+        step = max(1, 65535 // C)                      # one launch covers at most 65535 (image, channel) planes (grid.z)
+        for i in range(0, N, step):
+            n = min(step, N - i)
+            L.check(L.load().fsr_psnr_ssim(sr[i:i + n].data_ptr(), hr[i:i + n].data_ptr(), n, C, H, W, s, b, self.data_range,
+                                           ctypes.cast(self._taps, ctypes.c_void_p), self._sse.data_ptr(), sums[i:i + n].data_ptr(),
+                                           L.stream_ptr(sr.device)), "psnr/ssim")
         self._ssim.append(sums / float(C * (H - KERNEL_SIZE + 1) * (W - KERNEL_SIZE + 1)))
         self._numel += sr.numel()
 
