@@ -3,7 +3,6 @@
 #include "conv3x3_tc.cuh"
 #include "conv3x3_gen.cuh"
 #include "conv3x3_gen_ws.cuh"
-#include "conv3x3_up_2cta.cuh"
 #include "conv3x3_head.cuh"
 #include "conv3x3_wgrad.cuh"
 #include "train_kernels.cuh"
@@ -140,43 +139,6 @@ int ws_mode() {
   return g_ws;
 }
 
-int g_two_cta = -1;   // EXPERIMENTAL: 64->256 upsampling conv as a CTA-pair kernel (conv3x3_up_2cta.cuh); default OFF, not yet run on hardware
-int two_cta_mode() {
-  if (g_two_cta < 0) {
-    const char* e = getenv("FSR_2CTA");
-    g_two_cta = (e && e[0] == '1') ? 1 : 0;
-  }
-  return g_two_cta;
-}
-
-template <typename T>
-int launch_up_2cta(const void* x, const void* w_packed, ConvParams p, int dtype, cudaStream_t st) {
-  using Cfg = Up2Cfg;
-  using Geo = Cfg::Geo;
-  auto kern = conv3x3_up_2cta_kernel<T>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    FSR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_done = true;
-  }
-  p.tiles_x = (p.W + Geo::TW - 1) / Geo::TW;
-  p.tiles_y = (p.H + Geo::TH - 1) / Geo::TH;
-  p.num_tiles = p.N * p.tiles_x * p.tiles_y;
-  CUtensorMap tmx, tmw;
-  int rc = make_act_map(&tmx, x, p.N, p.H, p.W, 64, Geo::kBoxW, Geo::kBoxH, dtype);
-  if (rc) return rc;
-  if ((rc = make_w_map(&tmw, w_packed, 9 * Cfg::kN, Cfg::kN / 2, dtype))) return rc;
-  const int pairs = (p.num_tiles + 1) / 2;
-  int clusters = num_sms() / 2;
-  if (clusters > pairs) clusters = pairs;
-  if (clusters < 1) clusters = 1;
-  {
-    LaunchScope scope(FSR_K_CONV_UP, st);
-    kern<<<2 * clusters, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tmx, tmw, p);   // __cluster_dims__(2,1,1)
-  }
-  return cuda_rc(cudaGetLastError());
-}
-
 int g_fuse_in = -1;   // Generator.forward: 1 = the res-block's first InstanceNorm + PReLU is applied inside conv2's load path
 int fuse_in_mode() {
   if (g_fuse_in < 0) {
@@ -286,7 +248,6 @@ int conv_dispatch(const void* x, const void* w_packed, void* out, const float* b
     case FSR_EPI_PS_PRELU: {
       if (cout != 256 || !alpha) return FSR_ERR_BAD_ARG;
       p.cout_total = 256; p.num_slices = 2;
-      if (two_cta_mode() && halo_mode()) return launch_up_2cta<T>(x, w_packed, p, dtype, st);
       return launch_conv_mode<128, EPI_PS_PRELU, T>(x, w_packed, 9 * 256, p, dtype, st);
     }
     case FSR_EPI_HEAD_TANH: {

@@ -1,6 +1,7 @@
-"""Opt-in GPU tests of kernels that are compiled but have NOT run on hardware yet (skipped unless FSR_TEST_EXPERIMENTAL=1;
-the product never launches them unless their switch is set):
-  conv3x3_up_2cta_kernel (FSR_2CTA=1): the 64->256 upsampling conv as a tcgen05 CTA-pair (cta_group::2) kernel."""
+"""Opt-in GPU tests of kernels that are compiled (libfsr_b200_experimental.so, its own library) but have NOT run on hardware
+yet; skipped unless FSR_TEST_EXPERIMENTAL=1.  The product never loads that library.
+  conv3x3_up_2cta_kernel: the 64->256 upsampling conv as a tcgen05 CTA-pair (cta_group::2) kernel."""
+import ctypes
 import os
 
 import pytest
@@ -19,17 +20,26 @@ def rnd(shape, seed, scale=1.0):
 @pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("shape", [(1, 16, 8), (1, 16, 16), (2, 13, 21), (3, 24, 24), (1, 40, 72), (4, 90, 160)])
 def test_up_conv_cta_pair_matches_single_cta(dt, shape):
-    """Run in a fresh process with FSR_2CTA=1 FSR_TEST_EXPERIMENTAL=1: the pair kernel replaces fsr_conv3x3_c64(PS_PRELU);
-    reference = PyTorch fp32 on the same rounded operands (model.py:30-40)."""
-    assert os.environ.get("FSR_2CTA") == "1", "set FSR_2CTA=1 together with FSR_TEST_EXPERIMENTAL=1"
-    from fast_srgan_b200 import ops
+    """The pair kernel against the validated single-CTA kernel (expected bit-identical: same tap / k order per tile) and
+    PyTorch fp32 on the same rounded operands (model.py:30-40)."""
+    from fast_srgan_b200 import ops, _lib as L
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    xlib = ctypes.CDLL(os.path.join(root, "fast-srgan_b200", "libfsr_b200_experimental.so"))
+    xlib.fsrx_conv3x3_up_2cta.restype = ctypes.c_int
+    xlib.fsrx_conv3x3_up_2cta.argtypes = [ctypes.c_void_p] * 5 + [ctypes.c_int] * 4 + [ctypes.c_void_p]
     N, H, W = shape
     x = rnd((N, 64, H, W), 1).permute(0, 2, 3, 1).contiguous().to(dt)
     w = rnd((256, 64, 3, 3), 2, 0.05).to(dt).float()
     b = rnd((256,), 3, 0.1)
     alpha = torch.tensor([0.2], device="cuda")
     wp, bp = ops.pack_conv3x3(w, b, dt, ps_perm=True)
-    got = ops.conv3x3_c64_ps_prelu(x, wp, bp, alpha)
+    base = ops.conv3x3_c64_ps_prelu(x, wp, bp, alpha)
+    got = torch.empty_like(base)
+    rc = xlib.fsrx_conv3x3_up_2cta(x.data_ptr(), wp.data_ptr(), got.data_ptr(), bp.data_ptr(), alpha.data_ptr(), N, H, W,
+                                   L.dtype_code(dt), L.stream_ptr(x.device))
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert torch.equal(got, base)
     ref = F.prelu(F.pixel_shuffle(F.conv2d(x.float().permute(0, 3, 1, 2), w, b, padding=1), 2), alpha)
     eps = 2.0 ** -11 if dt == torch.float16 else 2.0 ** -8
     assert (got.float().permute(0, 3, 1, 2) - ref).abs().max().item() <= 2 * eps * ref.abs().max().item() + 1e-5
