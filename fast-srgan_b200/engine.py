@@ -70,6 +70,23 @@ class FlatParams:
     def zero_grad(self):
         self.grad.zero_()
 
+    def optimizer_state(self) -> Dict[str, object]:
+        """AdamW state of this network (what `optim.state_dict()` holds in trainer.py:149-156): step + both moments, with the
+        flat layout (names / offsets) so that it can be re-applied to a freshly built network."""
+        return {"step": self.step_count, "exp_avg": self.m.detach().clone(), "exp_avg_sq": self.v.detach().clone(),
+                "names": list(self.names), "offsets": dict(self.offsets)}
+
+    def load_optimizer_state(self, state: Dict[str, object]):
+        """Inverse of optimizer_state() (resume, trainer.py:90-94).  The flat layout must match (same architecture)."""
+        if list(state["names"]) != list(self.names) or dict(state["offsets"]) != dict(self.offsets):
+            raise RuntimeError("optimizer state was saved for a different parameter layout")
+        if tuple(state["exp_avg"].shape) != tuple(self.m.shape):
+            raise RuntimeError("optimizer state size mismatch")
+        self.m.copy_(state["exp_avg"].to(self.m.device))
+        self.v.copy_(state["exp_avg_sq"].to(self.v.device))
+        self.step_count = int(state["step"])
+        self.step_dev.fill_(self.step_count)               # the device-side counter the fused AdamW kernel increments
+
     def adamw_step(self, lr: float, grad_scale: float = 1.0):
         """torch.optim.AdamW defaults of trainer.py:33-38 (betas .9/.999, eps 1e-8, weight_decay 1e-2)."""
         self.step_count += 1

@@ -121,5 +121,15 @@ class Trainer:
         torch.save(self.discriminator.state_dict(), os.path.join(save_dir, f"discriminator_epoch_{step}.pt"))
         e = self.engine
         for name, fp in (("generator", e.gp), ("discriminator", e.dp)):
-            torch.save({"step": fp.step_count, "exp_avg": fp.m, "exp_avg_sq": fp.v, "names": fp.names, "offsets": fp.offsets},
-                       os.path.join(save_dir, f"{name}_optim_epoch_{step}.pt"))
+            torch.save(fp.optimizer_state(), os.path.join(save_dir, f"{name}_optim_epoch_{step}.pt"))
+
+    def load_checkpoints(self, step: int, save_dir: Optional[str] = None):
+        """Resume from the four files save_checkpoints(step) wrote (the reference only reloads its pretrain checkpoint,
+        trainer.py:90-94; here both networks and both AdamW states)."""
+        save_dir = save_dir or os.path.join("runs", self.config.experiment.name)
+        self.generator.load_state_dict(torch.load(os.path.join(save_dir, f"generator_epoch_{step}.pt"), map_location="cpu"))
+        self.discriminator.load_state_dict(torch.load(os.path.join(save_dir, f"discriminator_epoch_{step}.pt"), map_location="cpu"))
+        e = self.engine
+        for name, fp in (("generator", e.gp), ("discriminator", e.dp)):
+            fp.load_optimizer_state(torch.load(os.path.join(save_dir, f"{name}_optim_epoch_{step}.pt"), map_location="cpu"))
+            fp.version += 1                                  # parameters changed: weight packs are stale
