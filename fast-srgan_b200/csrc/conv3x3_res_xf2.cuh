@@ -1,0 +1,477 @@
+// conv3x3_res_xf2.cuh - EXPERIMENTAL (own library, not yet run on hardware): the FIRST conv of a residual block (and the
+// bottleneck conv) with the previous block's  bn2 + skip  (reference model.py:65 + 69) fused into its load path.
+//
+//   x_next = InstanceNorm(c2_prev) + x_prev      formed in shared memory on the staged halo tile of the RAW c2_prev,
+//   out, stats = conv3x3(x_next)                 and x_next's own-tile pixels are written back for the next skip.
+//
+// Together with the validated fsr_conv3x3_c64_in (bn1 + relu1 fused into conv2) this removes 8 of the 9
+// remaining `instnorm_apply` passes of Generator.forward (109 us each at b32 180x320, at the HBM roofline).
+// The kernel text is conv3x3_c64_kernel<64, EPI_RAW_STATS, T, true, true> from conv3x3_tc.cuh (GPU-validated) with the
+// input-transform role replaced; kept as a separate kernel so that the validated library is not rebuilt from changed
+// sources.  Parity test: tests/test_experimental_gpu.py (opt-in).
+#pragma once
+#include "conv3x3_tc.cuh"
+
+namespace fsr {
+
+struct ConvParamsXf2 : ConvParams {
+  const void* in_res;   // x_prev  [N,H,W,64] NHWC T: the residual added to the normalised input
+  void* x_out;          // x_next  [N,H,W,64] NHWC T: written by this kernel (must alias neither x_prev nor the raw input)
+};
+
+template <typename T>
+__global__ void __launch_bounds__(ConvCfg<64, true>::kThreadsXf, 1)
+conv3x3_c64_xf2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
+                       const __grid_constant__ CUtensorMap tm_out, const ConvParamsXf2 p) {
+  // specialisation of conv3x3_c64_kernel<64, EPI_RAW_STATS, T, HALO1 = true, XF = true> (text below is that kernel's;
+  // only the input-transform role differs)
+  constexpr int NS = 64;
+  constexpr int EPI = EPI_RAW_STATS;
+  constexpr bool HALO1 = true;
+  constexpr bool XF = true;
+  // NHWC outputs leave through a TMA store of the staged (swizzled) tile: no smem read-back, hardware edge clipping
+  constexpr bool kTmaStore = (EPI == EPI_RAW_STATS || EPI == EPI_BIAS_ACT);
+  using Cfg = ConvCfg<NS, HALO1>;
+  using Geo = ConvGeo<HALO1>;
+  constexpr int TH = Geo::TH, TW = Geo::TW;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_w = smem;
+  uint8_t* smem_a = smem_w + Cfg::kWBytes;
+  uint8_t* smem_stg = smem_a + Cfg::kStages * Geo::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stg + Cfg::kStagingBytes);
+  uint64_t* full_bar = bars;                       // [kStages]
+  uint64_t* empty_bar = bars + Cfg::kStages;       // [kStages]
+  uint64_t* w_bar = bars + 2 * Cfg::kStages;       // [1]
+  uint64_t* tfull_bar = w_bar + 1;                 // [4]
+  uint64_t* tempty_bar = tfull_bar + 4;            // [4]
+  uint64_t* xfull_bar = tempty_bar + 4;            // [kStages] (XF: the stage's halo tile has been transformed)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xfull_bar + Cfg::kStages);
+  float* smem_bias = reinterpret_cast<float*>(tmem_slot + 4);   // [NS]
+  static_assert(!XF || (HALO1 && NS == 64), "the fused input transform exists for the single-halo-tile 64->64 conv");
+  // the MMA warp consumes a stage once it is `ready`: filled by TMA, and in the XF variant transformed in place
+  uint64_t* ready_bar = XF ? xfull_bar : full_bar;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int slice = blockIdx.x % p.num_slices;
+  const int cta_in_slice = blockIdx.x / p.num_slices;
+  const int ctas_per_slice = gridDim.x / p.num_slices;
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+  // contiguous tile range per CTA: consecutive tiles share halos (L2 locality) and mostly one image
+  // (InstanceNorm statistics stay in registers across tiles, see the epilogue)
+  const int t_begin = (int)(((long long)cta_in_slice * p.num_tiles) / ctas_per_slice);
+  const int t_end = (int)(((long long)(cta_in_slice + 1) * p.num_tiles) / ctas_per_slice);
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_x);
+    tma_prefetch_desc(&tm_w);
+    for (int i = 0; i < Cfg::kStages; ++i) {
+      mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); mbar_init(&xfull_bar[i], kXfWarps);
+    }
+    mbar_init(w_bar, 1);
+    for (int i = 0; i < 4; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+    fence_mbar_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  // accumulator ring: HALO1 issues the MMAs of TWO tiles interleaved (two independent accumulation chains keep the
+  // tensor pipe busy while each chain waits on its own previous MMA) -> 4 accumulators, tile `it` uses
+  // ((it>>1)&1)*2 + (it&1), reused every 4 tiles; HALO0 keeps the plain double buffer.
+  auto acc_of = [](int it) { return Cfg::kPair ? (((it >> 1) & 1) * 2 + (it & 1)) : (it & 1); };
+  auto phase_of = [](int it) { return (uint32_t)(Cfg::kPair ? ((it >> 2) & 1) : ((it >> 1) & 1)); };
+  if (EPI != EPI_RAW_STATS && p.bias != nullptr) {
+    for (int i = threadIdx.x; i < NS; i += blockDim.x) smem_bias[i] = p.bias[slice * NS + i];
+  } else {
+    for (int i = threadIdx.x; i < NS; i += blockDim.x) smem_bias[i] = 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // =============================== TMA producer (whole warp runs the loop, one elected lane issues)
+    if (elect_one()) {
+      mbar_arrive_expect_tx(w_bar, Cfg::kWBytes);
+      for (int tap = 0; tap < 9; ++tap)
+        tma_load_2d(smem_w + tap * NS * 128, &tm_w, w_bar, 0, tap * p.cout_total + slice * NS);
+    }
+    __syncwarp();
+    int stage = 0; uint32_t phase = 0;
+    for (int t = t_begin; t < t_end; ++t) {
+      const int n = t / tiles_per_img;
+      const int rem = t - n * tiles_per_img;
+      const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+      const int x0 = tx * TW, y0 = ty * TH;
+#pragma unroll
+      for (int s = 0; s < Geo::kLoads; ++s) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&full_bar[stage], Geo::kTxBytes);
+          tma_load_4d(smem_a + stage * Geo::kStageBytes, &tm_x, &full_bar[stage], 0,
+                      HALO1 ? x0 - 1 : x0 + s - 1, y0 - 1, n);
+        }
+        __syncwarp();
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer: warp-uniform control flow so that descriptors live in
+    // uniform registers; only the tcgen05 instructions are predicated on the elected lane.
+    constexpr uint32_t idesc = make_idesc_f16(128, NS, std::is_same<T, __nv_bfloat16>::value);
+    const uint32_t a_lo0 = desc_lo_sw128(smem_u32(smem_a));
+    const uint32_t b_lo0 = desc_lo_sw128(smem_u32(smem_w));
+    mbar_wait(w_bar, 0);
+    tc_fence_after();
+    int stage = 0; uint32_t phase = 0;
+    int it = 0;
+    if constexpr (HALO1) {
+      constexpr int kStep = Cfg::kPair ? 2 : 1;
+      for (int t = t_begin; t < t_end; t += kStep, it += kStep) {
+        const bool two = Cfg::kPair && (t + 1 < t_end);
+        const int acc_a = acc_of(it), acc_b = Cfg::kPair ? acc_of(it + 1) : acc_a;
+        const uint32_t ph = phase_of(it);
+        mbar_wait(&tempty_bar[acc_a], ph ^ 1);
+        if (two) mbar_wait(&tempty_bar[acc_b], ph ^ 1);
+        tc_fence_after();
+        const int stage_a = stage;
+        const uint32_t phase_a = phase;
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        const int stage_b = stage;
+        const uint32_t phase_b = phase;
+        if (two) { if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; } }
+        mbar_wait(&ready_bar[stage_a], phase_a);
+        if (two) mbar_wait(&ready_bar[stage_b], phase_b);
+        tc_fence_after();
+        const uint32_t a_lo_a = a_lo0 + stage_a * (Geo::kStageBytes >> 4);
+        const uint32_t a_lo_b = a_lo0 + stage_b * (Geo::kStageBytes >> 4);
+        const uint32_t d_a = tmem_base + acc_a * NS, d_b = tmem_base + acc_b * NS;
+        if (elect_one()) {
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+              // halo row r*10+s: the start address is only 128-B aligned and core groups are 1280 B apart.
+              // The 128B swizzle XOR is a function of the absolute smem address bits [7,10) (measured on
+              // B200: SBO = 1280 reads TMA-written data correctly), so the base-offset field stays 0.
+              constexpr uint32_t kSbo = (uint32_t)((TW + 2) * 128) >> 4;     // 1280 B between core groups
+              const uint32_t hi = kSbo | (1u << 14) | (2u << 29);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint32_t aoff = (uint32_t)(((r * (TW + 2) + s) * 128 + k * 32) >> 4);
+                const uint64_t bdesc = desc_join(b_lo0 + (((r * 3 + s) * (NS * 128) + k * 32) >> 4), kDescHiSw128);
+                if (two && p.ws) {
+                  umma_f16_ws_fill(d_a, desc_join(a_lo_a + aoff, hi), bdesc, idesc, (s | r | k) != 0 ? 1u : 0u);
+                  umma_f16_ws_lastuse(d_b, desc_join(a_lo_b + aoff, hi), bdesc, idesc, (s | r | k) != 0 ? 1u : 0u);
+                } else {
+                  umma_f16(d_a, desc_join(a_lo_a + aoff, hi), bdesc, idesc, (s | r | k) != 0 ? 1u : 0u);
+                  if (two) umma_f16(d_b, desc_join(a_lo_b + aoff, hi), bdesc, idesc, (s | r | k) != 0 ? 1u : 0u);
+                }
+              }
+            }
+          }
+          umma_commit(&empty_bar[stage_a]);
+          if (two) umma_commit(&empty_bar[stage_b]);
+          umma_commit(&tfull_bar[acc_a]);
+          if (two) umma_commit(&tfull_bar[acc_b]);
+        }
+        __syncwarp();
+      }
+    } else {
+      for (int t = t_begin; t < t_end; ++t, ++it) {
+        const int acc = acc_of(it);
+        const uint32_t acc_phase = phase_of(it);
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * NS;
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_lo = a_lo0 + stage * (Geo::kStageBytes >> 4);
+          if (elect_one()) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t adesc = desc_join(a_lo + ((r * (TW * 128) + k * 32) >> 4), kDescHiSw128);
+                const uint64_t bdesc = desc_join(b_lo0 + (((r * 3 + s) * (NS * 128) + k * 32) >> 4), kDescHiSw128);
+                umma_f16(d_tmem, adesc, bdesc, idesc, (s | r | k) != 0 ? 1u : 0u);
+              }
+            }
+            umma_commit(&empty_bar[stage]);
+            if (s == 2) umma_commit(&tfull_bar[acc]);
+          }
+          __syncwarp();
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (XF && warp >= 2 + Cfg::kEpiWarps) {
+    // =============================== input-transform warps (XF2) ===============================
+    // y = (raw - mean[n,c]) * rstd[n,c] + residual  (bn2 + skip, model.py:65+69 / bottleneck :94 fed by the chain) applied
+    // IN PLACE to the TMA-written halo tile of the RAW conv2 output; the residual x comes straight from global memory
+    // (16-byte vectors, 1.4x halo overhead, L2 hits for the halo) and the tile's OWN 16x8 pixels of y are written back to
+    // x_out for the next block's skip connection.  Same fp32 operations as instnorm_apply_kernel (normalise, no
+    // activation, add the residual as float, round once) -> bit-identical activations.
+    {
+      const int tid = threadIdx.x - (64 + 32 * Cfg::kEpiWarps);      // 0 .. 32*kXfWarps-1
+      const int g = tid & 7, r_first = tid >> 3;
+      constexpr int kRowStep = 4 * kXfWarps;
+      const double inv_hw = 1.0 / (double)(p.H * p.W);
+      float mean[8], rstd[8];
+      int cur_n = -1;
+      int stage = 0; uint32_t phase = 0;
+      const T* res = reinterpret_cast<const T*>(p.in_res);
+      T* xo = reinterpret_cast<T*>(p.x_out);
+      for (int t = t_begin; t < t_end; ++t) {
+        const int n = t / tiles_per_img;
+        const int rem = t - n * tiles_per_img;
+        const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+        const int x0 = tx * TW, y0 = ty * TH;
+        if (n != cur_n) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            stat_mean_rstd(p.in_stats + ((size_t)n * 64 + 8 * g + k) * 2, inv_hw, p.in_eps, mean[k], rstd[k]);
+          cur_n = n;
+        }
+        constexpr int kRows = Geo::kBoxW * Geo::kBoxH;                    // 180
+        // coordinates of the NEXT tile: its residual rows are prefetched into L2 one tile (~1.5 us) ahead, so that the
+        // loads of the rolled loop below are L2 hits (x_prev was written two launches ago: 236 MB, not L2 resident)
+        const bool has_next = t + 1 < t_end;
+        const int tn = has_next ? t + 1 : t;
+        const int nn = tn / tiles_per_img;
+        const int remn = tn - nn * tiles_per_img;
+        const int tyn = remn / p.tiles_x, txn = remn - tyn * p.tiles_x;
+        const int x0n = txn * TW, y0n = tyn * TH;
+        mbar_wait(&full_bar[stage], phase);
+        const uint32_t base = smem_u32(smem_a + stage * Geo::kStageBytes);
+#pragma unroll 4
+        for (int r = r_first; r < kRows; r += kRowStep) {
+          const int by = r / Geo::kBoxW, bx = r - by * Geo::kBoxW;
+          const int gy = y0 - 1 + by, gx = x0 - 1 + bx;
+          const bool ok = gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
+          const size_t goff = (((size_t)n * p.H + (ok ? gy : 0)) * p.W + (ok ? gx : 0)) * 64 + 8 * g;
+          const uint4 rv = *reinterpret_cast<const uint4*>(res + goff);
+          if (has_next && (g & 1) == 0) {          // one prefetch per 32-byte sector of the next tile's row
+            const int gyn = y0n - 1 + by, gxn = x0n - 1 + bx;
+            if (gyn >= 0 && gyn < p.H && gxn >= 0 && gxn < p.W)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(res + (((size_t)nn * p.H + gyn) * p.W + gxn) * 64 + 8 * g));
+          }
+          const uint32_t addr = base + (uint32_t)r * 128u + (uint32_t)((g ^ (r & 7)) << 4);
+          const uint4 v = ld_shared_v4(addr);
+          const uint32_t vu[4] = {v.x, v.y, v.z, v.w};
+          const uint32_t su[4] = {rv.x, rv.y, rv.z, rv.w};
+          uint32_t ou[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 f = Cvt<T>::unpack2(vu[k]);
+            const float2 s2 = Cvt<T>::unpack2(su[k]);
+            float a = (f.x - mean[2 * k]) * rstd[2 * k];
+            float b = (f.y - mean[2 * k + 1]) * rstd[2 * k + 1];
+            a += s2.x;
+            b += s2.y;
+            ou[k] = ok ? Cvt<T>::pack2(a, b) : vu[k];                     // rows outside the image stay zero
+          }
+          st_shared_v4(addr, ou[0], ou[1], ou[2], ou[3]);
+          // write-back of the tile's own pixels (each image pixel is interior to exactly one tile)
+          if (ok && by >= 1 && by <= TH && bx >= 1 && bx <= TW)
+            *reinterpret_cast<uint4*>(xo + goff) = make_uint4(ou[0], ou[1], ou[2], ou[3]);
+        }
+        fence_proxy_async();                 // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&xfull_bar[stage]);
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // =============================== epilogue warps ===============================
+    const int ew = warp - 2;
+    const int q = warp & 3;                      // TMEM lane quarter this warp may access
+    const int egroup = ew >> 2;                  // with 8 warps: group g serves tiles with (it & 1) == g
+    const uint32_t stg = smem_u32(smem_stg + ew * 4096);   // warp-private 32 x 128 B transpose buffer
+    const int m = q * 32 + lane;                 // accumulator row == pixel within the tile
+    const int yy = m / TW, xx = m % TW;
+    float prelu_a = 0.f;
+    if (EPI == EPI_PS_PRELU || (EPI == EPI_BIAS_ACT && p.act == ACT_PRELU)) prelu_a = __ldg(p.alpha);
+    const float slope = (EPI == EPI_PS_PRELU || p.act == ACT_PRELU) ? prelu_a : p.slope;
+    // InstanceNorm statistics of channels (2*lane, 2*lane+1) of the current image, carried across tiles
+    // (each TILE's partial sums are converted to fixed point before they are added up: the totals are independent of
+    //  how tiles are distributed over warps / CTAs / launches -> batch-size and run-to-run invariant)
+    long long st_s0 = 0, st_q0 = 0, st_s1 = 0, st_q1 = 0;
+    int st_n = -1;
+    auto flush_stats = [&](int img) {
+      if (EPI == EPI_RAW_STATS && img >= 0) {
+        long long* st = p.stats + ((size_t)img * p.cout_total + slice * NS + 2 * lane) * 2;
+        stat_atomic_add(st + 0, st_s0);
+        stat_atomic_add(st + 1, st_q0);
+        stat_atomic_add(st + 2, st_s1);
+        stat_atomic_add(st + 3, st_q1);
+      }
+      st_s0 = st_q0 = st_s1 = st_q1 = 0;
+    };
+    int it = 0;
+    for (int t = t_begin; t < t_end; ++t, ++it) {
+      if (Cfg::kEpiWarps == 8 && (it & 1) != egroup) continue;
+      const int acc = acc_of(it);
+      const uint32_t acc_phase = phase_of(it);
+      const int n = t / tiles_per_img;
+      const int rem = t - n * tiles_per_img;
+      const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+      const int x0 = tx * TW, y0 = ty * TH;
+      const int y = y0 + yy, x = x0 + xx;
+      const bool pvalid = (y < p.H) && (x < p.W);
+      const bool interior = (y0 + TH <= p.H) && (x0 + TW <= p.W);   // warp-uniform
+      if (EPI == EPI_RAW_STATS && n != st_n) { flush_stats(st_n); st_n = n; }
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * NS;
+
+      if constexpr (EPI == EPI_HEAD_TANH) {
+        uint32_t r[16];
+        tmem_ld16(t_row, r);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        if (pvalid) {
+          float o[3];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const float v = __uint_as_float(r[c]) + smem_bias[c];
+            o[c] = p.out_u8 >= 2 ? v : tanhf(v);
+          }
+          if (p.out_u8 == 1) {
+            // reference inference.py:54-56: ((y+1)/2*255).astype(uint8)  (truncation)
+            uint8_t* o8 = reinterpret_cast<uint8_t*>(p.out) + ((size_t)(n * p.H + y) * p.W + x) * 3;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              float f = (o[c] + 1.0f) / 2.0f * 255.0f;
+              o8[c] = (uint8_t)(int)fminf(fmaxf(f, 0.f), 255.f);
+            }
+          } else {
+            float* of = reinterpret_cast<float*>(p.out);
+            const size_t plane = (size_t)p.H * p.W;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              float* dst = of + ((size_t)n * 3 + c) * plane + (size_t)y * p.W + x;
+              *dst = (p.out_u8 == 3) ? *dst + o[c] : o[c];
+            }
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int chunk = 0; chunk < NS / 64; ++chunk) {
+          uint32_t pk[32];                        // 64 output values packed to 2-byte pairs
+          {
+            uint32_t r0[32], r1[32];
+            tmem_ld32(t_row + chunk * 64, r0);
+            tmem_ld32(t_row + chunk * 64 + 32, r1);
+            tmem_ld_wait();
+            if (chunk == NS / 64 - 1) {           // all TMEM reads of this accumulator are done
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float a0 = __uint_as_float(r0[2 * i]), a1 = __uint_as_float(r0[2 * i + 1]);
+              float b0 = __uint_as_float(r1[2 * i]), b1 = __uint_as_float(r1[2 * i + 1]);
+              if constexpr (EPI != EPI_RAW_STATS) {
+                a0 += smem_bias[chunk * 64 + 2 * i];      a1 += smem_bias[chunk * 64 + 2 * i + 1];
+                b0 += smem_bias[chunk * 64 + 32 + 2 * i]; b1 += smem_bias[chunk * 64 + 32 + 2 * i + 1];
+                if constexpr (EPI == EPI_PS_PRELU) {
+                  a0 = a0 >= 0.f ? a0 : a0 * slope; a1 = a1 >= 0.f ? a1 : a1 * slope;
+                  b0 = b0 >= 0.f ? b0 : b0 * slope; b1 = b1 >= 0.f ? b1 : b1 * slope;
+                } else {
+                  a0 = apply_act(a0, p.act, slope); a1 = apply_act(a1, p.act, slope);
+                  b0 = apply_act(b0, p.act, slope); b1 = apply_act(b1, p.act, slope);
+                }
+              }
+              pk[i] = Cvt<T>::pack2(a0, a1);
+              pk[16 + i] = Cvt<T>::pack2(b0, b1);
+            }
+          }
+          const int col0 = slice * NS + chunk * 64;   // first GEMM column of this chunk
+
+          // ---- registers -> swizzled smem (row = pixel, 8 x 16B chunks) -> global
+          if constexpr (kTmaStore) {
+            if (lane == 0) tma_store_wait_read();       // the previous TMA store has finished reading this buffer
+          }
+          __syncwarp();
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            st_shared_v4(stg + lane * 128 + ((k ^ (lane & 7)) << 4), pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
+          if constexpr (kTmaStore) {
+            fence_proxy_async();                         // generic-proxy writes -> visible to the TMA (async proxy)
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_4d(&tm_out, smem_stg + ew * 4096, col0, x0, y0 + (q * 32) / TW, n);
+              tma_store_commit();
+            }
+          } else {
+            __syncwarp();
+            uint4 val[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int rrow = j * 4 + (lane >> 3);
+              val[j] = ld_shared_v4(stg + rrow * 128 + (((lane & 7) ^ (rrow & 7)) << 4));
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int rrow = j * 4 + (lane >> 3);
+              const int mm = q * 32 + rrow;
+              const int py = y0 + mm / TW, px = x0 + mm % TW;
+              if (interior || (py < p.H && px < p.W)) {
+                T* dst;
+                if constexpr (EPI == EPI_PS_PRELU) {
+                  const int qq = col0 >> 6;               // GEMM column block = 2*i + j
+                  const int oy = 2 * py + (qq >> 1), ox = 2 * px + (qq & 1);
+                  dst = reinterpret_cast<T*>(p.out) + ((size_t)(n * 2 * p.H + oy) * (2 * p.W) + ox) * 64;
+                } else {
+                  dst = reinterpret_cast<T*>(p.out) + ((size_t)(n * p.H + py) * p.W + px) * p.cout_total + col0;
+                }
+                *reinterpret_cast<uint4*>(dst + (lane & 7) * 8) = val[j];
+              }
+            }
+          }
+
+          if constexpr (EPI == EPI_RAW_STATS) {
+            // InstanceNorm statistics (reference model.py:55,65,94,132) of the STORED (rounded) values, reduced in
+            // registers: a butterfly over the warp's 32 pixels leaves channels (2L, 2L+1) in lane L.
+            float v[64];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float2 f = Cvt<T>::unpack2(pk[i]);
+              v[2 * i] = pvalid ? f.x : 0.f;
+              v[2 * i + 1] = pvalid ? f.y : 0.f;
+            }
+            warp_reduce64(v, lane);
+            const float sum0 = v[0], sum1 = v[1];
+            if constexpr (XF) asm volatile("" ::: "memory");   // XF runs at 146 registers: keep the two butterflies apart
+            float sq[64];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float2 f = Cvt<T>::unpack2(pk[i]);
+              sq[2 * i] = pvalid ? f.x * f.x : 0.f;
+              sq[2 * i + 1] = pvalid ? f.y * f.y : 0.f;
+            }
+            warp_reduce64(sq, lane);
+            v[0] = sum0; v[1] = sum1;
+            st_s0 += stat_fix(v[0], kStatSumScale); st_q0 += stat_fix(sq[0], kStatSqScale);
+            st_s1 += stat_fix(v[1], kStatSumScale); st_q1 += stat_fix(sq[1], kStatSqScale);
+          }
+        }
+      }
+    }
+    if (kTmaStore && lane == 0) tma_store_wait_all();
+    if (EPI == EPI_RAW_STATS) flush_stats(st_n);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+}
+
+}  // namespace fsr

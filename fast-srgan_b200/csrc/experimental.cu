@@ -2,6 +2,7 @@
 // (libfsr_b200_experimental.so) so that libfsr_b200.so stays exactly the binary the GPU suite validated.
 // Nothing in the product loads this library; tests/test_experimental_gpu.py does, when FSR_TEST_EXPERIMENTAL=1.
 #include "conv3x3_up_2cta.cuh"
+#include "conv3x3_res_xf2.cuh"
 
 #include <cudaTypedefs.h>
 
@@ -74,9 +75,51 @@ int launch_up_2cta(const void* x, const void* w_packed, ConvParams p, int dtype,
   return e == cudaSuccess ? FSR_OK : FSR_ERR_CUDA_BASE - (int)e;
 }
 
+template <typename T>
+int launch_res_xf2(const void* x_raw, const void* w_packed, ConvParamsXf2 p, int dtype, cudaStream_t st) {
+  using Cfg = ConvCfg<64, true>;
+  using Geo = ConvGeo<true>;
+  auto kern = conv3x3_c64_xf2_kernel<T>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+  if (e != cudaSuccess) return FSR_ERR_CUDA_BASE - (int)e;
+  p.tiles_x = (p.W + Geo::TW - 1) / Geo::TW;
+  p.tiles_y = (p.H + Geo::TH - 1) / Geo::TH;
+  p.num_tiles = p.N * p.tiles_x * p.tiles_y;
+  p.ws = 1;
+  CUtensorMap tmx, tmw, tmo;
+  int rc = act_map(&tmx, x_raw, p.N, p.H, p.W, Geo::kBoxW, Geo::kBoxH, dtype);
+  if (rc) return rc;
+  if ((rc = w_map(&tmw, w_packed, 9 * 64, 64, dtype))) return rc;
+  if ((rc = act_map(&tmo, p.out, p.N, p.H, p.W, Geo::TW, 32 / Geo::TW, dtype))) return rc;   // one epilogue warp's TMA store
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int grid = sms < p.num_tiles ? sms : p.num_tiles;
+  kern<<<grid, Cfg::kThreadsXf, Cfg::kSmemBytes, st>>>(tmx, tmw, tmo, p);
+  e = cudaGetLastError();
+  return e == cudaSuccess ? FSR_OK : FSR_ERR_CUDA_BASE - (int)e;
+}
+
 }  // namespace
 
 extern "C" {
+
+/* x_next = InstanceNorm(x_raw; in_stats) + res (written to x_out, NHWC [N,H,W,64]);  out, stats = conv3x3(x_next) RAW_STATS.
+ * model.py:65+69 of block l folded into :47-54 of block l+1 (or the bottleneck :87-93).  x_out must alias neither res nor x_raw;
+ * stats [N,64,2] int64 must be zeroed by the caller. */
+int fsrx_conv3x3_c64_res_in(const void* x_raw, const int64_t* in_stats, float in_eps, const void* res, void* x_out,
+                            const void* w_packed, void* out, int64_t* stats, int N, int H, int W, int dtype, void* stream) {
+  if (!x_raw || !in_stats || !res || !x_out || !w_packed || !out || !stats) return FSR_ERR_BAD_ARG;
+  if (x_out == res || x_out == x_raw || out == x_raw || N <= 0 || H <= 0 || W <= 0) return FSR_ERR_BAD_ARG;
+  ConvParamsXf2 p{};
+  p.N = N; p.H = H; p.W = W; p.out = out; p.stats = reinterpret_cast<long long*>(stats);
+  p.cout_total = 64; p.num_slices = 1;
+  p.in_stats = reinterpret_cast<const long long*>(in_stats); p.in_eps = in_eps; p.in_alpha = nullptr;
+  p.in_res = res; p.x_out = x_out;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == 1) return launch_res_xf2<__nv_bfloat16>(x_raw, w_packed, p, dtype, st);
+  return launch_res_xf2<__half>(x_raw, w_packed, p, dtype, st);
+}
 
 /* Same contract as fsr_conv3x3_c64(..., FSR_EPI_PS_PRELU): x [N,H,W,64] NHWC, w_packed [9][256][64] (pixel-shuffle column
  * order), bias_packed [256], alpha device pointer -> out [N,2H,2W,64] = PReLU(PixelShuffle2(conv + bias)).  dtype 0 = fp16, 1 = bf16. */
