@@ -92,3 +92,29 @@ def test_metrics_and_data_need_cuda():
         metrics.ValidationMetrics("cpu")
     with pytest.raises(RuntimeError, match="no CPU"):
         data.DeviceImageCache([np.zeros((3, 8, 8), np.uint8)], device="cpu")
+
+
+def test_crop_offsets_are_in_bounds_and_seeded_per_rank():
+    """GpuCropLoader.draw (dataloader.py:27-29 for a batch): offsets keep the HR crop inside every image, are reproducible
+    for a (seed, rank) and differ between ranks.  Host logic only: a stub stands in for the device-resident cache."""
+    import types
+    from fast_srgan_b200.data import GpuCropLoader, ShardedReplacementSampler
+    shapes = [(96, 96), (100, 131), (240, 97), (96, 300)]
+    stub = types.SimpleNamespace(shapes=shapes, device=torch.device("cpu"))
+    pin = torch.Tensor.pin_memory
+    torch.Tensor.pin_memory = lambda self, *a, **k: self            # no CUDA in this container
+    try:
+        def loader(rank):
+            return GpuCropLoader(stub, ShardedReplacementSampler(len(shapes), 64, 8, seed=1, rank=rank, world=2), 24, 4, seed=9)
+        idx = torch.arange(32) % len(shapes)
+        a, b, c = loader(0).draw(idx), loader(0).draw(idx), loader(1).draw(idx)
+    finally:
+        torch.Tensor.pin_memory = pin
+    assert a.dtype == torch.int32 and tuple(a.shape) == (32, 3) and torch.equal(a, b) and not torch.equal(a, c)
+    for i, cy, cx in a.tolist():
+        h, w = shapes[i]
+        assert 0 <= cy <= h - 96 and 0 <= cx <= w - 96
+    assert all(int(a[k, 1]) == 0 and int(a[k, 2]) == 0 for k in range(32) if shapes[int(a[k, 0])] == (96, 96))
+    with pytest.raises(ValueError):
+        GpuCropLoader(types.SimpleNamespace(shapes=[(95, 200)], device=torch.device("cpu")),
+                      ShardedReplacementSampler(1, 8, 8, seed=1), 24, 4)
