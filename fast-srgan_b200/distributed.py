@@ -49,3 +49,16 @@ def allreduce_flat(flat_grad: torch.Tensor, group=None) -> torch.Tensor:
     if dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
     return flat_grad
+
+
+def broadcast_flat(flat: torch.Tensor, group=None, src: int = 0) -> torch.Tensor:
+    """Rank `src`'s flat parameter / Adam-moment buffer to every rank (replica initialisation and resume)."""
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.broadcast(flat, src=src, group=group)
+    return flat
+
+
+def rank_and_world(group=None) -> Tuple[int, int]:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1

@@ -61,6 +61,7 @@ class FlatParams:
             self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)     # device-side step counter (graph safe)
         self.step_count = 0
         self.version = 0
+        self.ext_version = 0                               # bumped when the parameters are changed from OUTSIDE the engine
         module._fsr_flat = self                            # lets the module's own forward reuse this aliasing
 
     def aliases(self, module) -> bool:
@@ -70,22 +71,42 @@ class FlatParams:
     def zero_grad(self):
         self.grad.zero_()
 
-    def optimizer_state(self) -> Dict[str, object]:
-        """AdamW state of this network (what `optim.state_dict()` holds in trainer.py:149-156): step + both moments, with the
-        flat layout (names / offsets) so that it can be re-applied to a freshly built network."""
-        return {"step": self.step_count, "exp_avg": self.m.detach().clone(), "exp_avg_sq": self.v.detach().clone(),
-                "names": list(self.names), "offsets": dict(self.offsets)}
+    def optimizer_state(self, lr: float = 1e-4) -> Dict[str, object]:
+        """AdamW state in **torch.optim.AdamW.state_dict() format** (what trainer.py:149-156 and the pretrain files of
+        trainer.py:131-141 hold): per-parameter {step, exp_avg, exp_avg_sq} in `module.parameters()` order plus one
+        param_group with the hyper-parameters of trainer.py:33-38 - loadable by the reference's optimizer and vice versa."""
+        state = {}
+        for i, n in enumerate(self.names):
+            o, numel = self.offsets[n], self.p[n].numel()
+            state[i] = {"step": torch.tensor(float(self.step_count)),
+                        "exp_avg": self.m[o:o + numel].view_as(self.p[n]).detach().clone(),
+                        "exp_avg_sq": self.v[o:o + numel].view_as(self.p[n]).detach().clone()}
+        group = {"lr": lr, "betas": (0.9, 0.999), "eps": 1e-8, "weight_decay": 1e-2, "amsgrad": False, "maximize": False,
+                 "foreach": None, "capturable": False, "differentiable": False, "fused": True,
+                 "params": list(range(len(self.names)))}
+        return {"state": state, "param_groups": [group]}
 
     def load_optimizer_state(self, state: Dict[str, object]):
-        """Inverse of optimizer_state() (resume, trainer.py:90-94).  The flat layout must match (same architecture)."""
-        if list(state["names"]) != list(self.names) or dict(state["offsets"]) != dict(self.offsets):
-            raise RuntimeError("optimizer state was saved for a different parameter layout")
-        if tuple(state["exp_avg"].shape) != tuple(self.m.shape):
-            raise RuntimeError("optimizer state size mismatch")
-        self.m.copy_(state["exp_avg"].to(self.m.device))
-        self.v.copy_(state["exp_avg_sq"].to(self.v.device))
-        self.step_count = int(state["step"])
-        self.step_dev.fill_(self.step_count)               # the device-side counter the fused AdamW kernel increments
+        """Inverse of optimizer_state(); accepts a genuine torch.optim.AdamW state_dict of the same architecture
+        (resume, trainer.py:90-94).  An empty `state` (optimizer that never stepped) resets the moments."""
+        st = state["state"]
+        if len(st) not in (0, len(self.names)):
+            raise RuntimeError(f"optimizer state holds {len(st)} parameters, this network has {len(self.names)}")
+        self.m.zero_()
+        self.v.zero_()
+        step = 0
+        for i, n in enumerate(self.names):
+            if i not in st:
+                continue
+            o, numel = self.offsets[n], self.p[n].numel()
+            if tuple(st[i]["exp_avg"].shape) != tuple(self.p[n].shape):
+                raise RuntimeError(f"optimizer state of parameter {i} ({n}) has shape {tuple(st[i]['exp_avg'].shape)}, "
+                                   f"expected {tuple(self.p[n].shape)}")
+            self.m[o:o + numel].copy_(st[i]["exp_avg"].reshape(-1).to(self.m.device, torch.float32))
+            self.v[o:o + numel].copy_(st[i]["exp_avg_sq"].reshape(-1).to(self.v.device, torch.float32))
+            step = int(float(st[i]["step"]))
+        self.step_count = step
+        self.step_dev.fill_(step)                          # the device-side counter the fused AdamW kernel increments
 
     def adamw_step(self, lr: float, grad_scale: float = 1.0):
         """torch.optim.AdamW defaults of trainer.py:33-38 (betas .9/.999, eps 1e-8, weight_decay 1e-2)."""
@@ -275,8 +296,13 @@ class VGGNet:
         self.idx = vgg_conv_indices()
         self.P: Dict[str, torch.Tensor] = {}
         self._packed = False
+        self._version = -1
 
     def pack(self, need_bwd: bool):
+        ver = getattr(self.m, "_weights_version", 0)
+        if ver != self._version:                     # perceptual_network.load_state_dict() after the first step: repack
+            self.P.clear()
+            self._packed, self._version = False, ver
         if self._packed and (not need_bwd or "bwd" in self.P):
             return
         sd = {k: v for k, v in self.m.state_dict().items()}
@@ -354,6 +380,14 @@ class GANEngine:
         self.world = 1
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.world = torch.distributed.get_world_size(process_group)
+        if self.world > 1:
+            # replicas must START identical (they stay identical because every rank applies the same reduced gradient):
+            # rank 0's parameters and Adam moments win, whatever each rank's RNG produced at construction
+            from .distributed import broadcast_flat
+            for fp in (self.gp, self.dp):
+                for buf in (fp.flat, fp.m, fp.v):
+                    broadcast_flat(buf, self.pg)
+                fp.version += 1
 
     def _allreduce(self, flat_grad: torch.Tensor):
         if self.world > 1:
@@ -375,6 +409,12 @@ class GANEngine:
         if not self.use_graph:
             return self._run_segments(ins, None)
         key = (tuple(lr_img.shape), tuple(hr_img.shape))
+        ext = (self.gp.ext_version, self.dp.ext_version, getattr(self.V.m, "_weights_version", 0))
+        if ext != getattr(self, "_ext_seen", ext):
+            # load_state_dict / load_checkpoints since the capture: the captured graphs only re-pack what was stale at
+            # capture time (and VGG packs are re-allocated) -> drop them; the next two steps run eagerly, then re-capture
+            self._graphs.clear()
+        self._ext_seen = ext
         st = self._graphs.get(key)
         if st is None:
             st = self._graphs[key] = dict(calls=0, graphs=None)

@@ -113,7 +113,12 @@ class Generator(torch.nn.Module):
 
     # -- checkpoints saved from torch.compile'd modules carry `_orig_mod.` (inference.py:30-33)
     def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
-        return super().load_state_dict(_strip_prefix(state_dict), strict=strict, assign=assign)
+        res = super().load_state_dict(_strip_prefix(state_dict), strict=strict, assign=assign)
+        fp = getattr(self, "_fsr_flat", None)
+        if fp is not None:                 # a training engine aliases these parameters: its weight packs are stale now
+            fp.version += 1
+            fp.ext_version += 1
+        return res
 
     # ------------------------------------------------------------------ weight packing
     def _conv_list(self):
@@ -282,7 +287,12 @@ class Discriminator(torch.nn.Module):
         self._net = None
 
     def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
-        return super().load_state_dict(_strip_prefix(state_dict), strict=strict, assign=assign)
+        res = super().load_state_dict(_strip_prefix(state_dict), strict=strict, assign=assign)
+        fp = getattr(self, "_fsr_flat", None)
+        if fp is not None:                 # a training engine aliases these parameters: its weight packs are stale now
+            fp.version += 1
+            fp.ext_version += 1
+        return res
 
     def _engine(self):
         from .engine import DiscriminatorNet, FlatParams
@@ -329,6 +339,22 @@ class VGG19(torch.nn.Module):
         self.register_buffer("std", torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1))
         self.compute_dtype = compute_dtype or _default_dtype()
         self._net = None
+        self.weights_loaded = False       # True once load_state_dict() ran (the reference loads IMAGENET1K_V1, model.py:8)
+        self._weights_version = 0         # bumped by every load: the engine's packed copies are re-made (engine.VGGNet.pack)
+
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        """Accepts the reference's keys (`vgg.{idx}.weight/bias`, `mean`, `std`; model.py:8-18) and torchvision's own
+        vgg19 checkpoint keys (`features.{idx}.*`, e.g. a locally cached vgg19-dcbb9e9d.pth)."""
+        sd = _strip_prefix(state_dict)
+        if any(k.startswith("features.") for k in sd):
+            keep = {f"features.{i}." for i in self.vgg.keys()}
+            sd = {k.replace("features.", "vgg."): v for k, v in sd.items() if k[:k.rfind(".") + 1] in keep}
+            sd.setdefault("mean", self.mean)
+            sd.setdefault("std", self.std)
+        res = super().load_state_dict(sd, strict=strict, assign=assign)
+        self.weights_loaded = True
+        self._weights_version += 1
+        return res
 
     def _engine(self):
         from .engine import VGGNet

@@ -15,6 +15,7 @@ own shard of the mini-batch, gradients are summed with one NCCL all-reduce per n
 from __future__ import annotations
 
 import os
+import warnings
 from typing import Dict, Optional
 
 import torch
@@ -33,17 +34,37 @@ class Trainer:
         dt = compute_dtype or (torch.float16 if os.environ.get("FSR_TRAIN_DTYPE", "bf16") == "fp16" else torch.bfloat16)
         self.generator = Generator(config=config.generator, compute_dtype=dt).to(dev)
         self.discriminator = Discriminator(config=config.discriminator, compute_dtype=dt).to(dev)
-        self.perceptual_network = VGG19(compute_dtype=dt).to(dev)      # trainer.py:22 (weights: load_state_dict)
+        self.perceptual_network = VGG19(compute_dtype=dt).to(dev)      # trainer.py:22
+        # The reference's VGG19() downloads IMAGENET1K_V1 (model.py:8).  Here the weights come, in this order, from
+        # `vgg_state_dict`, `config.training.vgg_weights` (a file), torchvision's local hub cache - never a silent
+        # random init: training the content loss against random features is not the reference's objective.
+        vgg_state_dict = vgg_state_dict if vgg_state_dict is not None else self._find_vgg_weights(config)
         if vgg_state_dict is not None:
             self.perceptual_network.load_state_dict(vgg_state_dict)
+        else:
+            warnings.warn("fast_srgan_b200.Trainer: no VGG19 weights given (vgg_state_dict=, config.training.vgg_weights, or "
+                          "~/.cache/torch/hub/checkpoints/vgg19-dcbb9e9d.pth) - the perceptual network is RANDOMLY "
+                          "initialised, unlike the reference (model.py:8 loads IMAGENET1K_V1).  Call "
+                          "trainer.perceptual_network.load_state_dict(...) before training for real.", RuntimeWarning, stacklevel=2)
         self.perceptual_network.eval()
         self.device = dev
         self._dtype = dt
         self._engine: Optional[GANEngine] = None
-        self._noise_gen = torch.Generator(device=dev)
-        self._noise_gen.manual_seed(int(getattr(getattr(config, "experiment", None), "seed", 0) or 0))
+        from .distributed import rank_and_world
+        self.rank, self.world = rank_and_world()
+        self._noise_gen = torch.Generator(device=dev)                  # per-rank label noise: every shard draws its own
+        self._noise_gen.manual_seed(int(getattr(getattr(config, "experiment", None), "seed", 0) or 0) + self.rank)
         self.metrics = ValidationMetrics(dev, data_range=1.0)          # trainer.py:46-51
         self.history: list = []                                        # (phase, step, dict) instead of the SummaryWriter
+
+    @staticmethod
+    def _find_vgg_weights(config):
+        cand = [getattr(getattr(config, "training", None), "vgg_weights", None),
+                os.path.join(os.environ.get("TORCH_HOME", os.path.expanduser("~/.cache/torch")), "hub", "checkpoints", "vgg19-dcbb9e9d.pth")]
+        for path in cand:
+            if path and os.path.exists(str(path)):
+                return torch.load(str(path), map_location="cpu")
+        return None
 
     @property
     def engine(self) -> GANEngine:
@@ -92,6 +113,11 @@ class Trainer:
         return n > 0 and step % n == 0
 
     def pretrain(self, train_dataloader, val_dataloader=None):
+        if os.path.exists("runs/pretrain.pt"):                                             # trainer.py:90-94
+            ck = torch.load("runs/pretrain.pt", map_location="cpu")
+            self.generator.load_state_dict(ck["model"])
+            self.engine.gp.load_optimizer_state(ck["optimizer"])
+            return None
         if val_dataloader is not None:
             self.calculate_metrics_over_dataset(val_dataloader, "Pretrain", 0)            # trainer.py:95
         last = None
@@ -99,7 +125,19 @@ class Trainer:
             last = self.pretrain_step(lr_images, hr_images)
             if val_dataloader is not None and self._every("checkpoint_iter", step):
                 self.calculate_metrics_over_dataset(val_dataloader, "Pretrain", step)     # trainer.py:126
+        if self.rank == 0:                                                                 # trainer.py:131-141
+            os.makedirs("runs", exist_ok=True)
+            e, t = self.engine, self.config.training
+            torch.save({"model": self.generator.state_dict(), "optimizer": e.gp.optimizer_state(float(t.generator_lr))},
+                       "runs/pretrain_generator.pt")
+            torch.save({"model": self.discriminator.state_dict(), "optimizer": e.dp.optimizer_state(float(t.discriminator_lr))},
+                       "runs/pretrain_discriminator.pt")
+        self._barrier()
         return last
+
+    def _barrier(self):
+        if self.world > 1:
+            torch.distributed.barrier()
 
     def train(self, train_dataloader, val_dataloader=None):
         if val_dataloader is not None:
@@ -114,22 +152,26 @@ class Trainer:
         return last
 
     def save_checkpoints(self, step: int):
-        """trainer.py:143-156: generator / discriminator state dicts + optimizer states under runs/<name>/."""
+        """trainer.py:143-156: generator / discriminator state dicts + optimizer states (torch.optim.AdamW state_dict
+        format) under runs/<name>/.  Replicas are identical, so rank 0 alone writes; the others wait at a barrier."""
         save_dir = os.path.join("runs", self.config.experiment.name)
-        os.makedirs(save_dir, exist_ok=True)
-        torch.save(self.generator.state_dict(), os.path.join(save_dir, f"generator_epoch_{step}.pt"))
-        torch.save(self.discriminator.state_dict(), os.path.join(save_dir, f"discriminator_epoch_{step}.pt"))
-        e = self.engine
-        for name, fp in (("generator", e.gp), ("discriminator", e.dp)):
-            torch.save(fp.optimizer_state(), os.path.join(save_dir, f"{name}_optim_epoch_{step}.pt"))
+        if self.rank == 0:
+            os.makedirs(save_dir, exist_ok=True)
+            torch.save(self.generator.state_dict(), os.path.join(save_dir, f"generator_epoch_{step}.pt"))
+            torch.save(self.discriminator.state_dict(), os.path.join(save_dir, f"discriminator_epoch_{step}.pt"))
+            e, t = self.engine, self.config.training
+            for name, fp, lr in (("generator", e.gp, t.generator_lr), ("discriminator", e.dp, t.discriminator_lr)):
+                torch.save(fp.optimizer_state(float(lr)), os.path.join(save_dir, f"{name}_optim_epoch_{step}.pt"))
+        self._barrier()
 
     def load_checkpoints(self, step: int, save_dir: Optional[str] = None):
         """Resume from the four files save_checkpoints(step) wrote (the reference only reloads its pretrain checkpoint,
         trainer.py:90-94; here both networks and both AdamW states)."""
         save_dir = save_dir or os.path.join("runs", self.config.experiment.name)
+        e = self.engine                                      # build first: the modules' parameters alias its flat buffers
         self.generator.load_state_dict(torch.load(os.path.join(save_dir, f"generator_epoch_{step}.pt"), map_location="cpu"))
         self.discriminator.load_state_dict(torch.load(os.path.join(save_dir, f"discriminator_epoch_{step}.pt"), map_location="cpu"))
-        e = self.engine
         for name, fp in (("generator", e.gp), ("discriminator", e.dp)):
             fp.load_optimizer_state(torch.load(os.path.join(save_dir, f"{name}_optim_epoch_{step}.pt"), map_location="cpu"))
             fp.version += 1                                  # parameters changed: weight packs are stale
+            fp.ext_version += 1                              # ... and captured CUDA graphs with them
