@@ -94,10 +94,37 @@ def _host_threads():
         return os.cpu_count() or 1
 
 
+class _CpuGenerator:
+    """The reference's CPU implementation of the path: the UNMODIFIED reference model.py from git-ignored baseline/_ref/
+    (placed there by __graft_entry__.build() while /root/reference is mounted; it travels to the GPU box with the
+    snapshot) - kind "reference"; when that copy is absent, the oracle port of model.py:112-117 - kind "port"."""
+
+    def __init__(self):
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import srgan_oracle as O
+        self.sd = O.make_generator_state(NF, NL, seed=1234)
+        ref_dir = os.path.join(ROOT, "baseline", "_ref")
+        self.kind, self.what = "port", "oracle port of model.py:112-117 (oracle/srgan_oracle.py), fp32 oneDNN"
+        self.fn = lambda x: O.generator_forward(self.sd, x)
+        if os.path.exists(os.path.join(ref_dir, "model.py")):
+            try:
+                sys.path.insert(0, ref_dir)
+                import types
+                import model as ref_model                       # the reference's own model.py, unmodified
+                g = ref_model.Generator(types.SimpleNamespace(n_filters=NF, n_layers=NL))
+                g.load_state_dict(self.sd)
+                g.eval()
+                self.fn, self.kind = g, "reference"
+                self.what = "unmodified reference model.py Generator.forward (baseline/_ref), fp32 oneDNN, eval/no_grad"
+            except Exception as exc:                            # torchvision missing etc.: say so, use the port
+                self.what += f" [baseline/_ref import failed: {exc!r}]"
+            finally:
+                sys.path.remove(ref_dir)
+
+
 def _cpu_setup():
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import srgan_oracle as O
-    return O, O.make_generator_state(NF, NL, seed=1234)
+    c = _CpuGenerator()
+    return c, c.sd
 
 
 def _time_cpu(O, sd, rows, iters):
@@ -106,7 +133,7 @@ def _time_cpu(O, sd, rows, iters):
     with torch.no_grad():
         t0 = time.perf_counter()
         for _ in range(iters):
-            O.generator_forward(sd, x)
+            O.fn(x)
     return (time.perf_counter() - t0) / iters
 
 
@@ -133,12 +160,12 @@ def cpu_generator_fps(budget_s=20.0):
     rows = int(max(9, min(H, H * (budget_s / 3.0) / (t_probe * 4.0))))
     _time_cpu(O, sd, rows, 1)
     t = _time_cpu(O, sd, rows, 2)
-    return (rows / H) / t, threads, f"2 x 1 band of {rows}x{W} px of a {H}x{W} frame ({2 * t:.1f} s), fps = (rows/{H})/t"
+    return (rows / H) / t, threads, f"2 x 1 band of {rows}x{W} px of a {H}x{W} frame ({2 * t:.1f} s), fps = (rows/{H})/t; {O.what}", O.kind
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's own CPU implementation of the path, rank 0 only.  The reference is
-    Python (cannot travel to the GPU box), so this times the oracle port of model.py:112-117 (kind "port")."""
+    """--impl reference: the reference's own CPU implementation of the path, rank 0 only: the unmodified reference
+    model.py from baseline/_ref when present (kind "reference"), else the oracle port (kind "port")."""
     if rank != 0:
         return
     O, sd = _cpu_setup()
@@ -150,55 +177,169 @@ def run_reference(args, rank, world):
         _time_cpu(O, sd, rows, 1)
     t = _time_cpu(O, sd, rows, args.steps)
     fps = (rows / H) / t
-    sample = f"{args.steps} steps x 1 band of {rows}x{W} px of a {H}x{W} frame; fps = (rows/{H}) / step time"
+    sample = f"{args.steps} steps x 1 band of {rows}x{W} px of a {H}x{W} frame; fps = (rows/{H}) / step time; {O.what}"
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"generator-only 4x SR {H}x{W}->{4*H}x{4*W}, L={NL} F={NF} (BASELINE configs[1]); CPU sample: {sample}"},
-        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": O.kind, "sample": sample},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
 
 
-def bench_train_step(args, rank, world, dev, dist):
-    """GAN train step (trainer.py:168-196): G + D + VGG19 perceptual, 24x24 LR / 96x96 HR synthetic pairs, bf16 operands.
-    Per-GPU batch 64 at N=1 (BASELINE configs[2]); 32 per GPU for N>1 (configs[3]: global 256 on 8 GPUs), one NCCL
-    all-reduce per network per step.  Device-timed, max over ranks."""
-    import types
-    from fast_srgan_b200.trainer import Trainer
-    ns = types.SimpleNamespace
-    B = 64 if world == 1 else 32
-    cfg = ns(experiment=ns(name="bench", seed=0), generator=ns(n_filters=NF, n_layers=NL), discriminator=ns(n_filters=64, n_layers=7),
-             training=ns(device=str(dev), generator_lr=1e-4, discriminator_lr=1e-4))
-    torch.manual_seed(1234)                       # same random init on every rank (replicas must start identical)
-    tr = Trainer(cfg, compute_dtype=torch.bfloat16)   # G, D: torch default init; VGG19: torchvision's init (no ImageNet download)
-    g = torch.Generator().manual_seed(7 + rank)
-    lr = (torch.rand((B, 3, 24, 24), generator=g) * 2 - 1).to(dev)
-    hr = (torch.rand((B, 3, 96, 96), generator=g) * 2 - 1).to(dev)
-    noise = {k: torch.rand((B, 1, 6, 6), generator=g).to(dev) for k in ("d_real", "d_fake", "g_real")}
-    steps = max(5, min(args.steps, 20))
-    for _ in range(4):                               # 2 eager + graph capture + 1 replay
-        out = tr.train_step(lr, hr, noise=noise)
+K_NAMES = {0: "neck_conv3x3", 1: "conv3x3_c64<64,RAW_STATS> (64->64 res-block convs, incl. fused-input variants)", 2: "instnorm_apply",
+           3: "conv3x3_up (64->256 + PixelShuffle + PReLU)", 4: "conv3x3_head", 5: "conv3x3_c64<64,BIAS_ACT> (64->64 dgrad)",
+           6: "conv3x3_gen_ws (general conv: VGG19 / discriminator forward + data gradient)", 7: "conv3x3_wgrad"}
+
+
+def read_profile(lib):
+    """-> {kernel id: [(ms, flops), ...]} of the launches timed since fsr_profile_enable_mask."""
+    import ctypes
+    cap = 8192
+    ms, ids, fl = (ctypes.c_float * cap)(), (ctypes.c_int * cap)(), (ctypes.c_double * cap)()
+    n = lib.fsr_profile_read_ex(ms, ids, fl, cap)
+    out = {}
+    for i in range(n):
+        out.setdefault(ids[i], []).append((ms[i], fl[i]))
+    return out
+
+
+def load_traffic():
+    """DRAM bytes per launch of the profiled kernels, written by tools/ncu_summary.py from the committed `ncu --set full`
+    capture (profiles/r02/traffic.json); None when no capture of this round's kernels is committed."""
+    for rnd in ("r02",):
+        path = os.path.join(ROOT, "profiles", rnd, "traffic.json")
+        if os.path.exists(path):
+            try:
+                d = json.load(open(path))
+                d["_source"] = f"profiles/{rnd}/traffic.json"
+                return d
+            except ValueError:
+                pass
+    return {}
+
+
+def _time_steps(fn, n, dev, dist):
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(steps):
-        out = tr.train_step(lr, hr, noise=noise)
+    for _ in range(n):
+        fn()
     e1.record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / steps
+    ms = e0.elapsed_time(e1) / n
     if dist is not None:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = t.item()
-    return {"metric": "GAN train-step ms", "ms_per_step": ms, "per_gpu_batch": B, "global_batch": B * world, "steps": steps,
-            "samples_per_s": B * world / (ms / 1e3), "dtype": "bf16 operands, fp32 accumulate",
-            "needed_tflops_per_gpu": 2636e9 * B / 64.0 / (ms * 1e-3) / 1e12,
-            "content_loss": float(out["content_loss"])}
+    return ms
+
+
+def bench_train_step(args, rank, world, dev, dist, lib):
+    """GAN train step (trainer.py:168-196): G + D + VGG19 perceptual, 24x24 LR / 96x96 HR synthetic pairs, bf16 operands,
+    random-init weights (VGG19 too: no ImageNet download).  Measured at 32 samples per GPU for EVERY N (BASELINE
+    configs[3]: global batch 256 on 8 GPUs; the same shape at N=1 is the weak-scaling anchor) and, at N=1, also at batch
+    64 (configs[2]).  N>1: gradients are summed with libfsr_b200's NCCL all-reduce inside the step's CUDA graph; the
+    same run also times the step WITHOUT the exchange (world forced to 1 on every rank) -> efficiency_vs_n1, times the
+    two all-reduces alone, and checks that all replicas hold identical parameters after the timed steps."""
+    import types
+    import warnings
+    from fast_srgan_b200.trainer import Trainer
+    ns = types.SimpleNamespace
+    steps = max(5, min(args.steps, 20))
+    FLOPS_B64 = 2636e9                                 # SURVEY.md 8(a10)/(d): needed conv FLOPs of one step at batch 64
+
+    def make(B, standalone):
+        cfg = ns(experiment=ns(name="bench", seed=0), generator=ns(n_filters=NF, n_layers=NL), discriminator=ns(n_filters=64, n_layers=7),
+                 training=ns(device=str(dev), generator_lr=1e-4, discriminator_lr=1e-4))
+        torch.manual_seed(1234)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")               # random-init VGG19 is stated in `data`
+            tr = Trainer(cfg, compute_dtype=torch.bfloat16)
+        e = tr.engine
+        if standalone:
+            e.world = 1                                   # no exchange: this GPU alone on its 32 samples
+        g = torch.Generator().manual_seed(7 + rank)
+        lr = (torch.rand((B, 3, 24, 24), generator=g) * 2 - 1).to(dev)
+        hr = (torch.rand((B, 3, 96, 96), generator=g) * 2 - 1).to(dev)
+        noise = {k: torch.rand((B, 1, 6, 6), generator=g).to(dev) for k in ("d_real", "d_fake", "g_real")}
+        return tr, (lambda: tr.train_step(lr, hr, noise=noise))
+
+    def run(B, standalone):
+        tr, step = make(B, standalone)
+        for _ in range(4):                                # 2 eager + graph capture + 1 replay
+            out = step()
+        ms = _time_steps(step, steps, dev, None if standalone else dist)
+        if standalone and dist is not None:               # anchor: slowest rank, like the sharded run
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return tr, step, ms, float(out["content_loss"])
+
+    res = {"metric": "GAN train-step ms", "dtype": "bf16 operands, fp32 accumulate", "steps": steps,
+           "data": "synthetic 24x24 LR / 96x96 HR pairs, random-init G / D / VGG19"}
+    tr, step, ms32, closs = run(32, standalone=False)
+    res["b32_per_gpu"] = {"ms_per_step": ms32, "per_gpu_batch": 32, "global_batch": 32 * world, "samples_per_s": 32 * world / (ms32 / 1e3),
+                          "needed_tflops_per_gpu": FLOPS_B64 * 0.5 / (ms32 * 1e-3) / 1e12, "content_loss": closs}
+    if world > 1:
+        e = tr.engine
+        # every replica must hold the same parameters after the timed steps (the only multi-GPU correctness number that
+        # reaches the SCALE record): max over ranks - min over ranks, element-wise, summed over both networks
+        diff = 0.0
+        for fp in (e.gp, e.dp):
+            hi, lo = fp.flat.clone(), fp.flat.clone()
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            diff = max(diff, (hi - lo).abs().max().item())
+        res["replica_max_diff"] = diff
+        res["exchange"] = "fsr_nccl_allreduce (libfsr_b200, captured in the step graph)" if e.comm.native else "torch.distributed.all_reduce"
+        res["overlap"] = bool(e.overlap)
+        # the two exchanges alone (flat fp32 gradient buffers: D 18.7 MB, G 3.7 MB), device-timed, max over ranks
+        ar = {}
+        for name, fp in (("d_grads", e.dp), ("g_grads", e.gp)):
+            buf = torch.zeros_like(fp.grad)
+            for _ in range(3):
+                e.comm.allreduce(buf)
+            ar[name + "_us"] = _time_steps(lambda: e.comm.allreduce(buf), 20, dev, dist) * 1e3
+            ar[name + "_bytes"] = buf.numel() * 4
+        res["allreduce"] = ar
+        del tr, step
+        _, _, ms_anchor, _ = run(32, standalone=True)
+        res["n1_anchor_b32_ms"] = ms_anchor
+        res["efficiency_vs_n1"] = ms_anchor / ms32
+    else:
+        # in-situ roofline of the training kernels: ONE eager step (launches are event-bracketed; a graph replay is not)
+        e = tr.engine
+        e.use_graph = False
+        lib.fsr_profile_enable_mask((1 << 6) | (1 << 7) | (1 << 1) | (1 << 5) | (1 << 3))
+        step()
+        torch.cuda.synchronize()
+        prof = read_profile(lib)
+        lib.fsr_profile_enable_mask(0)
+        tf_peak, _, peak_src = load_peaks()
+        kern = {}
+        for kid, recs in prof.items():
+            t = sum(r[0] for r in recs) * 1e-3
+            f = sum(r[1] for r in recs)
+            kern[K_NAMES.get(kid, str(kid))] = {"launches": len(recs), "ms": t * 1e3, "achieved_tflops": f / t / 1e12 if t > 0 else None,
+                                              "frac_of_peak": f / t / 1e12 / tf_peak if t > 0 else None}
+        res["kernels_b32_eager_step"] = kern
+        if 6 in prof:
+            t = sum(r[0] for r in prof[6]) * 1e-3
+            f = sum(r[1] for r in prof[6])
+            res["roofline"] = {"bound": "tensor", "kernel": K_NAMES[6], "achieved": f / t / 1e12, "peak": tf_peak, "unit": "TFLOP/s",
+                               "frac": f / t / 1e12 / tf_peak, "launches_timed": len(prof[6]), "flops": f, "peak_source": peak_src,
+                               "traffic": None, "how": "sum of algorithmic FLOPs / sum of per-launch CUDA-event times over one eager b32 step"}
+        del tr, step
+        _, _, ms64, closs64 = run(64, standalone=False)
+        res["b64"] = {"ms_per_step": ms64, "per_gpu_batch": 64, "global_batch": 64, "samples_per_s": 64 / (ms64 / 1e3),
+                      "needed_tflops_per_gpu": FLOPS_B64 / (ms64 * 1e-3) / 1e12, "content_loss": closs64}
+    res["ms_per_step"] = res["b64"]["ms_per_step"] if world == 1 else ms32
+    return res
 
 
 _REAL_STDOUT = None
@@ -292,7 +433,7 @@ def main():
         sampler = ClockSampler(local_rank)
         if rank == 0:
             sampler.start()
-        lib.fsr_profile_enable(L.K_CONV_UP)
+        lib.fsr_profile_enable_mask((1 << L.K_CONV_UP) | (1 << L.K_CONV_RES))
         launches0 = lib.fsr_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -303,13 +444,12 @@ def main():
         ms_total = max_over_ranks(e0.elapsed_time(e1))
         launches = lib.fsr_launch_count() - launches0
         clocks = sampler.stop() if rank == 0 else None
-        import ctypes
-        buf = (ctypes.c_float * 4096)()
-        nrec = lib.fsr_profile_read(buf, 4096)
-        lib.fsr_profile_enable(L.K_NONE)
-    up_ms = sorted(buf[i] for i in range(nrec))
-    # two upsampling convs per step: the larger half of the sorted times are the 360x640 launches
-    up1 = up_ms[len(up_ms) // 2:] if up_ms else []
+        prof = read_profile(lib)
+        lib.fsr_profile_enable_mask(0)
+    up1_flops = 2.0 * BATCH * (2 * H) * (2 * W) * 64 * 256 * 9
+    # two upsampling convs per step: the 360x640 launches are the ones tagged with up1's FLOPs
+    up1 = [ms for ms, fl in prof.get(L.K_CONV_UP, []) if abs(fl - up1_flops) < 1e-3 * up1_flops]
+    res_ms = [ms for ms, fl in prof.get(L.K_CONV_RES, [])]
     ms_step = ms_total / args.steps
     fps = world * BATCH * args.steps / (ms_total / 1e3)
 
@@ -357,7 +497,7 @@ def main():
     train_aux = None
     if not args.no_train:
         try:
-            train_aux = bench_train_step(args, rank, world, dev, dist)
+            train_aux = bench_train_step(args, rank, world, dev, dist, lib)
         except Exception as exc:                     # never let the auxiliary number break the headline line
             train_aux = {"error": repr(exc)[:200]}
 
@@ -367,16 +507,28 @@ def main():
         return
 
     tf_peak, hbm_peak, peak_src = load_peaks()
-    up1_flops = 2.0 * BATCH * (2 * H) * (2 * W) * 64 * 256 * 9
-    roof = None
+    traffic = load_traffic()
+    roof = roof_res = None
     if up1:
         avg = sum(up1) / len(up1)
         ach = up1_flops / (avg * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "conv3x3_c64_kernel<128,EPI_PS_PRELU> (upsampling.1.conv, 360x640, 64->256)",
+        roof = {"bound": "tensor", "kernel": "conv3x3_up_2cta_kernel (upsampling.1.conv, 360x640, 64->256, tcgen05 cta_group::2)"
+                if os.environ.get("FSR_UP_2CTA", "1") != "0" else "conv3x3_c64_kernel<128,EPI_PS_PRELU> (upsampling.1.conv, 360x640, 64->256)",
                 "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
-                "traffic": 4.779e9,   # dram__bytes_read+write per launch, ncu --set full (profiles/r01/ncu_full_upsample_convs.md); algorithmic 4.72e9
-                "traffic_source": "profiles/r01/ncu_full_upsample_convs.md",
+                "traffic": traffic.get("conv_up1_bytes_per_launch"), "traffic_source": traffic.get("_source"),
+                "algorithmic_bytes": BATCH * (2 * H) * (2 * W) * 64 * 2 * 5 + 9 * 256 * 64 * 2,
                 "avg_launch_ms": avg, "launches_timed": len(up1), "flops_per_launch": up1_flops, "peak_source": peak_src}
+    if res_ms:
+        # the north_star's 70 % kernel: the 64->64 residual-block convs (17 per forward: plain, fused bn1+relu1 input,
+        # fused bn2+skip input), all launches of the timed region
+        res_flops = 2.0 * BATCH * H * W * 64 * 64 * 9
+        avg = sum(res_ms) / len(res_ms)
+        ach = res_flops / (avg * 1e-3) / 1e12
+        roof_res = {"bound": "tensor", "kernel": "conv3x3_c64_kernel<64,RAW_STATS,XF=0|1|2> (17 residual-chain convs per forward, 180x320, 64->64)",
+                    "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
+                    "traffic": traffic.get("conv_res_bytes_per_launch"), "traffic_source": traffic.get("_source"),
+                    "avg_launch_ms": avg, "launches_timed": len(res_ms), "flops_per_launch": res_flops, "peak_source": peak_src,
+                    "note": "the fused variants also do the InstanceNorm(+PReLU | +skip) pass of their input inside this time"}
     total_flops = gen_flops_per_frame(H, W) * BATCH
     line = {
         "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -386,19 +538,19 @@ def main():
                    "parallelism": f"{world} independent replicas (frames shard, no collective)",
                    "l2": "activations streamed per step (>5 GB) exceed the 126 MB L2; no explicit flush",
                    "l2_group": args.l2_group, "overlap_streams": args.streams,
-                   "switches": {k: os.environ.get(k, "default") for k in ("FSR_FUSE_IN", "FSR_GEN_WS", "FSR_SMALL_MMA", "FSR_WS", "FSR_HALO1")}},
+                   "switches": {k: os.environ.get(k, "default") for k in ("FSR_FUSE_IN", "FSR_FUSE_RES", "FSR_UP_2CTA", "FSR_GEN_WS", "FSR_SMALL_MMA", "FSR_WS", "FSR_HALO1")}},
         "whole_model_tflops": total_flops / (ms_step * 1e-3) / 1e12 * 1.0,
         "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": e2e_fps, "unit": UNIT, "h2d_bytes_per_step": BATCH * H * W * 3,
                 "d2h_bytes_per_step": BATCH * 16 * H * W * 3, "api": "Generator.super_resolve_u8 (uint8 NHWC host frames in/out)",
                 "ms_per_step": e2e_ms / args.steps},
         "roofline": roof,
+        "roofline_resblock_conv": roof_res,
         "train_step": train_aux,
     }
     if not args.no_cpu_baseline and world == 1:
-        cfps, cthreads, csample = cpu_generator_fps()
-        line["cpu_baseline"] = {"value": cfps, "unit": UNIT, "cores": cthreads, "kind": "port",
-                                "sample": csample + "; oracle port of model.py:112-117, fp32 oneDNN"}
+        cfps, cthreads, csample, ckind = cpu_generator_fps()
+        line["cpu_baseline"] = {"value": cfps, "unit": UNIT, "cores": cthreads, "kind": ckind, "sample": csample}
     if dist is not None:
         dist.destroy_process_group()
     emit(line)

@@ -63,6 +63,9 @@ _SIGS = {
     "fsr_nhwc_to_nchw_f32": (_i, [_vp, _fp, _i, _i, _i, _i, _vp]),
     "fsr_profile_enable": (_i, [_i]),
     "fsr_profile_read": (_i, [_vp, _i]),
+    "fsr_profile_enable_mask": (_i, [C.c_uint]),
+    "fsr_profile_read_ids": (_i, [_vp, _vp, _i]),
+    "fsr_profile_read_ex": (_i, [_vp, _vp, _vp, _i]),
     "fsr_launch_count": (C.c_ulonglong, []),
     "fsr_set_halo_mode": (_i, [_i]),
     "fsr_set_ws_mode": (_i, [_i]),
@@ -70,9 +73,19 @@ _SIGS = {
     "fsr_set_gen_ws": (_i, [_i]),
     "fsr_set_fuse_in": (_i, [_i]),
     "fsr_conv3x3_c64_in": (_i, [_vp, _vp, _fp, _f, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "fsr_conv3x3_c64_res_in": (_i, [_vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "fsr_set_fuse_res": (_i, [_i]),
+    "fsr_set_up_2cta": (_i, [_i]),
     "fsr_psnr_ssim": (_i, [_fp, _fp, _i, _i, _i, _i, _f, _f, _f, _vp, _vp, _vp, _vp]),
     "fsr_crop_resize_aa": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _fp, _fp, _vp]),
     "fsr_set_overlap_streams": (_i, [_i]),
+    "fsr_nccl_available": (_i, []),
+    "fsr_nccl_version": (_i, []),
+    "fsr_nccl_unique_id": (_i, [_vp]),
+    "fsr_nccl_init": (_i, [_vp, _i, _i, C.POINTER(_vp)]),
+    "fsr_nccl_allreduce": (_i, [_vp, _fp, _sz, _vp]),
+    "fsr_nccl_broadcast": (_i, [_vp, _fp, _sz, _i, _vp]),
+    "fsr_nccl_destroy": (_i, [_vp]),
     "fsr_generator_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "fsr_generator_forward": (_i, [C.POINTER(FsrGeneratorParams), _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _i, _vp]),
 }

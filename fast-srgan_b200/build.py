@@ -9,11 +9,10 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfsr_b200.so")
-LIB_EXPERIMENTAL = os.path.join(HERE, "libfsr_b200_experimental.so")   # kernels not yet run on hardware: never loaded by the product
 SOURCES = ["capi.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-         "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-shared", "-cudart", "static"]
+         "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-shared", "-cudart", "static", "-ldl"]
 
 
 def _stale(lib=LIB):
@@ -40,21 +39,6 @@ def build(force=False, verbose=False):
     return LIB
 
 
-def build_experimental(force=False, verbose=False):
-    """csrc/experimental.cu -> libfsr_b200_experimental.so (compile check of kernels that have not run on hardware)."""
-    if not force and not _stale(LIB_EXPERIMENTAL):
-        return LIB_EXPERIMENTAL
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + [os.path.join(CSRC, "experimental.cu"), "-o", LIB_EXPERIMENTAL]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or r.returncode != 0:
-        sys.stderr.write(r.stdout + r.stderr)
-    if r.returncode != 0:
-        raise RuntimeError("nvcc failed building libfsr_b200_experimental.so")
-    return LIB_EXPERIMENTAL
-
-
 if __name__ == "__main__":
     build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
     print(LIB)
-    if "--experimental" in sys.argv:
-        print(build_experimental(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

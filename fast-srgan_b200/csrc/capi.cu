@@ -1,6 +1,7 @@
 // capi.cu - extern "C" entry points of libfsr_b200.so (see include/fsr_b200.h) and host launchers.
 #include "../../include/fsr_b200.h"
 #include "conv3x3_tc.cuh"
+#include "conv3x3_up_2cta.cuh"
 #include "conv3x3_gen.cuh"
 #include "conv3x3_gen_ws.cuh"
 #include "conv3x3_head.cuh"
@@ -9,10 +10,12 @@
 #include "elementwise.cuh"
 #include "small_mma.cuh"
 #include "aux_kernels.cuh"
+#include "nccl_comm.cuh"
 
 #include <cudaTypedefs.h>
 #include <atomic>
 #include <cstdlib>
+#include <cstring>
 #include <cmath>
 #include <mutex>
 #include <vector>
@@ -22,21 +25,23 @@ using namespace fsr;
 namespace {
 
 std::atomic<unsigned long long> g_launches{0};
-int g_prof_kernel = FSR_K_NONE;
-std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
+unsigned g_prof_mask = 0;            // bit k set: launches of kernel id k are bracketed with an event pair
+struct ProfRec { int id; cudaEvent_t a, b; double flops; };
+std::vector<ProfRec> g_prof_events;
 
 // Brackets one launch with an event pair when profiling of `kernel_id` is enabled.
 struct LaunchScope {
   cudaStream_t st;
   cudaEvent_t stop = nullptr;
-  LaunchScope(int kernel_id, cudaStream_t s) : st(s) {
+  // flops: ALGORITHMIC work of the launch (2 * N * Ho * Wo * Cout * Cin * taps), reported with its time
+  LaunchScope(int kernel_id, cudaStream_t s, double flops = 0.0) : st(s) {
     g_launches.fetch_add(1, std::memory_order_relaxed);
-    if (kernel_id == g_prof_kernel && g_prof_events.size() < FSR_PROFILE_MAX) {
+    if (kernel_id >= 0 && kernel_id < 32 && ((g_prof_mask >> kernel_id) & 1u) && g_prof_events.size() < FSR_PROFILE_MAX) {
       cudaEvent_t a, b;
       if (cudaEventCreate(&a) == cudaSuccess && cudaEventCreate(&b) == cudaSuccess) {
         cudaEventRecord(a, st);
         stop = b;
-        g_prof_events.emplace_back(a, b);
+        g_prof_events.push_back(ProfRec{kernel_id, a, b, flops});
       }
     }
   }
@@ -148,6 +153,24 @@ int fuse_in_mode() {
   return g_fuse_in;
 }
 
+int g_fuse_res = -1;   // Generator.forward: 1 = bn2 + skip of block l is applied inside conv1 of block l+1 (XF == 2)
+int fuse_res_mode() {
+  if (g_fuse_res < 0) {
+    const char* e = getenv("FSR_FUSE_RES");
+    g_fuse_res = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_fuse_res;
+}
+
+int g_up_2cta = -1;    // 64 -> 256 upsampling conv: 1 = CTA-pair kernel (tcgen05 cta_group::2, conv3x3_up_2cta.cuh)
+int up_2cta_mode() {
+  if (g_up_2cta < 0) {
+    const char* e = getenv("FSR_UP_2CTA");
+    g_up_2cta = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_up_2cta;
+}
+
 int g_small_mma = -1;   // 3-channel-sided convs (neck / wgrad_c3): 1 = mma.sync tensor-core kernels (small_mma.cuh), 0 = CUDA cores
 int small_mma_mode() {
   if (g_small_mma < 0) {
@@ -157,7 +180,7 @@ int small_mma_mode() {
   return g_small_mma;
 }
 
-template <int NS, int EPI, typename T, bool HALO1, bool XF = false>
+template <int NS, int EPI, typename T, bool HALO1, int XF = 0>
 int launch_conv(const void* x, const void* w_packed, int w_rows, ConvParams p, int dtype, cudaStream_t st) {
   using Cfg = ConvCfg<NS, HALO1>;
   using Geo = ConvGeo<HALO1>;
@@ -188,7 +211,7 @@ int launch_conv(const void* x, const void* w_packed, int w_rows, ConvParams p, i
   constexpr int kid = EPI == EPI_RAW_STATS ? FSR_K_CONV_RES : EPI == EPI_PS_PRELU ? FSR_K_CONV_UP
                     : EPI == EPI_HEAD_TANH ? FSR_K_CONV_HEAD : FSR_K_CONV_BIAS_ACT;
   {
-    LaunchScope scope(kid, st);
+    LaunchScope scope(kid, st, 2.0 * p.N * p.H * p.W * (double)(EPI == EPI_HEAD_TANH ? 3 : p.cout_total) * 64 * 9);
     kern<<<grid, XF ? Cfg::kThreadsXf : Cfg::kThreads, Cfg::kSmemBytes, st>>>(tmx, tmw, tmo, p);
   }
   return cuda_rc(cudaGetLastError());
@@ -198,6 +221,35 @@ template <int NS, int EPI, typename T>
 int launch_conv_mode(const void* x, const void* w_packed, int w_rows, const ConvParams& p, int dtype, cudaStream_t st) {
   if (halo_mode()) return launch_conv<NS, EPI, T, true>(x, w_packed, w_rows, p, dtype, st);
   return launch_conv<NS, EPI, T, false>(x, w_packed, w_rows, p, dtype, st);
+}
+
+// 64 -> 256 upsampling conv as a CTA-pair kernel (conv3x3_up_2cta.cuh): M = 256 (one 128-pixel tile per CTA), N = 256
+template <typename T>
+int launch_up_2cta(const void* x, const void* w_packed, ConvParams p, int dtype, cudaStream_t st) {
+  using Cfg = Up2Cfg;
+  using Geo = Cfg::Geo;
+  auto kern = conv3x3_up_2cta_kernel<T>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    FSR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_done = true;
+  }
+  p.tiles_x = (p.W + Geo::TW - 1) / Geo::TW;
+  p.tiles_y = (p.H + Geo::TH - 1) / Geo::TH;
+  p.num_tiles = p.N * p.tiles_x * p.tiles_y;
+  CUtensorMap tmx, tmw;
+  int rc = make_act_map(&tmx, x, p.N, p.H, p.W, 64, Geo::kBoxW, Geo::kBoxH, dtype);
+  if (rc) return rc;
+  if ((rc = make_w_map(&tmw, w_packed, 9 * Cfg::kN, Cfg::kN / 2, dtype))) return rc;
+  const int pairs = (p.num_tiles + 1) / 2;
+  int clusters = num_sms() / 2;
+  if (clusters > pairs) clusters = pairs;
+  if (clusters < 1) clusters = 1;
+  {
+    LaunchScope scope(FSR_K_CONV_UP, st, 2.0 * p.N * p.H * p.W * 256.0 * 64 * 9);
+    kern<<<2 * clusters, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tmx, tmw, p);   // __cluster_dims__(2,1,1)
+  }
+  return cuda_rc(cudaGetLastError());
 }
 
 // 3-output-channel conv as 1x1 GEMM + shift-add epilogue (conv3x3_head.cuh)
@@ -219,7 +271,7 @@ int launch_head(const void* x, const void* w_packed, ConvParams p, int dtype, cu
   int grid = num_sms();
   if (grid > p.num_tiles) grid = p.num_tiles;
   {
-    LaunchScope scope(FSR_K_CONV_HEAD, st);
+    LaunchScope scope(FSR_K_CONV_HEAD, st, 2.0 * p.N * p.H * p.W * 3.0 * cin * 9);
     kern<<<grid, HeadCfg::kThreads, HeadCfg::kSmemBytes, st>>>(tmx, reinterpret_cast<const T*>(w_packed), p, cin);
   }
   return cuda_rc(cudaGetLastError());
@@ -247,6 +299,7 @@ int conv_dispatch(const void* x, const void* w_packed, void* out, const float* b
     }
     case FSR_EPI_PS_PRELU: {
       if (cout != 256 || !alpha) return FSR_ERR_BAD_ARG;
+      if (up_2cta_mode() && halo_mode()) { p.cout_total = 256; p.num_slices = 1; return launch_up_2cta<T>(x, w_packed, p, dtype, st); }
       p.cout_total = 256; p.num_slices = 2;
       return launch_conv_mode<128, EPI_PS_PRELU, T>(x, w_packed, 9 * 256, p, dtype, st);
     }
@@ -278,6 +331,9 @@ int launch_gen(const CUtensorMap* maps, const CUtensorMap& tmw, GenParams& p, cu
   if (ctas_per_slice < 1) ctas_per_slice = 1;
   if (ctas_per_slice > p.num_tiles) ctas_per_slice = p.num_tiles;
   const int grid = ctas_per_slice * p.num_slices;
+  int ntaps = 0;
+  for (int k = 0; k < p.nkinds; ++k) ntaps += p.kinds[k].ntaps;
+  const double flops = 2.0 * p.N * p.Ho * p.Wo * (double)p.cout_total * p.cin * ntaps;
   if (gen_ws_mode()) {
     using WCfg = GenWsCfg<MAXTAPS>;
     auto wkern = conv3x3_gen_ws_kernel<EPI, T, MAXTAPS>;
@@ -286,7 +342,7 @@ int launch_gen(const CUtensorMap* maps, const CUtensorMap& tmw, GenParams& p, cu
       FSR_CUDA(cudaFuncSetAttribute(wkern, cudaFuncAttributeMaxDynamicSharedMemorySize, WCfg::kSmemBytes));
       wattr_done = true;
     }
-    LaunchScope scope(FSR_K_CONV_GEN, st);
+    LaunchScope scope(FSR_K_CONV_GEN, st, flops);
     wkern<<<grid, WCfg::kThreads, WCfg::kSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], tmw, p);
     return cuda_rc(cudaGetLastError());
   }
@@ -297,7 +353,7 @@ int launch_gen(const CUtensorMap* maps, const CUtensorMap& tmw, GenParams& p, cu
     attr_done = true;
   }
   {
-    LaunchScope scope(FSR_K_CONV_GEN, st);
+    LaunchScope scope(FSR_K_CONV_GEN, st, flops);
     kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], tmw, p);
   }
   return cuda_rc(cudaGetLastError());
@@ -440,7 +496,7 @@ int wgrad_dispatch(const void* x, const void* dy, float* dw, int N, int H, int W
   if (cpp < 1) cpp = 1;
   if (cpp > p.num_tiles) cpp = p.num_tiles;
   {
-    LaunchScope scope(FSR_K_CONV_WGRAD, st);
+    LaunchScope scope(FSR_K_CONV_WGRAD, st, 2.0 * N * Ho * Wo * (double)cin * cout * 9);
     kern<<<npairs * cpp, WgradCfg::kThreads, WgradCfg::kSmemBytes, st>>>(mx[0], mx[1], mx[2], mx[3], mdy, p);
   }
   return cuda_rc(cudaGetLastError());
@@ -466,6 +522,8 @@ const char* fsr_error_string(int code) {
     case FSR_ERR_TENSORMAP: return "cuTensorMapEncodeTiled failed";
     case FSR_ERR_WORKSPACE: return "workspace too small";
     case FSR_ERR_NO_DRIVER: return "CUDA driver entry point cuTensorMapEncodeTiled unavailable";
+    case FSR_ERR_NO_NCCL: return "libnccl.so.2 could not be bound (dlopen)";
+    case FSR_ERR_NCCL: return "NCCL call failed";
     default:
       if (code <= FSR_ERR_CUDA_BASE) return cudaGetErrorString((cudaError_t)(FSR_ERR_CUDA_BASE - code));
       return "unknown error";
@@ -507,8 +565,34 @@ int fsr_conv3x3_c64_in(const void* x_raw, const int64_t* in_stats, const float* 
   p.N = N; p.H = H; p.W = W; p.out = out; p.stats = reinterpret_cast<long long*>(stats);
   p.cout_total = 64; p.num_slices = 1;
   p.in_stats = reinterpret_cast<const long long*>(in_stats); p.in_alpha = in_alpha; p.in_eps = in_eps;
-  if (dtype == FSR_BF16) return launch_conv<64, EPI_RAW_STATS, __nv_bfloat16, true, true>(x_raw, w_packed, 9 * 64, p, dtype, st);
-  return launch_conv<64, EPI_RAW_STATS, __half, true, true>(x_raw, w_packed, 9 * 64, p, dtype, st);
+  if (dtype == FSR_BF16) return launch_conv<64, EPI_RAW_STATS, __nv_bfloat16, true, 1>(x_raw, w_packed, 9 * 64, p, dtype, st);
+  return launch_conv<64, EPI_RAW_STATS, __half, true, 1>(x_raw, w_packed, 9 * 64, p, dtype, st);
+}
+
+int fsr_conv3x3_c64_res_in(const void* x_raw, const int64_t* in_stats, float in_eps, const void* res, void* x_out,
+                           const void* w_packed, void* out, int64_t* stats, int N, int H, int W, int dtype, void* stream) {
+  if (!x_raw || !in_stats || !res || !x_out || !w_packed || !out || !stats) return FSR_ERR_BAD_ARG;
+  if (x_out == res || x_out == x_raw || out == x_raw || out == x_out || out == res) return FSR_ERR_BAD_ARG;
+  if (N <= 0 || H <= 0 || W <= 0) return FSR_ERR_BAD_SHAPE;
+  if (!halo_mode()) return FSR_ERR_BAD_ARG;      // exists for the single-halo-tile staging only
+  cudaStream_t st = (cudaStream_t)stream;
+  ConvParams p{};
+  p.N = N; p.H = H; p.W = W; p.out = out; p.stats = reinterpret_cast<long long*>(stats);
+  p.cout_total = 64; p.num_slices = 1;
+  p.in_stats = reinterpret_cast<const long long*>(in_stats); p.in_eps = in_eps;
+  p.in_res = res; p.x_out = x_out;
+  if (dtype == FSR_BF16) return launch_conv<64, EPI_RAW_STATS, __nv_bfloat16, true, 2>(x_raw, w_packed, 9 * 64, p, dtype, st);
+  return launch_conv<64, EPI_RAW_STATS, __half, true, 2>(x_raw, w_packed, 9 * 64, p, dtype, st);
+}
+
+int fsr_set_fuse_res(int on) {
+  g_fuse_res = on < 0 ? -1 : (on ? 1 : 0);   // -1: back to the environment default (FSR_FUSE_RES)
+  return FSR_OK;
+}
+
+int fsr_set_up_2cta(int on) {
+  g_up_2cta = on < 0 ? -1 : (on ? 1 : 0);    // -1: back to the environment default (FSR_UP_2CTA)
+  return FSR_OK;
 }
 
 int fsr_set_fuse_in(int on) {
@@ -627,26 +711,40 @@ int fsr_nhwc_to_nchw_f32(const void* in, float* out, int N, int C, int HW, int d
   return cuda_rc(cudaGetLastError());
 }
 
-int fsr_profile_enable(int kernel_id) {
-  for (auto& e : g_prof_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+static void prof_clear() {
+  for (auto& e : g_prof_events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
   g_prof_events.clear();
-  g_prof_kernel = kernel_id;
+}
+
+int fsr_profile_enable(int kernel_id) {
+  prof_clear();
+  g_prof_mask = (kernel_id >= 0 && kernel_id < 32) ? (1u << kernel_id) : 0u;
   return FSR_OK;
 }
 
-int fsr_profile_read(float* ms_out, int capacity) {
+int fsr_profile_enable_mask(unsigned mask) {
+  prof_clear();
+  g_prof_mask = mask;
+  return FSR_OK;
+}
+
+int fsr_profile_read_ex(float* ms_out, int* ids_out, double* flops_out, int capacity) {
   int n = 0;
   for (auto& e : g_prof_events) {
     float ms = 0.f;
-    if (cudaEventSynchronize(e.second) == cudaSuccess && cudaEventElapsedTime(&ms, e.first, e.second) == cudaSuccess &&
-        ms_out && n < capacity)
+    if (cudaEventSynchronize(e.b) == cudaSuccess && cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess && ms_out && n < capacity) {
+      if (ids_out) ids_out[n] = e.id;
+      if (flops_out) flops_out[n] = e.flops;
       ms_out[n++] = ms;
-    cudaEventDestroy(e.first);
-    cudaEventDestroy(e.second);
+    }
   }
-  g_prof_events.clear();
+  prof_clear();
   return n;
 }
+
+int fsr_profile_read_ids(float* ms_out, int* ids_out, int capacity) { return fsr_profile_read_ex(ms_out, ids_out, nullptr, capacity); }
+
+int fsr_profile_read(float* ms_out, int capacity) { return fsr_profile_read_ids(ms_out, nullptr, capacity); }
 
 unsigned long long fsr_launch_count(void) { return g_launches.load(); }
 
@@ -676,7 +774,7 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 size_t fsr_generator_workspace_bytes(int N, int H, int W, int n_filters, int n_layers) {
   const size_t P = align_up((size_t)N * H * W * n_filters * 2, 1024);
   const size_t stats = align_up((size_t)(2 * n_layers + 1) * N * n_filters * 2 * sizeof(int64_t), 1024);
-  return 4 * P + 4 * P + 16 * P + stats + 4096;
+  return 5 * P + 4 * P + 16 * P + stats + 4096;
 }
 
 // Sub-batches of the forward run on internal side streams so that the HBM-bound kernels of one sub-batch
@@ -700,37 +798,67 @@ int fsr_set_overlap_streams(int parts) {
   return FSR_OK;
 }
 
-static int generator_chain(const FsrGeneratorParams* prm, const uint8_t* xin, uint8_t* yout, uint8_t* res, uint8_t* xb,
-                           uint8_t* raw, uint8_t* yb, uint8_t* u0, uint8_t* u1, int64_t* stats, size_t stats_per_conv,
+static int generator_chain(const FsrGeneratorParams* prm, const uint8_t* xin, uint8_t* yout, uint8_t* res, uint8_t* xa,
+                           uint8_t* xb2, uint8_t* raw, uint8_t* yb, uint8_t* u0, uint8_t* u1, int64_t* stats, size_t stats_per_conv,
                            int nb, int H, int W, int in_u8, int out_u8, cudaStream_t st) {
   const int F = 64, L = prm->n_layers, dt = prm->dtype;
   int rc;
   // neck (model.py:75-78)
   if ((rc = fsr_neck_conv3x3(xin, prm->neck_w, prm->neck_b, prm->neck_alpha, res, nb, H, W, F, FSR_ACT_PRELU, 0.f, in_u8, 0, dt, st)))
     return rc;
-  const uint8_t* cur = res;
-  for (int l = 0; l < L; ++l) {   // ResidualBlock.forward (model.py:67-69)
-    int64_t* s1 = stats + (size_t)(2 * l) * stats_per_conv;
-    int64_t* s2 = stats + (size_t)(2 * l + 1) * stats_per_conv;
-    if ((rc = fsr_conv3x3_c64(cur, prm->stem_w1[l], raw, nullptr, s1, nullptr, nb, H, W, F, FSR_EPI_RAW_STATS, 0, 0.f, 0, dt, st))) return rc;
-    if (fuse_in_mode() && halo_mode()) {
-      // bn1 + relu1 (model.py:55-56) applied to the halo tile inside conv2's load path: one HBM round trip less per block
+  const bool fuse_in = fuse_in_mode() && halo_mode();
+  const bool fuse_res = fuse_in && fuse_res_mode();
+  int64_t* sb = stats + (size_t)(2 * L) * stats_per_conv;
+  uint8_t* xlast;
+  if (fuse_res && L > 0) {
+    // Fully fused residual chain: per block TWO launches and no elementwise pass.
+    //   conv1 of block 0 reads x_0 = neck output;  conv2 applies bn1 + relu1 in its load path (XF 1);
+    //   conv1 of block l+1 - and the bottleneck conv - form x_{l+1} = bn2(c2_l) + x_l in their load path (XF 2) and write
+    //   x_{l+1} back (ping-pong xa / xb2; x_0 stays in `res` for the long skip, model.py:115).
+    const uint8_t* xprev = res;
+    uint8_t* xnext = xa;
+    for (int l = 0; l < L; ++l) {   // ResidualBlock.forward (model.py:67-69)
+      int64_t* s1 = stats + (size_t)(2 * l) * stats_per_conv;
+      int64_t* s2 = stats + (size_t)(2 * l + 1) * stats_per_conv;
+      if (l == 0) {
+        if ((rc = fsr_conv3x3_c64(res, prm->stem_w1[0], raw, nullptr, s1, nullptr, nb, H, W, F, FSR_EPI_RAW_STATS, 0, 0.f, 0, dt, st))) return rc;
+      } else {
+        int64_t* s2p = stats + (size_t)(2 * l - 1) * stats_per_conv;
+        if ((rc = fsr_conv3x3_c64_res_in(yb, s2p, 1e-5f, xprev, xnext, prm->stem_w1[l], raw, s1, nb, H, W, dt, st))) return rc;
+        xprev = xnext;
+        xnext = (xnext == xa) ? xb2 : xa;
+      }
       if ((rc = fsr_conv3x3_c64_in(raw, s1, prm->stem_alpha[l], 1e-5f, prm->stem_w2[l], yb, s2, nb, H, W, dt, st))) return rc;
-      if ((rc = fsr_instnorm_apply(yb, s2, cur, xb, nullptr, nb, H * W, F, FSR_ACT_NONE, 0.f, 1e-5f, dt, st))) return rc;
-    } else {
-      if ((rc = fsr_instnorm_apply(raw, s1, nullptr, yb, prm->stem_alpha[l], nb, H * W, F, FSR_ACT_PRELU, 0.f, 1e-5f, dt, st))) return rc;
-      if ((rc = fsr_conv3x3_c64(yb, prm->stem_w2[l], raw, nullptr, s2, nullptr, nb, H, W, F, FSR_EPI_RAW_STATS, 0, 0.f, 0, dt, st))) return rc;
-      if ((rc = fsr_instnorm_apply(raw, s2, cur, xb, nullptr, nb, H * W, F, FSR_ACT_NONE, 0.f, 1e-5f, dt, st))) return rc;
     }
-    cur = xb;
-  }
-  {   // bottleneck + long skip (model.py:86-95, 115)
-    int64_t* sb = stats + (size_t)(2 * L) * stats_per_conv;
+    // bottleneck (model.py:86-95): its input x_L = bn2(c2_{L-1}) + x_{L-1} is formed in the load path as well
+    int64_t* s2p = stats + (size_t)(2 * L - 1) * stats_per_conv;
+    if ((rc = fsr_conv3x3_c64_res_in(yb, s2p, 1e-5f, xprev, xnext, prm->bott_w, raw, sb, nb, H, W, dt, st))) return rc;
+    xlast = (xnext == xa) ? xb2 : xa;      // free buffer for the bottleneck's normalised output
+  } else {
+    const uint8_t* cur = res;
+    for (int l = 0; l < L; ++l) {   // ResidualBlock.forward (model.py:67-69)
+      int64_t* s1 = stats + (size_t)(2 * l) * stats_per_conv;
+      int64_t* s2 = stats + (size_t)(2 * l + 1) * stats_per_conv;
+      if ((rc = fsr_conv3x3_c64(cur, prm->stem_w1[l], raw, nullptr, s1, nullptr, nb, H, W, F, FSR_EPI_RAW_STATS, 0, 0.f, 0, dt, st))) return rc;
+      if (fuse_in) {
+        // bn1 + relu1 (model.py:55-56) applied to the halo tile inside conv2's load path: one HBM round trip less per block
+        if ((rc = fsr_conv3x3_c64_in(raw, s1, prm->stem_alpha[l], 1e-5f, prm->stem_w2[l], yb, s2, nb, H, W, dt, st))) return rc;
+        if ((rc = fsr_instnorm_apply(yb, s2, cur, xa, nullptr, nb, H * W, F, FSR_ACT_NONE, 0.f, 1e-5f, dt, st))) return rc;
+      } else {
+        if ((rc = fsr_instnorm_apply(raw, s1, nullptr, yb, prm->stem_alpha[l], nb, H * W, F, FSR_ACT_PRELU, 0.f, 1e-5f, dt, st))) return rc;
+        if ((rc = fsr_conv3x3_c64(yb, prm->stem_w2[l], raw, nullptr, s2, nullptr, nb, H, W, F, FSR_EPI_RAW_STATS, 0, 0.f, 0, dt, st))) return rc;
+        if ((rc = fsr_instnorm_apply(raw, s2, cur, xa, nullptr, nb, H * W, F, FSR_ACT_NONE, 0.f, 1e-5f, dt, st))) return rc;
+      }
+      cur = xa;
+    }
+    // bottleneck (model.py:86-95)
     if ((rc = fsr_conv3x3_c64(cur, prm->bott_w, raw, nullptr, sb, nullptr, nb, H, W, F, FSR_EPI_RAW_STATS, 0, 0.f, 0, dt, st))) return rc;
-    if ((rc = fsr_instnorm_apply(raw, sb, res, xb, nullptr, nb, H * W, F, FSR_ACT_NONE, 0.f, 1e-5f, dt, st))) return rc;
+    xlast = xb2;
   }
+  // + long skip (model.py:115)
+  if ((rc = fsr_instnorm_apply(raw, sb, res, xlast, nullptr, nb, H * W, F, FSR_ACT_NONE, 0.f, 1e-5f, dt, st))) return rc;
   // upsampling x2 (model.py:39-40) and head (model.py:102-110)
-  if ((rc = fsr_conv3x3_c64(xb, prm->up_w[0], u0, prm->up_b[0], nullptr, prm->up_alpha[0], nb, H, W, 256, FSR_EPI_PS_PRELU, 0, 0.f, 0, dt, st))) return rc;
+  if ((rc = fsr_conv3x3_c64(xlast, prm->up_w[0], u0, prm->up_b[0], nullptr, prm->up_alpha[0], nb, H, W, 256, FSR_EPI_PS_PRELU, 0, 0.f, 0, dt, st))) return rc;
   if ((rc = fsr_conv3x3_c64(u0, prm->up_w[1], u1, prm->up_b[1], nullptr, prm->up_alpha[1], nb, 2 * H, 2 * W, 256, FSR_EPI_PS_PRELU, 0, 0.f, 0, dt, st))) return rc;
   return fsr_conv3x3_c64(u1, prm->head_w, yout, prm->head_b, nullptr, nullptr, nb, 4 * H, 4 * W, 16, FSR_EPI_HEAD_TANH, 0, 0.f, out_u8, dt, st);
 }
@@ -747,10 +875,11 @@ int fsr_generator_forward(const FsrGeneratorParams* prm, const void* x, void* y,
   uint8_t* b_res = base;            // neck output (long-skip source)
   uint8_t* b_x = base + P;          // running residual-chain activation
   uint8_t* b_raw = base + 2 * P;    // raw conv output (pre InstanceNorm)
-  uint8_t* b_y = base + 3 * P;      // normalised + PReLU intermediate
-  uint8_t* b_u0 = base + 4 * P;     // [N,2H,2W,64]
-  uint8_t* b_u1 = base + 8 * P;     // [N,4H,4W,64]
-  int64_t* b_stats = reinterpret_cast<int64_t*>(base + 24 * P);
+  uint8_t* b_y = base + 3 * P;      // normalised + PReLU intermediate / raw conv2 output of the fused chain
+  uint8_t* b_x2 = base + 4 * P;     // second residual-chain buffer (ping-pong of the fused chain)
+  uint8_t* b_u0 = base + 5 * P;     // [N,2H,2W,64]
+  uint8_t* b_u1 = base + 9 * P;     // [N,4H,4W,64]
+  int64_t* b_stats = reinterpret_cast<int64_t*>(base + 25 * P);
   const size_t stats_per_conv = (size_t)N * F * 2;
   FSR_CUDA(cudaMemsetAsync(b_stats, 0, (size_t)(2 * L + 1) * stats_per_conv * sizeof(int64_t), st));
 
@@ -782,7 +911,7 @@ int fsr_generator_forward(const FsrGeneratorParams* prm, const void* x, void* y,
       FSR_CUDA(cudaStreamWaitEvent(s, g_fork, 0));
     }
     rc = generator_chain(prm, reinterpret_cast<const uint8_t*>(x) + n0 * in_img, reinterpret_cast<uint8_t*>(y) + n0 * out_img,
-                         b_res + n0 * img_bytes, b_x + n0 * img_bytes, b_raw + n0 * img_bytes, b_y + n0 * img_bytes,
+                         b_res + n0 * img_bytes, b_x + n0 * img_bytes, b_x2 + n0 * img_bytes, b_raw + n0 * img_bytes, b_y + n0 * img_bytes,
                          b_u0 + n0 * 4 * img_bytes, b_u1 + n0 * 16 * img_bytes, b_stats + (size_t)n0 * F * 2, stats_per_conv,
                          nb, H, W, in_u8, out_u8, s);
     if (rc) return rc;
@@ -1071,6 +1200,57 @@ int fsr_crop_resize_aa(const uint8_t* cache, const int64_t* img_off, const int32
   LaunchScope scope(FSR_K_NONE - 1, st);
   crop_resize_aa_kernel<<<dim3((unsigned)B, 3), 256, smem, st>>>(p);
   return cuda_rc(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------ data-parallel exchange (nccl_comm.cuh)
+int fsr_nccl_available(void) { return nccl_api().ok ? 1 : 0; }
+
+int fsr_nccl_version(void) {
+  const NcclApi& a = nccl_api();
+  if (!a.ok || !a.GetVersion) return FSR_ERR_NO_NCCL;
+  int v = 0;
+  return a.GetVersion(&v) == 0 ? v : FSR_ERR_NCCL;
+}
+
+int fsr_nccl_unique_id(void* id_out_host) {
+  const NcclApi& a = nccl_api();
+  if (!a.ok) return FSR_ERR_NO_NCCL;
+  if (!id_out_host) return FSR_ERR_BAD_ARG;
+  return a.GetUniqueId(reinterpret_cast<NcclUniqueId*>(id_out_host)) == 0 ? FSR_OK : FSR_ERR_NCCL;
+}
+
+int fsr_nccl_init(const void* id_host, int rank, int world, void** comm_out) {
+  const NcclApi& a = nccl_api();
+  if (!a.ok) return FSR_ERR_NO_NCCL;
+  if (!id_host || !comm_out || world < 1 || rank < 0 || rank >= world) return FSR_ERR_BAD_ARG;
+  NcclUniqueId id;
+  memcpy(&id, id_host, sizeof(id));
+  NcclComm c = nullptr;
+  if (a.CommInitRank(&c, world, id, rank) != 0) return FSR_ERR_NCCL;
+  *comm_out = c;
+  return FSR_OK;
+}
+
+int fsr_nccl_allreduce(void* comm, float* buf, size_t n, void* stream) {
+  const NcclApi& a = nccl_api();
+  if (!a.ok) return FSR_ERR_NO_NCCL;
+  if (!comm || !buf) return FSR_ERR_BAD_ARG;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return a.AllReduce(buf, buf, n, kNcclFloat32, kNcclSum, comm, (cudaStream_t)stream) == 0 ? FSR_OK : FSR_ERR_NCCL;
+}
+
+int fsr_nccl_broadcast(void* comm, float* buf, size_t n, int root, void* stream) {
+  const NcclApi& a = nccl_api();
+  if (!a.ok) return FSR_ERR_NO_NCCL;
+  if (!comm || !buf) return FSR_ERR_BAD_ARG;
+  return a.Broadcast(buf, buf, n, kNcclFloat32, root, comm, (cudaStream_t)stream) == 0 ? FSR_OK : FSR_ERR_NCCL;
+}
+
+int fsr_nccl_destroy(void* comm) {
+  const NcclApi& a = nccl_api();
+  if (!a.ok) return FSR_ERR_NO_NCCL;
+  if (!comm) return FSR_OK;
+  return a.CommDestroy(comm) == 0 ? FSR_OK : FSR_ERR_NCCL;
 }
 
 }  // extern "C"

@@ -18,6 +18,10 @@
 //   * B       = the Cout-slice of the weights, resident in smem for the whole persistent CTA
 //               (9 taps x NS rows x 128 B, K-major, 128B swizzle).
 //   * D       = fp32 accumulators in TMEM, double buffered (2 x NS columns).
+// XF (fused input transform, HALO1 + NS = 64 only): 0 = none; 1 = the input is the RAW output of the block's first conv
+// and y = PReLU(InstanceNorm(raw)) (model.py:55-56) is applied to the staged halo tile before the MMAs read it;
+// 2 = the input is the RAW conv2 output of the PREVIOUS block: x_next = InstanceNorm(raw) + x_prev (model.py:65+69) is
+// formed on the staged tile, and the tile's own pixels of x_next are written back for the next skip connection.
 // Warp roles: warp0 = TMA producer, warp1 = MMA issuer (+TMEM alloc), then 4 or 8 epilogue warps
 // (TMEM -> registers -> fused epilogue -> swizzled smem transpose -> coalesced global stores); with 8,
 // the two groups of 4 alternate tiles (group g owns accumulator buffer g).
@@ -54,8 +58,12 @@ struct ConvParams {
   // XF (fused input transform): the conv input is the RAW output of the previous conv; its InstanceNorm + PReLU
   // (model.py:55-56) is applied to the staged halo tile in shared memory before the MMAs read it
   const long long* in_stats;  // [N][64][2] fixed-point statistics of the input tensor
-  const float* in_alpha;      // PReLU slope (device pointer)
+  const float* in_alpha;      // PReLU slope (device pointer)                                   (XF == 1)
   float in_eps;
+  // XF == 2: the input is the RAW conv2 output of the PREVIOUS residual block; x_next = InstanceNorm(raw) + in_res
+  // (model.py:65 + :69) is formed on the staged tile and the tile's own pixels of x_next are written to x_out
+  const void* in_res;         // x_prev [N,H,W,64] NHWC T
+  void* x_out;                // x_next [N,H,W,64] NHWC T (aliases neither in_res nor the raw input)
 };
 
 template <bool HALO1>
@@ -111,7 +119,7 @@ FSR_DEVINL void warp_reduce64(float (&v)[64], int lane) {
   }
 }
 
-template <int NS, int EPI, typename T, bool HALO1, bool XF = false>
+template <int NS, int EPI, typename T, bool HALO1, int XF = 0>
 __global__ void __launch_bounds__(XF ? ConvCfg<NS, HALO1>::kThreadsXf : ConvCfg<NS, HALO1>::kThreads, 1)
 conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                    const __grid_constant__ CUtensorMap tm_out, const ConvParams p) {
@@ -300,7 +308,7 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     // 128 B; the 16-byte chunk of channel group g sits at chunk g ^ (row & 7): 128B swizzle on absolute address bits,
     // stage bases are 1024-B aligned).  Same fp32 operations as instnorm_apply_kernel -> bit-identical activations.
     // Rows outside the image stay zero (the conv's zero padding comes AFTER the normalisation).
-    if constexpr (XF) {
+    if constexpr (XF == 1) {
       const int tid = threadIdx.x - (64 + 32 * Cfg::kEpiWarps);      // 0 .. 32*kXfWarps-1
       const int g = tid & 7, r_first = tid >> 3;
       constexpr int kRowStep = 4 * kXfWarps;
@@ -349,6 +357,82 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
             ou[k] = ok ? Cvt<T>::pack2(a, b) : vu[k];                     // rows outside the image stay zero
           }
           st_shared_v4(addr, ou[0], ou[1], ou[2], ou[3]);
+        }
+        fence_proxy_async();                 // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&xfull_bar[stage]);
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+    // =============================== input-transform warps (XF2) ===============================
+    // y = (raw - mean[n,c]) * rstd[n,c] + residual  (bn2 + skip, model.py:65+69 / bottleneck :94 fed by the chain) applied
+    // IN PLACE to the TMA-written halo tile of the RAW conv2 output; the residual x comes straight from global memory
+    // (16-byte vectors, 1.4x halo overhead, L2 hits for the halo) and the tile's OWN 16x8 pixels of y are written back to
+    // x_out for the next block's skip connection.  Same fp32 operations as instnorm_apply_kernel (normalise, no
+    // activation, add the residual as float, round once) -> bit-identical activations.
+    if constexpr (XF == 2) {
+      const int tid = threadIdx.x - (64 + 32 * Cfg::kEpiWarps);      // 0 .. 32*kXfWarps-1
+      const int g = tid & 7, r_first = tid >> 3;
+      constexpr int kRowStep = 4 * kXfWarps;
+      const double inv_hw = 1.0 / (double)(p.H * p.W);
+      float mean[8], rstd[8];
+      int cur_n = -1;
+      int stage = 0; uint32_t phase = 0;
+      const T* res = reinterpret_cast<const T*>(p.in_res);
+      T* xo = reinterpret_cast<T*>(p.x_out);
+      for (int t = t_begin; t < t_end; ++t) {
+        const int n = t / tiles_per_img;
+        const int rem = t - n * tiles_per_img;
+        const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+        const int x0 = tx * TW, y0 = ty * TH;
+        if (n != cur_n) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            stat_mean_rstd(p.in_stats + ((size_t)n * 64 + 8 * g + k) * 2, inv_hw, p.in_eps, mean[k], rstd[k]);
+          cur_n = n;
+        }
+        constexpr int kRows = Geo::kBoxW * Geo::kBoxH;                    // 180
+        // coordinates of the NEXT tile: its residual rows are prefetched into L2 one tile (~1.5 us) ahead, so that the
+        // loads of the rolled loop below are L2 hits (x_prev was written two launches ago: 236 MB, not L2 resident)
+        const bool has_next = t + 1 < t_end;
+        const int tn = has_next ? t + 1 : t;
+        const int nn = tn / tiles_per_img;
+        const int remn = tn - nn * tiles_per_img;
+        const int tyn = remn / p.tiles_x, txn = remn - tyn * p.tiles_x;
+        const int x0n = txn * TW, y0n = tyn * TH;
+        mbar_wait(&full_bar[stage], phase);
+        const uint32_t base = smem_u32(smem_a + stage * Geo::kStageBytes);
+#pragma unroll 4
+        for (int r = r_first; r < kRows; r += kRowStep) {
+          const int by = r / Geo::kBoxW, bx = r - by * Geo::kBoxW;
+          const int gy = y0 - 1 + by, gx = x0 - 1 + bx;
+          const bool ok = gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
+          const size_t goff = (((size_t)n * p.H + (ok ? gy : 0)) * p.W + (ok ? gx : 0)) * 64 + 8 * g;
+          const uint4 rv = *reinterpret_cast<const uint4*>(res + goff);
+          if (has_next && (g & 1) == 0) {          // one prefetch per 32-byte sector of the next tile's row
+            const int gyn = y0n - 1 + by, gxn = x0n - 1 + bx;
+            if (gyn >= 0 && gyn < p.H && gxn >= 0 && gxn < p.W)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(res + (((size_t)nn * p.H + gyn) * p.W + gxn) * 64 + 8 * g));
+          }
+          const uint32_t addr = base + (uint32_t)r * 128u + (uint32_t)((g ^ (r & 7)) << 4);
+          const uint4 v = ld_shared_v4(addr);
+          const uint32_t vu[4] = {v.x, v.y, v.z, v.w};
+          const uint32_t su[4] = {rv.x, rv.y, rv.z, rv.w};
+          uint32_t ou[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 f = Cvt<T>::unpack2(vu[k]);
+            const float2 s2 = Cvt<T>::unpack2(su[k]);
+            float a = (f.x - mean[2 * k]) * rstd[2 * k];
+            float b = (f.y - mean[2 * k + 1]) * rstd[2 * k + 1];
+            a += s2.x;
+            b += s2.y;
+            ou[k] = ok ? Cvt<T>::pack2(a, b) : vu[k];                     // rows outside the image stay zero
+          }
+          st_shared_v4(addr, ou[0], ou[1], ou[2], ou[3]);
+          // write-back of the tile's own pixels (each image pixel is interior to exactly one tile)
+          if (ok && by >= 1 && by <= TH && bx >= 1 && bx <= TW)
+            *reinterpret_cast<uint4*>(xo + goff) = make_uint4(ou[0], ou[1], ou[2], ou[3]);
         }
         fence_proxy_async();                 // generic-proxy writes -> visible to the tensor core's async-proxy reads
         __syncwarp();

@@ -1,5 +1,5 @@
-// conv3x3_up_2cta.cuh - EXPERIMENTAL (compiled into libfsr_b200_experimental.so only, which the product never loads;
-// not yet run on hardware; parity test: tests/test_experimental_gpu.py, opt-in).
+// conv3x3_up_2cta.cuh - the CTA-pair form of the upsampling conv (default; GPU-validated bit-identical to the single-CTA kernel,
+// tests/test_fused_chain_gpu.py).
 //
 // The 64 -> 256 upsampling conv (+ bias + PixelShuffle(2) + PReLU; reference model.py:30-40) as a CTA-PAIR kernel:
 // tcgen05.mma.cta_group::2, M = 256 (two 128-pixel tiles, one per CTA), N = 256 (all output channels), K = 16.

@@ -20,6 +20,8 @@ enum : int {
   FSR_ERR_TENSORMAP = -3,
   FSR_ERR_WORKSPACE = -4,
   FSR_ERR_NO_DRIVER = -5,
+  FSR_ERR_NO_NCCL = -6,
+  FSR_ERR_NCCL = -7,
   FSR_ERR_CUDA_BASE = -1000,  // -(1000 + cudaError_t)
 };
 

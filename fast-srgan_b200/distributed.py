@@ -8,8 +8,9 @@ The path shards on batch: every op is per-sample (InstanceNorm has no cross-samp
 """
 from __future__ import annotations
 
+import ctypes
 import os
-from typing import Dict, Tuple
+from typing import Dict, Optional, Tuple
 
 import torch
 import torch.distributed as dist
@@ -62,3 +63,62 @@ def rank_and_world(group=None) -> Tuple[int, int]:
     if dist.is_available() and dist.is_initialized():
         return dist.get_rank(group), dist.get_world_size(group)
     return 0, 1
+
+
+class FlatComm:
+    """The gradient exchange of the GAN step: in-place sum of a flat fp32 buffer over the ranks.
+
+    On CUDA it is libfsr_b200's own NCCL communicator (fsr_nccl_* in include/fsr_b200.h: ncclAllReduce on the CURRENT
+    stream, so the call can sit inside the step's CUDA graph and on the side stream of the overlap window).  The
+    128-byte NCCL id travels from rank 0 over the existing torch.distributed group (any backend).  FSR_NCCL_CAPI=0, a
+    CPU device or a missing libnccl fall back to torch.distributed.all_reduce on the same group."""
+
+    def __init__(self, device: torch.device, group=None):
+        self.group = group
+        self.rank, self.world = rank_and_world(group)
+        self._h: Optional[ctypes.c_void_p] = None
+        self._lib = None
+        if self.world > 1 and device.type == "cuda" and os.environ.get("FSR_NCCL_CAPI", "1") != "0":
+            from . import _lib as L
+            lib = L.load()
+            if lib.fsr_nccl_available():
+                buf = ctypes.create_string_buffer(128)
+                if self.rank == 0:
+                    L.check(lib.fsr_nccl_unique_id(buf), "fsr_nccl_unique_id")
+                obj = [buf.raw if self.rank == 0 else None]
+                src = dist.get_global_rank(group, 0) if group is not None else 0
+                dist.broadcast_object_list(obj, src=src, group=group)
+                h = ctypes.c_void_p()
+                with torch.cuda.device(device):
+                    L.check(lib.fsr_nccl_init(obj[0], self.rank, self.world, ctypes.byref(h)), "fsr_nccl_init")
+                self._h, self._lib, self._L = h, lib, L
+
+    @property
+    def native(self) -> bool:
+        return self._h is not None
+
+    def allreduce(self, flat: torch.Tensor) -> torch.Tensor:
+        if self._h is not None:
+            assert flat.dtype == torch.float32 and flat.is_contiguous()
+            self._L.check(self._lib.fsr_nccl_allreduce(self._h, flat.data_ptr(), flat.numel(), self._L.stream_ptr(flat.device)),
+                          "fsr_nccl_allreduce")
+            return flat
+        return allreduce_flat(flat, self.group)
+
+    def broadcast(self, flat: torch.Tensor, src: int = 0) -> torch.Tensor:
+        if self._h is not None:
+            self._L.check(self._lib.fsr_nccl_broadcast(self._h, flat.data_ptr(), flat.numel(), src, self._L.stream_ptr(flat.device)),
+                          "fsr_nccl_broadcast")
+            return flat
+        return broadcast_flat(flat, self.group, src)
+
+    def close(self):
+        if self._h is not None:
+            self._lib.fsr_nccl_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -135,13 +135,15 @@ class GeneratorNet:
             names += [f"stem.{i}.conv1.weight", f"stem.{i}.conv2.weight"]
         return names + ["bottleneck.0.weight"]
 
-    def pack(self, need_bwd: bool):
+    def pack(self, need_bwd: bool, force: bool = False):
         """(Re)pack into PERSISTENT buffers (same addresses for the lifetime of the net): a captured CUDA graph keeps
-        reading the right memory, and no allocation happens per step."""
-        if self._packed_version == self.fp.version and (not need_bwd or self._bwd_version == self.fp.version):
+        reading the right memory, and no allocation happens per step.  force: re-pack whatever the version counters
+        say (the step calls it right after the point where the parameters change, so that the pack kernels are part of
+        every captured graph, not only of those captured while the Python-side version happened to be stale)."""
+        if not force and self._packed_version == self.fp.version and (not need_bwd or self._bwd_version == self.fp.version):
             return
         p, P, dt = self.fp.p, self.P, self.dt
-        fwd_stale = self._packed_version != self.fp.version
+        fwd_stale = force or self._packed_version != self.fp.version
         for n in self._convs64():
             if fwd_stale:
                 P[n], _ = ops.pack_conv3x3(p[n], None, dt, out_w=P.get(n))
@@ -229,12 +231,12 @@ class DiscriminatorNet:
         self._bwd_version = -1
         self.P: Dict[str, torch.Tensor] = {}
 
-    def pack(self, need_bwd: bool):
+    def pack(self, need_bwd: bool, force: bool = False):
         """(Re)pack into persistent buffers (CUDA-graph safe, see GeneratorNet.pack)."""
-        if self._packed_version == self.fp.version and (not need_bwd or self._bwd_version == self.fp.version):
+        if not force and self._packed_version == self.fp.version and (not need_bwd or self._bwd_version == self.fp.version):
             return
         p, P, dt = self.fp.p, self.P, self.dt
-        fwd_stale = self._packed_version != self.fp.version
+        fwd_stale = force or self._packed_version != self.fp.version
         for i in range(7):
             w = p[f"stem.{i}.conv.weight"]
             if fwd_stale:
@@ -361,7 +363,19 @@ class VGGNet:
 
 # ====================================================================================== GAN step
 class GANEngine:
-    """One iteration of trainer.py:168-196 (`train_step`) and of the pre-training loop (:104-111)."""
+    """One iteration of trainer.py:168-196 (`train_step`) and of the pre-training loop (:104-111).
+
+    Schedule of a step (same results as the reference's order; what differs is only WHEN things run):
+      * `G(lr)` is evaluated ONCE.  The reference evaluates it at :173 (detached, for the discriminator step) and again
+        at :185; between the two only the discriminator is updated, the forward is deterministic and InstanceNorm keeps
+        no running statistics, so both evaluations are the same tensor bit for bit (asserted in
+        tests/test_train_step_gpu.py::test_generator_forward_is_identical_before_and_after_the_d_step).
+      * the discriminator's gradient exchange (all-reduce over ranks), its AdamW step and the re-pack of its weights
+        run on a SIDE stream while the main stream runs the two VGG19 passes, the content loss and the VGG data
+        gradient - none of which touch the discriminator (SURVEY.md 8e "legal overlap windows"); D(sr) at :186 waits
+        for the side stream.
+      * the whole step - collectives included, issued through libfsr_b200's fsr_nccl_* - is captured into ONE CUDA graph
+        per input shape after two eager warm-up steps."""
 
     def __init__(self, generator, discriminator, vgg, lr_g: float, lr_d: float, dtype: torch.dtype = torch.bfloat16,
                  loss_scale: Optional[float] = None, process_group=None):
@@ -376,95 +390,107 @@ class GANEngine:
         self.pg = process_group
         import os
         self.use_graph = os.environ.get("FSR_GRAPH", "1") != "0"
+        self.overlap = os.environ.get("FSR_TRAIN_OVERLAP", "1") != "0"
         self._graphs: Dict = {}
+        self._side: Optional[torch.cuda.Stream] = None
+        self.comm = None                                    # distributed.FlatComm: NCCL through the C ABI
         self.world = 1
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.world = torch.distributed.get_world_size(process_group)
         if self.world > 1:
+            from .distributed import FlatComm
+            self.comm = FlatComm(self.gp.flat.device, process_group)
             # replicas must START identical (they stay identical because every rank applies the same reduced gradient):
             # rank 0's parameters and Adam moments win, whatever each rank's RNG produced at construction
-            from .distributed import broadcast_flat
             for fp in (self.gp, self.dp):
                 for buf in (fp.flat, fp.m, fp.v):
-                    broadcast_flat(buf, self.pg)
+                    self.comm.broadcast(buf)
                 fp.version += 1
 
     def _allreduce(self, flat_grad: torch.Tensor):
         if self.world > 1:
-            from .distributed import allreduce_flat
-            allreduce_flat(flat_grad, self.pg)                         # NCCL sum over NVLink; 1/world is folded into AdamW
+            self.comm.allreduce(flat_grad)                  # NCCL sum over NVLink on the current stream; 1/world is folded into AdamW
 
+    # ------------------------------------------------------------------ public steps
     def train_step(self, lr_img: torch.Tensor, hr_img: torch.Tensor, noise: Dict[str, torch.Tensor]):
         """lr_img [B,3,h,w], hr_img [B,3,4h,4w] fp32 NCHW in [-1,1] (this rank's shard);
         noise = {"d_real","d_fake","g_real"}: uniform [0,1) tensors shaped like D's output (trainer.py:175,176,187).
 
-        With use_graph (default) the ~500 launches of a step are captured ONCE per input shape into three CUDA graphs
-        (after two eager warm-up steps) and replayed: [D forward/backward] -> all-reduce(D grads) -> [D AdamW + G step
-        forward/backward] -> all-reduce(G grads) -> [G AdamW].  The NCCL calls stay outside the graphs; inputs are copied
-        into static buffers; the AdamW step counters live in device memory."""
+        With use_graph (default) the ~450 launches of a step, both gradient all-reduces included, are captured ONCE per
+        input shape into one CUDA graph (after two eager warm-up steps) and replayed; inputs are copied into static
+        buffers; the AdamW step counters live in device memory."""
         lr_img, hr_img = lr_img.contiguous().float(), hr_img.contiguous().float()
         B = lr_img.shape[0]
         ins = (lr_img, hr_img, noise["d_real"].reshape(B, -1).contiguous().float(),
                noise["d_fake"].reshape(B, -1).contiguous().float(), noise["g_real"].reshape(B, -1).contiguous().float())
         if not self.use_graph:
-            return self._run_segments(ins, None)
+            return self._step(ins)
         key = (tuple(lr_img.shape), tuple(hr_img.shape))
         ext = (self.gp.ext_version, self.dp.ext_version, getattr(self.V.m, "_weights_version", 0))
         if ext != getattr(self, "_ext_seen", ext):
-            # load_state_dict / load_checkpoints since the capture: the captured graphs only re-pack what was stale at
-            # capture time (and VGG packs are re-allocated) -> drop them; the next two steps run eagerly, then re-capture
+            # load_state_dict / load_checkpoints since the capture: captured graphs only re-pack what the step itself
+            # changes (and VGG packs are re-allocated) -> drop them; the next two steps run eagerly, then re-capture
             self._graphs.clear()
         self._ext_seen = ext
         st = self._graphs.get(key)
         if st is None:
-            st = self._graphs[key] = dict(calls=0, graphs=None)
-        if st["graphs"] is None:
+            st = self._graphs[key] = dict(calls=0, graph=None)
+        if st["graph"] is None:
             st["calls"] += 1
             if st["calls"] <= 2:                                        # eager warm-up: allocator, func attributes, packs
-                return self._run_segments(ins, None)
+                return self._step(ins)
             st["inputs"] = [t.clone() for t in ins]
             torch.cuda.synchronize()
-            graphs, pool = [], None
-            for seg in (self._seg_d, self._seg_g, self._seg_opt):       # capture only: nothing executes here
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, pool=pool):
-                    seg(st["inputs"])
-                pool = g.pool()
-                graphs.append(g)
-            st["graphs"], st["out"] = graphs, self._out
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):                                   # capture only: nothing executes here
+                self._step(st["inputs"])
+            st["graph"], st["out"] = g, self._out
             for fp in (self.gp, self.dp):
                 fp.step_count -= 1                                      # undo the bookkeeping of the (non-executing) capture
         for dst, src in zip(st["inputs"], ins):
             dst.copy_(src, non_blocking=True)
-        self._run_segments(st["inputs"], st["graphs"])
+        st["graph"].replay()
         for fp in (self.gp, self.dp):
             fp.step_count += 1
             fp.version += 1
         self.G.m._packed_key = None
         return st["out"]
 
-    def _run_segments(self, ins, graphs):
-        if graphs is None:
-            self._seg_d(ins)
-            self._allreduce(self.dp.grad)
-            self._seg_g(ins)
-            self._allreduce(self.gp.grad)
-            self._seg_opt(ins)
+    def _step(self, ins):
+        """The whole iteration on the current stream (+ the side stream of the overlap window)."""
+        self._seg_d(ins)
+        main = torch.cuda.current_stream()
+        if self.overlap:
+            if self._side is None:
+                self._side = torch.cuda.Stream()
+            side = self._side
+            side.wait_stream(main)                                      # D gradients are complete
+            with torch.cuda.stream(side):
+                self._seg_d_update()
+            self._seg_content(ins)                                      # VGG passes: independent of the discriminator
+            main.wait_stream(side)                                      # updated + re-packed D before D(sr) at :186
         else:
-            graphs[0].replay()
-            self._allreduce(self.dp.grad)
-            graphs[1].replay()
-            self._allreduce(self.gp.grad)
-            graphs[2].replay()
+            self._seg_d_update()
+            self._seg_content(ins)
+        self._seg_adv_and_g(ins)
+        self._allreduce(self.gp.grad)
+        self._seg_opt(ins)
         return self._out
 
+    def _run_segments(self, ins, graphs=None):                          # kept for diagnostics / older callers
+        return self._step(ins)
+
+    # ------------------------------------------------------------------ segments
     def _seg_d(self, ins):
-        """discriminator step up to the gradient (trainer.py:171-180)."""
+        """G(lr) (saved for the generator step) and the discriminator step up to its gradient (trainer.py:171-180)."""
         lr_img, hr_img, n_real, n_fake, _ = ins
         S = self.S
         self._losses = losses = torch.zeros(4, dtype=torch.float32, device=lr_img.device)   # real, fake, adv bce, content sum
         self.dp.zero_grad()
-        sr, _ = self.G.forward(lr_img, save=False)                      # :173 (.detach())
+        self.gp.zero_grad()
+        self.G.pack(need_bwd=True, force=True)                          # G changed at the end of the previous step
+        self._sr, self._ctx_g = self.G.forward(lr_img, save=True)      # :173 == :185 (see class docstring)
+        sr = self._sr
         z_real, ctx_r = self.D.forward(hr_img, save=True)               # :172
         z_fake, ctx_f = self.D.forward(sr, save=True)                   # :174
         dz_r, dz_f = torch.empty_like(z_real), torch.empty_like(z_fake)
@@ -473,26 +499,34 @@ class GANEngine:
         self.D.backward(ctx_r, dz_r, wgrad=True, d_img=None)            # :180
         self.D.backward(ctx_f, dz_f, wgrad=True, d_img=None)
 
-    def _seg_g(self, ins):
-        """discriminator AdamW (trainer.py:181) and the generator step up to the gradient (:184-195)."""
-        lr_img, hr_img, _, _, n_g = ins
-        S, losses = self.S, self._losses
-        self.dp.adamw_step(self.lr_d, grad_scale=1.0 / (S * self.world))   # :181
-        self.gp.zero_grad()
-        sr, ctx_g = self.G.forward(lr_img, save=True)                   # :185
-        z, ctx_d = self.D.forward(sr, save=True)                        # :186 (updated D)
-        dz = torch.empty_like(z)
-        ops.bce_logits(z, n_g, 0.3, 0.7, losses[2:3], dz, grad_scale=0.5 * 0.1 * S)          # :187-188,194
+    def _seg_d_update(self):
+        """gradient exchange + discriminator AdamW (trainer.py:181) + re-pack of its weights (side stream)."""
+        self._allreduce(self.dp.grad)
+        self.dp.adamw_step(self.lr_d, grad_scale=1.0 / (self.S * self.world))
+        self.D.pack(need_bwd=True, force=True)
+
+    def _seg_content(self, ins):
+        """content loss and its gradient w.r.t. sr (trainer.py:190-192 and their part of :195)."""
+        _, hr_img, _, _, _ = ins
+        S, losses, sr = self.S, self._losses, self._sr
         fake_f, ctx_v = self.V.forward(sr, save=True)                   # :190
         real_f, _ = self.V.forward(hr_img, save=False)                  # :191
         dfeat = torch.empty_like(fake_f)
         ops.smooth_l1(fake_f, real_f, losses[3:4], dfeat, grad_scale=0.5 * S / fake_f.numel())   # :192,194
-        d_sr = torch.zeros_like(sr)
-        self.V.backward(ctx_v, dfeat, d_sr)                             # :195
-        self.D.backward(ctx_d, dz, wgrad=False, d_img=d_sr)
-        self.G.backward(ctx_g, d_sr)
-        nfeat = float(fake_f.numel())
-        self._out = dict(loss_real=losses[0], loss_fake=losses[1], adv_loss=0.1 * losses[2], content_loss=losses[3] / nfeat, sr=sr)
+        self._d_sr = torch.zeros_like(sr)
+        self.V.backward(ctx_v, dfeat, self._d_sr)                       # :195 (VGG branch)
+        self._nfeat = float(fake_f.numel())
+
+    def _seg_adv_and_g(self, ins):
+        """adversarial loss through the UPDATED discriminator and the generator backward (trainer.py:186-188, :195)."""
+        n_g = ins[4]
+        S, losses, sr = self.S, self._losses, self._sr
+        z, ctx_d = self.D.forward(sr, save=True)                        # :186 (updated D)
+        dz = torch.empty_like(z)
+        ops.bce_logits(z, n_g, 0.3, 0.7, losses[2:3], dz, grad_scale=0.5 * 0.1 * S)          # :187-188,194
+        self.D.backward(ctx_d, dz, wgrad=False, d_img=self._d_sr)       # :195 (D branch; its wasted wgrad is skipped)
+        self.G.backward(self._ctx_g, self._d_sr)
+        self._out = dict(loss_real=losses[0], loss_fake=losses[1], adv_loss=0.1 * losses[2], content_loss=losses[3] / self._nfeat, sr=sr)
 
     def _seg_opt(self, ins):
         self.gp.adamw_step(self.lr_g, grad_scale=1.0 / (self.S * self.world))   # :196

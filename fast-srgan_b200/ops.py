@@ -76,6 +76,21 @@ def conv3x3_c64_in(raw_in: torch.Tensor, stats_in: torch.Tensor, alpha: torch.Te
     return out, stats
 
 
+def conv3x3_c64_res_in(raw_in: torch.Tensor, stats_in: torch.Tensor, res: torch.Tensor, w_packed: torch.Tensor, eps: float = 1e-5):
+    """x_next = InstanceNorm(raw_in) + res formed in the conv's load path (model.py:65+69), then conv3x3(x_next):
+    -> (x_next NHWC, raw NHWC [N,H,W,64], stats int64 [N,64,2]); bit-identical to instnorm_apply(+residual) + conv."""
+    _cuda(raw_in, stats_in, res, w_packed)
+    N, H, W, C = raw_in.shape
+    assert C == 64 and raw_in.is_contiguous() and res.is_contiguous() and w_packed.shape[1] == 64
+    x_next = torch.empty_like(raw_in)
+    out = torch.empty_like(raw_in)
+    stats = torch.zeros((N, 64, 2), dtype=torch.int64, device=raw_in.device)
+    L.check(L.load().fsr_conv3x3_c64_res_in(raw_in.data_ptr(), stats_in.data_ptr(), eps, res.data_ptr(), x_next.data_ptr(),
+                                            w_packed.data_ptr(), out.data_ptr(), stats.data_ptr(), N, H, W,
+                                            L.dtype_code(raw_in.dtype), L.stream_ptr(raw_in.device)), "conv3x3 fused IN+skip input")
+    return x_next, out, stats
+
+
 def conv3x3_c64_bias_act(x, w_packed, bias, act: int = L.ACT_NONE, slope: float = 0.0, alpha=None):
     _cuda(x, w_packed, bias)
     N, H, W, C = x.shape

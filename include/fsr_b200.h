@@ -213,6 +213,11 @@ enum { FSR_K_NONE = -1, FSR_K_NECK = 0, FSR_K_CONV_RES = 1, FSR_K_IN_APPLY = 2, 
 #define FSR_PROFILE_MAX 4096
 int fsr_profile_enable(int kernel_id);
 int fsr_profile_read(float* ms_out, int capacity);
+/* same for several kernels at once: bit k of `mask` enables kernel id k; fsr_profile_read_ids also returns each record's id */
+int fsr_profile_enable_mask(unsigned mask);
+int fsr_profile_read_ids(float* ms_out, int* ids_out, int capacity);
+/* ... and the ALGORITHMIC FLOPs of each timed launch (2*N*Ho*Wo*Cout*Cin*taps for the conv kernels, 0 otherwise) */
+int fsr_profile_read_ex(float* ms_out, int* ids_out, double* flops_out, int capacity);
 unsigned long long fsr_launch_count(void);
 
 /* A-operand staging of the tensor-core conv: 0 = three column-shifted halo tiles per 8x16-pixel tile,
@@ -252,6 +257,23 @@ int fsr_crop_resize_aa(const uint8_t* cache, const int64_t* img_off, const int32
  * fsr_instnorm_apply -> bit-identical results).  out must not alias x_raw.  Single-halo-tile mode only. */
 int fsr_conv3x3_c64_in(const void* x_raw, const int64_t* in_stats, const float* in_alpha, float in_eps, const void* w_packed,
                        void* out, int64_t* stats, int N, int H, int W, int dtype, void* stream);
+/* The FIRST conv of a ResidualBlock (or the bottleneck conv) with the PREVIOUS block's second InstanceNorm + skip fused
+ * into its load path:
+ *   x_next = InstanceNorm(x_raw) + res        (model.py:65 + :69 of block l; written to x_out for the next skip)
+ *   out, stats = conv3x3(x_next)              (model.py:47-54 of block l+1, or the bottleneck :87-93)
+ * x_raw = RAW conv2 output of block l with statistics in_stats; res = x_l; x_out = x_{l+1}; all [N,H,W,64] NHWC dtype.
+ * x_out must alias neither res nor x_raw; out must alias none of them.  x_next, out and stats are bit-identical to
+ * fsr_instnorm_apply(+residual) followed by fsr_conv3x3_c64 RAW_STATS.  Single-halo-tile mode only. */
+int fsr_conv3x3_c64_res_in(const void* x_raw, const int64_t* in_stats, float in_eps, const void* res, void* x_out,
+                           const void* w_packed, void* out, int64_t* stats, int N, int H, int W, int dtype, void* stream);
+/* 1 (default): fsr_generator_forward runs the residual chain fully fused (fsr_conv3x3_c64_in + fsr_conv3x3_c64_res_in:
+ * two launches per block, one InstanceNorm pass left per forward); 0: one normalise pass per block; -1: environment
+ * default (FSR_FUSE_RES=0 disables).  Needs fuse_in. */
+int fsr_set_fuse_res(int on);
+/* 1 (default): the 64 -> 256 upsampling conv (FSR_EPI_PS_PRELU) runs as a CTA-pair kernel (tcgen05 cta_group::2, M = 256,
+ * N = 256: each SM feeds the pair's MMA with its own pixel tile and HALF of the weights); 0: one CTA per 128-column half;
+ * -1: environment default (FSR_UP_2CTA).  Bit-identical results. */
+int fsr_set_up_2cta(int on);
 /* 1 (default): fsr_generator_forward uses fsr_conv3x3_c64_in for every residual block; 0: separate normalise pass;
  * -1: environment default (FSR_FUSE_IN=0 disables). */
 int fsr_set_fuse_in(int on);
@@ -265,6 +287,23 @@ int fsr_set_gen_ws(int on);
  * (mma.sync m16n8k16, fp32 operand split hi+lo: fp32-input accuracy); 0: the CUDA-core kernels (A/B and tests);
  * -1: environment default (FSR_SMALL_MMA). */
 int fsr_set_small_mma(int on);
+
+/* ---- data-parallel exchange of the GAN step (the reference has no collective: trainer.py:180-181 and
+ * :195-196 run on one device).  One process per GPU; the flat fp32 gradient buffer of a network is summed over ranks
+ * with ncclAllReduce over NVLink/NVSwitch, issued on `stream` (capturable into the step's CUDA graph).  NCCL is bound
+ * at run time (dlopen libnccl.so.2 - PyTorch's bundled copy when PyTorch is in the process); without it these return
+ * FSR_ERR_NO_NCCL (-6).  Bootstrap: rank 0 calls fsr_nccl_unique_id, the 128 bytes travel to the other ranks by any
+ * side channel (torch.distributed store / broadcast), every rank calls fsr_nccl_init with its CUDA device current. */
+#define FSR_NCCL_ID_BYTES 128
+int fsr_nccl_available(void);                                /* 1 if libnccl could be bound, else 0 */
+int fsr_nccl_version(void);                                  /* e.g. 22809; <0 on error */
+int fsr_nccl_unique_id(void* id_out_host);                   /* HOST buffer of FSR_NCCL_ID_BYTES */
+int fsr_nccl_init(const void* id_host, int rank, int world, void** comm_out);     /* collective: all ranks call it */
+/* in-place sum over ranks of n fp32 values at `buf` (device) - after trainer.py:180 (discriminator) / :195 (generator) */
+int fsr_nccl_allreduce(void* comm, float* buf, size_t n, void* stream);
+/* rank `root`'s buffer to every rank (replica initialisation / resume) */
+int fsr_nccl_broadcast(void* comm, float* buf, size_t n, int root, void* stream);
+int fsr_nccl_destroy(void* comm);
 
 #ifdef __cplusplus
 }

@@ -42,8 +42,13 @@ def _worker(rank, world, port, ret):
     gl = d_grads(D.shard_batch(hr, rank, world), D.shard_noise(noise, rank, world)["d_real"])
     for k, v in gl.items():
         fp.g[k].copy_(v.float())
-    D.allreduce_flat(fp.grad)
+    comm = D.FlatComm(torch.device("cpu"))         # CPU / gloo: the torch.distributed fallback of the engine's exchange
+    assert not comm.native and (comm.rank, comm.world) == (rank, world)
+    comm.allreduce(fp.grad)
     fp.grad.mul_(1.0 / world)                      # the factor the engine folds into AdamW
+    probe = torch.full((5,), float(rank + 1))
+    comm.broadcast(probe)                          # replica initialisation: rank 0's buffer wins
+    assert torch.equal(probe, torch.ones(5))
     full = d_grads(hr, noise["d_real"])
     worst = max(((fp.g[k].double() - full[k]).norm() / full[k].norm()).item() for k in full)
     ret[rank] = worst

@@ -137,6 +137,25 @@ def test_gan_train_step_vs_fp64_oracle(golden, dt, ltol):
                 assert agree >= 0.8, (name, k, agree)
 
 
+def test_generator_forward_is_identical_before_and_after_the_d_step():
+    """The engine evaluates G(lr) once per step where the reference evaluates it twice (trainer.py:173 and :185).  That is
+    result-identical because only the discriminator changes in between and the forward is bitwise deterministic:
+    checked here by running the discriminator half of a step between two evaluations."""
+    tr, out, res, og, od = _run_step(torch.bfloat16)
+    e = tr.engine
+    g = torch.Generator().manual_seed(3)
+    lr_img = (torch.rand((4, 3, 24, 24), generator=g) * 2 - 1).cuda()
+    hr_img = (torch.rand((4, 3, 96, 96), generator=g) * 2 - 1).cuda()
+    n = [torch.rand((4, 36), generator=g).cuda() for _ in range(3)]
+    a, _ = e.G.forward(lr_img, save=False)
+    a = a.clone()
+    e._seg_d((lr_img, hr_img, n[0], n[1], n[2]))
+    e._seg_d_update()                                   # discriminator AdamW: the only parameter change between :173 and :185
+    b, _ = e.G.forward(lr_img, save=True)
+    torch.cuda.synchronize()
+    assert torch.equal(a, b) and torch.equal(e._sr, b)
+
+
 def test_train_step_updates_inference_weights():
     """After a step the Generator module (inference path) must see the updated parameters."""
     tr, out, res, og, od = _run_step(torch.bfloat16)
