@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libfsr_b200.so")
 FSR_MAX_LAYERS = 32
 FSR_F16, FSR_BF16 = 0, 1
-EPI_RAW_STATS, EPI_BIAS_ACT, EPI_PS_PRELU, EPI_HEAD_TANH = 0, 1, 2, 3
+EPI_RAW_STATS, EPI_BIAS_ACT, EPI_PS_PRELU, EPI_HEAD_TANH, EPI_F32 = 0, 1, 2, 3, 4
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_PRELU = 0, 1, 2, 3
 K_NONE, K_NECK, K_CONV_RES, K_IN_APPLY, K_CONV_UP, K_CONV_HEAD, K_CONV_BIAS_ACT, K_CONV_GEN, K_CONV_WGRAD = -1, 0, 1, 2, 3, 4, 5, 6, 7
 
@@ -79,6 +79,12 @@ _SIGS = {
     "fsr_psnr_ssim": (_i, [_fp, _fp, _i, _i, _i, _i, _f, _f, _f, _vp, _vp, _vp, _vp]),
     "fsr_crop_resize_aa": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _fp, _fp, _vp]),
     "fsr_set_overlap_streams": (_i, [_i]),
+    "fsr_split_f32": (_i, [_fp, _vp, _vp, _sz, _vp]),
+    "fsr_neck_conv3x3_f32": (_i, [_fp, _fp, _fp, _fp, _fp, _i, _i, _i, _vp]),
+    "fsr_in_stats_f32": (_i, [_fp, _vp, _i, _i, _vp]),
+    "fsr_in_apply_f32": (_i, [_fp, _vp, _fp, _fp, _vp, _vp, _fp, _i, _i, _i, _f, _vp]),
+    "fsr_ps_prelu_f32": (_i, [_fp, _fp, _fp, _fp, _vp, _vp, _i, _i, _i, _vp]),
+    "fsr_tanh_f32": (_i, [_fp, _vp, _i, _i, _vp]),
     "fsr_nccl_available": (_i, []),
     "fsr_nccl_version": (_i, []),
     "fsr_nccl_unique_id": (_i, [_vp]),

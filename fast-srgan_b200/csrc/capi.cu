@@ -11,6 +11,7 @@
 #include "small_mma.cuh"
 #include "aux_kernels.cuh"
 #include "nccl_comm.cuh"
+#include "precise.cuh"
 
 #include <cudaTypedefs.h>
 #include <atomic>
@@ -102,6 +103,20 @@ int make_act_map_strided(CUtensorMap* tm, const void* ptr, int N, int H, int W, 
   return r == CUDA_SUCCESS ? FSR_OK : FSR_ERR_TENSORMAP;
 }
 
+// PixelShuffle(2) output [N,2H,2W,64] viewed as [N][H][i:2][W][(j,c):128] (the up conv's store target): one box
+// {64 ch, 8 px, 1, 4 rows, 1} = the 32 pixels of an epilogue warp at sub-position (i, j), start coordinate j*64 in dim 0
+int make_ps_out_map(CUtensorMap* tm, const void* ptr, int N, int H, int W, int dtype) {
+  auto enc = get_encode_fn();
+  if (!enc) return FSR_ERR_NO_DRIVER;
+  cuuint64_t gdim[5] = {128, (cuuint64_t)W, 2, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t gstr[4] = {256, (cuuint64_t)2 * W * 128, (cuuint64_t)4 * W * 128, (cuuint64_t)2 * H * 2 * W * 128};
+  cuuint32_t box[5] = {64, 8, 1, 4, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(tm, tm_dtype(dtype), 5, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? FSR_OK : FSR_ERR_TENSORMAP;
+}
+
 // packed weights [rows][cin] (2-byte elements), box {64, box_rows}
 int make_w_map(CUtensorMap* tm, const void* ptr, int rows, int box_rows, int dtype, int cin = 64) {
   auto enc = get_encode_fn();
@@ -157,7 +172,7 @@ int g_fuse_res = -1;   // Generator.forward: 1 = bn2 + skip of block l is applie
 int fuse_res_mode() {
   if (g_fuse_res < 0) {
     const char* e = getenv("FSR_FUSE_RES");
-    g_fuse_res = (e && e[0] == '0') ? 0 : 1;
+    g_fuse_res = (e && e[0] == '1') ? 1 : 0;   // default OFF: measured 578 us vs 172 + 109 us unfused (profiles/r02)
   }
   return g_fuse_res;
 }
@@ -241,13 +256,15 @@ int launch_up_2cta(const void* x, const void* w_packed, ConvParams p, int dtype,
   int rc = make_act_map(&tmx, x, p.N, p.H, p.W, 64, Geo::kBoxW, Geo::kBoxH, dtype);
   if (rc) return rc;
   if ((rc = make_w_map(&tmw, w_packed, 9 * Cfg::kN, Cfg::kN / 2, dtype))) return rc;
+  CUtensorMap tmo;
+  if ((rc = make_ps_out_map(&tmo, p.out, p.N, p.H, p.W, dtype))) return rc;
   const int pairs = (p.num_tiles + 1) / 2;
   int clusters = num_sms() / 2;
   if (clusters > pairs) clusters = pairs;
   if (clusters < 1) clusters = 1;
   {
     LaunchScope scope(FSR_K_CONV_UP, st, 2.0 * p.N * p.H * p.W * 256.0 * 64 * 9);
-    kern<<<2 * clusters, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tmx, tmw, p);   // __cluster_dims__(2,1,1)
+    kern<<<2 * clusters, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tmx, tmw, tmo, p);   // __cluster_dims__(2,1,1)
   }
   return cuda_rc(cudaGetLastError());
 }
@@ -302,6 +319,12 @@ int conv_dispatch(const void* x, const void* w_packed, void* out, const float* b
       if (up_2cta_mode() && halo_mode()) { p.cout_total = 256; p.num_slices = 1; return launch_up_2cta<T>(x, w_packed, p, dtype, st); }
       p.cout_total = 256; p.num_slices = 2;
       return launch_conv_mode<128, EPI_PS_PRELU, T>(x, w_packed, 9 * 256, p, dtype, st);
+    }
+    case FSR_EPI_F32: {
+      if (cout % 64) return FSR_ERR_BAD_ARG;
+      p.cout_total = cout; p.num_slices = cout / 64; p.bias = nullptr;
+      if (!halo_mode()) return FSR_ERR_BAD_ARG;
+      return launch_conv<64, EPI_F32, T, true>(x, w_packed, 9 * cout, p, dtype, st);
     }
     case FSR_EPI_HEAD_TANH: {
       if (cout != 16 || out_u8 < 0 || out_u8 > 3) return FSR_ERR_BAD_ARG;   // padded head: 3 real + 13 zero rows
@@ -1199,6 +1222,71 @@ int fsr_crop_resize_aa(const uint8_t* cache, const int64_t* img_off, const int32
   cudaStream_t st = (cudaStream_t)stream;
   LaunchScope scope(FSR_K_NONE - 1, st);
   crop_resize_aa_kernel<<<dim3((unsigned)B, 3), 256, smem, st>>>(p);
+  return cuda_rc(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------ precise generator forward (precise.cuh)
+int fsr_split_f32(const float* x, void* hi, void* lo, size_t n_elems, void* stream) {
+  if (!x || !hi || !lo || n_elems % 8) return FSR_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  LaunchScope scope(FSR_K_NONE - 1, st);
+  split_f32_kernel<<<ew_blocks(n_elems / 8), 256, 0, st>>>(x, (__half*)hi, (__half*)lo, n_elems / 8);
+  return cuda_rc(cudaGetLastError());
+}
+
+int fsr_neck_conv3x3_f32(const float* x, const float* w, const float* bias, const float* alpha, float* out, int N, int H, int W,
+                         void* stream) {
+  if (!x || !w || !alpha || !out || N <= 0 || H <= 0 || W <= 0) return FSR_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t threads = (size_t)N * H * W * 2;
+  LaunchScope scope(FSR_K_NECK, st);
+  neck_conv3x3_f32_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(x, w, bias, alpha, out, N, H, W);
+  return cuda_rc(cudaGetLastError());
+}
+
+int fsr_in_stats_f32(const float* x, int64_t* stats, int N, int HW, void* stream) {
+  if (!x || !stats || N <= 0 || HW <= 0) return FSR_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  int bpi = (HW + 16 * 32 - 1) / (16 * 32);
+  const int cap = (num_sms() * 4 + N - 1) / N;
+  if (bpi > cap) bpi = cap;
+  if (bpi < 1) bpi = 1;
+  LaunchScope scope(FSR_K_NONE - 1, st);
+  in_stats_f32_kernel<<<dim3(bpi, N), 256, 0, st>>>(x, reinterpret_cast<long long*>(stats), HW);
+  return cuda_rc(cudaGetLastError());
+}
+
+int fsr_in_apply_f32(const float* x, const int64_t* stats, const float* residual, float* out, void* hi, void* lo,
+                     const float* alpha, int act, int N, int HW, float eps, void* stream) {
+  if (!x || !stats || !out || N <= 0 || HW <= 0 || (hi == nullptr) != (lo == nullptr)) return FSR_ERR_BAD_ARG;
+  if (act == FSR_ACT_PRELU && !alpha) return FSR_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  int bpi = (int)(((size_t)HW * 8 + 256 * 4 - 1) / (256 * 4));
+  const int cap = (num_sms() * 8 + N - 1) / N;
+  if (bpi > cap) bpi = cap;
+  if (bpi < 1) bpi = 1;
+  LaunchScope scope(FSR_K_IN_APPLY, st);
+  in_apply_f32_kernel<<<dim3(bpi, N), 256, 0, st>>>(x, reinterpret_cast<const long long*>(stats), residual, out, (__half*)hi, (__half*)lo,
+                                                     alpha, act, HW, eps);
+  return cuda_rc(cudaGetLastError());
+}
+
+int fsr_ps_prelu_f32(const float* conv, const float* bias_packed, const float* alpha, float* out, void* hi, void* lo, int N, int H,
+                     int W, void* stream) {
+  if (!conv || !bias_packed || !alpha || !out || N <= 0 || (hi == nullptr) != (lo == nullptr)) return FSR_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  LaunchScope scope(FSR_K_NONE - 1, st);
+  ps_prelu_f32_kernel<<<ew_blocks((size_t)N * H * W * 32), 256, 0, st>>>(conv, bias_packed, alpha, out, (__half*)hi, (__half*)lo, N, H, W);
+  return cuda_rc(cudaGetLastError());
+}
+
+int fsr_tanh_f32(float* pre, uint8_t* out_u8, int N, int HW, void* stream) {
+  if (!pre || N <= 0 || HW <= 0) return FSR_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n = (size_t)N * 3 * HW;
+  LaunchScope scope(FSR_K_NONE - 1, st);
+  if (out_u8) tanh_u8_kernel<<<ew_blocks(n), 256, 0, st>>>(pre, out_u8, N, HW);
+  else tanh_f32_kernel<<<ew_blocks(n), 256, 0, st>>>(pre, n);
   return cuda_rc(cudaGetLastError());
 }
 

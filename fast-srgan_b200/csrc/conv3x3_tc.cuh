@@ -36,6 +36,7 @@ enum ConvEpilogue : int {
   EPI_BIAS_ACT = 1,    // store act(conv + bias) NHWC
   EPI_PS_PRELU = 2,    // bias + PReLU + PixelShuffle(2) scatter: out[N,2H,2W,64]
   EPI_HEAD_TANH = 3,   // NS=16 (3 real channels): tanh(conv + bias) -> fp32 NCHW or uint8 NHWC
+  EPI_F32 = 4,         // precise mode: out fp32 NHWC [N,H,W,cout_total] = (act ? out : 0) + conv  (store | accumulate)
 };
 
 enum ActMode : int { ACT_NONE = 0, ACT_RELU = 1, ACT_LRELU = 2, ACT_PRELU = 3 };
@@ -529,8 +530,27 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
               __syncwarp();
               if (lane == 0) mbar_arrive(&tempty_bar[acc]);
             }
+            if constexpr (EPI == EPI_F32) {
+              // precise mode (precise.cuh): the fp32 accumulators go to HBM as they are; the second and third operand
+              // products of a split conv (a_lo*w_hi, a_hi*w_lo) are added onto the first (p.act = 1)
+              if (pvalid) {
+                float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) +
+                                                        ((size_t)(n * p.H + y) * p.W + x) * p.cout_total + slice * NS + chunk * 64);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
+                for (int i = 0; i < 16; ++i) {
+                  const uint32_t* r = i < 8 ? r0 : r1;
+                  const int j = (i & 7) * 4;
+                  float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                  if (p.act) {
+                    const float4 o = dst[i];
+                    v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+                  }
+                  dst[i] = v;
+                }
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 16 && EPI != EPI_F32; ++i) {
               float a0 = __uint_as_float(r0[2 * i]), a1 = __uint_as_float(r0[2 * i + 1]);
               float b0 = __uint_as_float(r1[2 * i]), b1 = __uint_as_float(r1[2 * i + 1]);
               if constexpr (EPI != EPI_RAW_STATS) {
@@ -548,6 +568,7 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
               pk[16 + i] = Cvt<T>::pack2(b0, b1);
             }
           }
+          if constexpr (EPI == EPI_F32) continue;
           const int col0 = slice * NS + chunk * 64;   // first GEMM column of this chunk
 
           // ---- registers -> swizzled smem (row = pixel, 8 x 16B chunks) -> global

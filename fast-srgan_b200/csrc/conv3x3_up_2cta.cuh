@@ -28,8 +28,8 @@ struct Up2Cfg {
   static constexpr int kN = 256;                         // GEMM columns of the pair's MMA
   static constexpr int kWBytes = 9 * (kN / 2) * 128;     // this CTA's half of the weights: 147456
   static constexpr int kStages = 2;
-  static constexpr int kEpiWarps = 4;
-  static constexpr int kThreads = 64 + 32 * kEpiWarps;   // 192
+  static constexpr int kEpiWarps = 8;                    // two per SM sub-partition (a lone warp cannot hide its own ALU latency)
+  static constexpr int kThreads = 64 + 32 * kEpiWarps;   // 320
   static constexpr int kStagingBytes = kEpiWarps * 4096;
   static constexpr int kTmemCols = 512;                  // 2 accumulators x 256 columns
   static constexpr int kSmemBytes = kWBytes + kStages * Geo::kStageBytes + kStagingBytes + 2048 /*barriers + bias*/ + 1024 /*align*/;
@@ -52,10 +52,13 @@ FSR_DEVINL uint32_t mapa_cluster(uint32_t smem_addr, uint32_t rank) {
   return r;
 }
 FSR_DEVINL void mbar_arrive_expect_tx_cluster(uint32_t cluster_bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_bar), "r"(bytes) : "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_bar), "r"(bytes) : "memory");
 }
 FSR_DEVINL void mbar_arrive_cluster(uint32_t cluster_bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+  // default semantics like CUTLASS' ClusterBarrier::arrive(cta_id): the TMEM reads that must precede it are ordered by
+  // tcgen05.wait::ld + tcgen05.fence::before_thread_sync, not by a memory fence (the .release.cluster form costs a
+  // MEMBAR.ALL.GPU + ERRBAR per arrive: 13 % of all stall samples in profiles/r02/ncu_full_up_2cta_v1.md)
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 // TMA loads whose completion lands on a barrier that may live in the peer CTA (cluster address)
 FSR_DEVINL void tma_load_2d_pair(void* dst, const CUtensorMap* m, uint32_t cluster_bar, int c0, int c1) {
@@ -97,7 +100,8 @@ FSR_DEVINL void tmem_dealloc_pair(uint32_t taddr) {
 
 template <typename T>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Up2Cfg::kThreads, 1)
-conv3x3_up_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w, const ConvParams p) {
+conv3x3_up_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
+                       const __grid_constant__ CUtensorMap tm_out, const ConvParams p) {
   using Cfg = Up2Cfg;
   using Geo = Cfg::Geo;
   constexpr int TH = Geo::TH, TW = Geo::TW;
@@ -131,9 +135,10 @@ conv3x3_up_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_x);
     tma_prefetch_desc(&tm_w);
+    tma_prefetch_desc(&tm_out);
     for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&full_bar[i], 2); mbar_init(&empty_bar[i], 1); }
     mbar_init(w_bar, 2);
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 2 * Cfg::kEpiWarps); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 2 * Cfg::kEpiWarps); }   // 8 warps x 2 CTAs
     fence_mbar_init();
     fence_proxy_async();
   }
@@ -216,8 +221,13 @@ conv3x3_up_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
     }
   } else {
     // =============================== epilogue warps (both CTAs, own 128 rows x 256 columns) ===============================
+    // 8 warps: warp (q, g) drains TMEM lane quarter q = warp % 4 of column half g (GEMM column blocks 2g, 2g+1 = the
+    // PixelShuffle positions (i, j) = (g, 0), (g, 1)).  Each 64-column block goes registers -> swizzled smem -> ONE TMA store:
+    // the output tensor map (host: make_ps_out_map) is [N][H][i:2][W][(j,c):128], so the 32 pixels x 64 channels of a warp at
+    // sub-position (i, j) are the box {64, 8, 1, 4, 1} at {j*64, x0, i, y0 + 4q, n}; image edges are clipped by the hardware.
     const int ew = warp - 2;
     const int q = warp & 3;
+    const int g = ew >> 2;
     const uint32_t stg = smem_u32(smem_stg + ew * 4096);
     const float slope = __ldg(p.alpha);
     int it = 0;
@@ -230,63 +240,50 @@ conv3x3_up_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
       const int rem = t - n * tiles_per_img;
       const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
       const int x0 = tx * TW, y0 = ty * TH;
-      const bool interior = (y0 + TH <= p.H) && (x0 + TW <= p.W);
       mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::kN;
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::kN + g * 128;
 #pragma unroll 1
-      for (int chunk = 0; chunk < Cfg::kN / 64; ++chunk) {
+      for (int c2 = 0; c2 < 2; ++c2) {
+        const int chunk = 2 * g + c2;             // GEMM column block = 2*i + j
         uint32_t pk[32];
         {
           uint32_t r0[32], r1[32];
-          tmem_ld32(t_row + chunk * 64, r0);
-          tmem_ld32(t_row + chunk * 64 + 32, r1);
+          tmem_ld32(t_row + c2 * 64, r0);
+          tmem_ld32(t_row + c2 * 64 + 32, r1);
           tmem_ld_wait();
-          if (chunk == Cfg::kN / 64 - 1) {
+          if (c2 == 1) {                          // this warp's TMEM reads of the accumulator are done
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(mapa_cluster(smem_u32(&tempty_bar[acc]), 0));
           }
+          const float* bs = smem_bias + chunk * 64;
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            float a0 = __uint_as_float(r0[2 * i]) + smem_bias[chunk * 64 + 2 * i];
-            float a1 = __uint_as_float(r0[2 * i + 1]) + smem_bias[chunk * 64 + 2 * i + 1];
-            float b0 = __uint_as_float(r1[2 * i]) + smem_bias[chunk * 64 + 32 + 2 * i];
-            float b1 = __uint_as_float(r1[2 * i + 1]) + smem_bias[chunk * 64 + 32 + 2 * i + 1];
+            float a0 = __uint_as_float(r0[2 * i]) + bs[2 * i];
+            float a1 = __uint_as_float(r0[2 * i + 1]) + bs[2 * i + 1];
+            float b0 = __uint_as_float(r1[2 * i]) + bs[32 + 2 * i];
+            float b1 = __uint_as_float(r1[2 * i + 1]) + bs[32 + 2 * i + 1];
             a0 = a0 >= 0.f ? a0 : a0 * slope; a1 = a1 >= 0.f ? a1 : a1 * slope;
             b0 = b0 >= 0.f ? b0 : b0 * slope; b1 = b1 >= 0.f ? b1 : b1 * slope;
             pk[i] = Cvt<T>::pack2(a0, a1);
             pk[16 + i] = Cvt<T>::pack2(b0, b1);
           }
         }
+        if (lane == 0) tma_store_wait_read();     // the previous TMA store has finished reading this warp's buffer
         __syncwarp();
 #pragma unroll
         for (int k = 0; k < 8; ++k)
           st_shared_v4(stg + lane * 128 + ((k ^ (lane & 7)) << 4), pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
+        fence_proxy_async();                      // generic-proxy writes -> visible to the TMA (async proxy)
         __syncwarp();
-        uint4 val[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int rrow = j * 4 + (lane >> 3);
-          val[j] = ld_shared_v4(stg + rrow * 128 + (((lane & 7) ^ (rrow & 7)) << 4));
+        if (lane == 0 && tile_valid) {
+          tma_store_5d(&tm_out, smem_stg + ew * 4096, (chunk & 1) * 64, x0, chunk >> 1, y0 + q * (32 / TW), n);
+          tma_store_commit();
         }
-        if (tile_valid) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int rrow = j * 4 + (lane >> 3);
-            const int mm = q * 32 + rrow;
-            const int py = y0 + mm / TW, px = x0 + mm % TW;
-            if (interior || (py < p.H && px < p.W)) {
-              // GEMM column block `chunk` = 2*i + j of PixelShuffle(2) (packed order)
-              const int oy = 2 * py + (chunk >> 1), ox = 2 * px + (chunk & 1);
-              T* dst = reinterpret_cast<T*>(p.out) + ((size_t)(n * 2 * p.H + oy) * (2 * p.W) + ox) * 64;
-              *reinterpret_cast<uint4*>(dst + (lane & 7) * 8) = val[j];
-            }
-          }
-        }
-        __syncwarp();
       }
     }
+    if (lane == 0) tma_store_wait_all();
   }
 
   tc_fence_before();

@@ -91,6 +91,8 @@ class Generator(torch.nn.Module):
     """Reference model.py:72-117 on B200 kernels.
 
     forward(x) : fp32 NCHW [N,3,H,W] in [-1,1] -> fp32 NCHW [N,3,4H,4W]   (model.py:112-117)
+    compute_dtype: torch.float16 (default: 1e-3 of the reference on random-init weights), torch.bfloat16 (1.5e-2), or
+    torch.float32 = precise mode (fp32 storage, split fp16 operands: 1e-3 on the reference's shipped checkpoint too).
     super_resolve_u8(img) : uint8 NHWC -> uint8 NHWC, the inference.py:48-56 pipeline fused into
     the neck load and the head store.
     """
@@ -110,6 +112,7 @@ class Generator(torch.nn.Module):
         self._packed: Dict[str, torch.Tensor] = {}
         self._packed_key = None
         self._ws = None
+        self._precise = None
 
     # -- checkpoints saved from torch.compile'd modules carry `_orig_mod.` (inference.py:30-33)
     def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
@@ -232,6 +235,12 @@ class Generator(torch.nn.Module):
             raise RuntimeError(f"n_layers > {L.FSR_MAX_LAYERS} not supported")
         if self.padded_filters > 512:
             raise RuntimeError("generator.n_filters > 512 is not supported by this build")
+        if self.compute_dtype == torch.float32:
+            # precise mode: fp32 storage, fp16 hi+lo split operands on the tensor cores (precise.py)
+            if self._precise is None:
+                from .precise import PreciseGenerator
+                self._precise = PreciseGenerator(self)
+            return self._precise.forward(x, out, in_u8, out_u8)
         if self.padded_filters != 64:
             return self._forward_wide(x, out, in_u8, out_u8)
         P = self._params_struct()

@@ -33,7 +33,8 @@ enum {
   FSR_EPI_RAW_STATS = 0, /* raw conv out + InstanceNorm sum/sumsq   (model.py:54-55,64-65,93-94,131-132) */
   FSR_EPI_BIAS_ACT = 1,  /* act(conv + bias)                         (VGG conv+ReLU, model.py:8)         */
   FSR_EPI_PS_PRELU = 2,  /* bias + PixelShuffle(2) + PReLU           (model.py:39-40)                    */
-  FSR_EPI_HEAD_TANH = 3  /* bias + tanh -> fp32 NCHW | uint8 NHWC    (model.py:102-110, inference.py:54-56) */
+  FSR_EPI_HEAD_TANH = 3, /* bias + tanh -> fp32 NCHW | uint8 NHWC    (model.py:102-110, inference.py:54-56) */
+  FSR_EPI_F32 = 4        /* precise mode: out fp32 NHWC [N,H,W,cout] = conv (act = 0) or out + conv (act = 1); see below */
 };
 enum { FSR_ACT_NONE = 0, FSR_ACT_RELU = 1, FSR_ACT_LRELU = 2, FSR_ACT_PRELU = 3 };
 
@@ -287,6 +288,28 @@ int fsr_set_gen_ws(int on);
  * (mma.sync m16n8k16, fp32 operand split hi+lo: fp32-input accuracy); 0: the CUDA-core kernels (A/B and tests);
  * -1: environment default (FSR_SMALL_MMA). */
 int fsr_set_small_mma(int on);
+
+/* ---- PRECISE generator forward (Generator(compute_dtype=torch.float32); model.py:112-117 at ~fp32 accuracy).
+ * The shipped checkpoint needs more than 16-bit operands for north_star's 1e-3 (fp16 measures 3.4e-3):
+ * activations are stored fp32 NHWC and split a = a_hi + a_lo into two fp16 planes (fsr_split_f32 or the hi/lo outputs
+ * below), weights likewise on the host, and every conv is THREE fsr_conv3x3_c64(..., FSR_EPI_F32) launches
+ * (a_hi*w_hi store; a_lo*w_hi, a_hi*w_lo accumulate) into one fp32 NHWC buffer; the 64->3 head is three
+ * fsr_conv3x3_c64(..., FSR_EPI_HEAD_TANH, out_u8 = 2 | 3 | 3) launches followed by fsr_tanh_f32. */
+int fsr_split_f32(const float* x, void* hi, void* lo, size_t n_elems, void* stream);           /* n_elems % 8 == 0 */
+/* neck (model.py:75-78) in fp32 arithmetic: x fp32 NCHW [N,3,H,W] -> out fp32 NHWC [N,H,W,64] = PReLU(conv + bias) */
+int fsr_neck_conv3x3_f32(const float* x, const float* w, const float* bias, const float* alpha, float* out, int N, int H, int W,
+                         void* stream);
+/* InstanceNorm statistics (model.py:55,65,94) of an fp32 NHWC tensor [N,HW,64]: stats [N,64,2] int64 fixed point +=, caller zeroes */
+int fsr_in_stats_f32(const float* x, int64_t* stats, int N, int HW, void* stream);
+/* out = act((x - mean) * rstd) (+ residual), fp32 NHWC [N,HW,64]; hi/lo (both or neither): fp16 split planes of out */
+int fsr_in_apply_f32(const float* x, const int64_t* stats, const float* residual, float* out, void* hi, void* lo,
+                     const float* alpha, int act, int N, int HW, float eps, void* stream);
+/* UpSamplingBlock tail (model.py:39-40): conv fp32 [N,H,W,256] (ps_perm column order) + bias_packed -> PixelShuffle(2) -> PReLU
+ * -> out fp32 [N,2H,2W,64] (+ hi/lo planes) */
+int fsr_ps_prelu_f32(const float* conv, const float* bias_packed, const float* alpha, float* out, void* hi, void* lo, int N, int H,
+                     int W, void* stream);
+/* tanh of the head's pre-activation fp32 NCHW [N,3,HW]: in place (out_u8 = NULL, model.py:109) or -> uint8 NHWC (inference.py:54-56) */
+int fsr_tanh_f32(float* pre, uint8_t* out_u8, int N, int HW, void* stream);
 
 /* ---- data-parallel exchange of the GAN step (the reference has no collective: trainer.py:180-181 and
  * :195-196 run on one device).  One process per GPU; the flat fp32 gradient buffer of a network is summed over ranks
