@@ -36,7 +36,9 @@ _SIGS = {
     "fsr_conv3x3_c64": (_i, [_vp, _vp, _vp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _f, _i, _i, _vp]),
     "fsr_conv3x3_gen": (_i, [_vp, _vp, _vp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp]),
     "fsr_pack_conv3x3_weight_t": (_i, [_fp, _vp, _i, _i, _i, _i, _i, _fp, _i, _vp]),
-    "fsr_conv3x3_wgrad": (_i, [_vp, _vp, _fp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "fsr_wgrad_workspace_bytes": (_sz, []),
+    "fsr_conv3x3_wgrad": (_i, [_vp, _vp, _fp, _i, _i, _i, _i, _i, _i, _i, _vp, _sz, _i, _vp]),
+    "fsr_conv3x3_wgrad_grouped": (_i, [_vp, _vp, _vp, _i, C.c_longlong, C.c_longlong, _i, _i, _i, _i, _i, _vp, _sz, _i, _vp]),
     "fsr_parity_layout": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "fsr_maxpool2": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "fsr_maxpool2_relu_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),

@@ -186,6 +186,15 @@ int up_2cta_mode() {
   return g_up_2cta;
 }
 
+int g_in_bwd_fused = -1;   // InstanceNorm backward: 1 = single-launch kernel for planes <= 64x64 (train_kernels.cuh)
+int in_bwd_fused_mode() {
+  if (g_in_bwd_fused < 0) {
+    const char* e = getenv("FSR_IN_BWD_FUSED");
+    g_in_bwd_fused = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_in_bwd_fused;
+}
+
 int g_small_mma = -1;   // 3-channel-sided convs (neck / wgrad_c3): 1 = mma.sync tensor-core kernels (small_mma.cuh), 0 = CUDA cores
 int small_mma_mode() {
   if (g_small_mma < 0) {
@@ -470,22 +479,42 @@ int gen_dispatch(const void* x, const void* w_packed, void* out, const float* bi
 
 
 // ------------------------------------------------------------------ weight gradient (conv3x3_wgrad.cuh)
+// 5-D activation map [groups][N][H][W][C] (2-byte elements), box {64, bw, bh, 1, 1}; img / group strides in elements
+int make_act_map5(CUtensorMap* tm, const void* ptr, int G, int N, int H, int W, int C, long long img_stride, long long grp_stride,
+                  int bw, int bh, int dtype) {
+  auto enc = get_encode_fn();
+  if (!enc) return FSR_ERR_NO_DRIVER;
+  cuuint64_t gdim[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N, (cuuint64_t)G};
+  cuuint64_t gstr[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)img_stride * 2, (cuuint64_t)(G > 1 ? grp_stride : img_stride * N) * 2};
+  cuuint32_t box[5] = {64, (cuuint32_t)bw, (cuuint32_t)bh, 1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(tm, tm_dtype(dtype), 5, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? FSR_OK : FSR_ERR_TENSORMAP;
+}
+
+size_t wgrad_workspace_bytes() { return (size_t)num_sms() * 5 * 128 * 64 * sizeof(float); }
+
+// groups problems of identical shape: x / dy point at group 0, consecutive groups are x_grp_stride / dy_grp_stride elements
+// apart; dw[g] = fp32 OIHW gradient of group g (accumulated).
 template <typename T>
-int wgrad_dispatch(const void* x, const void* dy, float* dw, int N, int H, int W, int cin, int cout, int stride,
-                   int ps_perm, int dtype, cudaStream_t st) {
-  if (N <= 0 || H <= 0 || W <= 0 || cin % 64 || cout % 64) return FSR_ERR_BAD_SHAPE;
+int wgrad_dispatch(const void* x, const void* dy, float* const* dw, int groups, long long x_grp_stride, long long dy_grp_stride,
+                   int N, int H, int W, int cin, int cout, int stride, int ps_perm, float* workspace, size_t ws_bytes, int dtype,
+                   cudaStream_t st) {
+  if (N <= 0 || H <= 0 || W <= 0 || cin % 64 || cout % 64 || groups < 1 || groups > kWgradMaxGroups) return FSR_ERR_BAD_SHAPE;
   if (stride != 1 && stride != 2) return FSR_ERR_BAD_ARG;
-  if (stride == 2 && ((H | W) & 1)) return FSR_ERR_BAD_SHAPE;
+  if (stride == 2 && (((H | W) & 1) || groups != 1)) return FSR_ERR_BAD_SHAPE;
+  if (!workspace || ws_bytes < wgrad_workspace_bytes()) return FSR_ERR_WORKSPACE;
   WgradParams p{};
   const int Ho = H / stride, Wo = W / stride;
-  p.N = N; p.Ho = Ho; p.Wo = Wo; p.cin = cin; p.cout = cout; p.dw = dw; p.ps_perm = ps_perm;
+  p.N = N; p.Ho = Ho; p.Wo = Wo; p.cin = cin; p.cout = cout; p.partial = workspace; p.groups = groups; p.ps_perm = ps_perm;
   p.tiles_x = (Wo + 7) / 8; p.tiles_y = (Ho + 15) / 16; p.num_tiles = N * p.tiles_x * p.tiles_y;
   CUtensorMap mx[4], mdy;
   int rc;
-  if ((rc = make_act_map(&mdy, dy, N, Ho, Wo, cout, 8, 16, dtype))) return rc;
+  if ((rc = make_act_map5(&mdy, dy, groups, N, Ho, Wo, cout, (long long)Ho * Wo * cout, dy_grp_stride, 8, 16, dtype))) return rc;
   if (stride == 1) {
     p.nplanes = 1; p.box_w = 10; p.box_rows = 180; p.plane_bytes = 23552; p.dx = -1; p.dy = -1;
-    if ((rc = make_act_map(&mx[0], x, N, H, W, cin, 10, 18, dtype))) return rc;
+    if ((rc = make_act_map5(&mx[0], x, groups, N, H, W, cin, (long long)H * W * cin, x_grp_stride, 10, 18, dtype))) return rc;
     mx[1] = mx[2] = mx[3] = mx[0];
     for (int t = 0; t < 9; ++t) { p.tap_row[t] = (t / 3) * 10 + (t % 3); p.tap_id[t] = t; }
   } else {
@@ -493,7 +522,7 @@ int wgrad_dispatch(const void* x, const void* dy, float* dw, int N, int H, int W
     p.nplanes = 4; p.box_w = 9; p.box_rows = 153; p.plane_bytes = 20480; p.dx = -1; p.dy = -1;
     const long long plane = (long long)Ho * Wo * cin;
     for (int pl = 0; pl < 4; ++pl)
-      if ((rc = make_act_map_strided(&mx[pl], (const uint8_t*)x + (size_t)pl * plane * 2, N, Ho, Wo, cin, 4 * plane, 9, 17, dtype)))
+      if ((rc = make_act_map5(&mx[pl], (const uint8_t*)x + (size_t)pl * plane * 2, 1, N, Ho, Wo, cin, 4 * plane, 0, 9, 17, dtype)))
         return rc;
     // order taps by their absolute row inside the stage so that pair distances (LBO) are non-negative
     int n = 0;
@@ -505,7 +534,6 @@ int wgrad_dispatch(const void* x, const void* dy, float* dw, int N, int H, int W
             p.tap_id[n] = r * 3 + s2;
             ++n;
           }
-    // within a plane rows may be unordered (e.g. plane 3: taps (0,0),(0,2),(2,0),(2,2) -> rows 0,1,9,10): sorted by construction
   }
   p.tap_row[9] = p.tap_row[8]; p.tap_id[9] = p.tap_id[8];
   auto kern = conv3x3_wgrad_kernel<T>;
@@ -514,13 +542,26 @@ int wgrad_dispatch(const void* x, const void* dy, float* dw, int N, int H, int W
     FSR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, WgradCfg::kSmemBytes));
     attr_done = true;
   }
-  const int npairs = (cin / 64) * (cout / 64);
-  int cpp = num_sms() / npairs;
+  const int npairs_all = groups * (cin / 64) * (cout / 64);
+  int cpp = num_sms() / npairs_all;          // split-K factor: CTAs per (group, cin chunk, cout slice)
   if (cpp < 1) cpp = 1;
   if (cpp > p.num_tiles) cpp = p.num_tiles;
+  // more pairs than SMs (512x512: 64 pairs x ...): the partial slots are indexed by blockIdx.x < npairs_all * cpp, and the
+  // workspace holds num_sms slots -> run the pairs in waves of at most num_sms CTAs
+  WgradReduceParams rp{};
+  rp.partial = workspace; rp.cin = cin; rp.cout = cout; rp.ps_perm = ps_perm;
+  for (int g = 0; g < groups; ++g) rp.dw[g] = dw[g];
+  for (int t = 0; t < 9; ++t) rp.slot_of_tap[p.tap_id[t]] = t;
+  if (npairs_all * cpp > num_sms()) return FSR_ERR_BAD_SHAPE;   // cannot happen for cin, cout <= 512 (64 pairs)
+  rp.npairs_all = npairs_all; rp.ctas_per_pair = cpp;
   {
-    LaunchScope scope(FSR_K_CONV_WGRAD, st, 2.0 * N * Ho * Wo * (double)cin * cout * 9);
-    kern<<<npairs * cpp, WgradCfg::kThreads, WgradCfg::kSmemBytes, st>>>(mx[0], mx[1], mx[2], mx[3], mdy, p);
+    LaunchScope scope(FSR_K_CONV_WGRAD, st, 2.0 * groups * N * Ho * Wo * (double)cin * cout * 9);
+    kern<<<npairs_all * cpp, WgradCfg::kThreads, WgradCfg::kSmemBytes, st>>>(mx[0], mx[1], mx[2], mx[3], mdy, p);
+  }
+  FSR_CUDA(cudaGetLastError());
+  {
+    LaunchScope scope(FSR_K_NONE - 1, st);
+    wgrad_reduce_kernel<<<dim3(npairs_all, 8), 256, 0, st>>>(rp);
   }
   return cuda_rc(cudaGetLastError());
 }
@@ -962,12 +1003,27 @@ int fsr_pack_conv3x3_weight_t(const float* w_oihw, void* w_packed, int cout, int
   return cuda_rc(cudaGetLastError());
 }
 
+size_t fsr_wgrad_workspace_bytes(void) { return wgrad_workspace_bytes(); }
+
 int fsr_conv3x3_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int cin, int cout, int stride,
-                      int ps_perm, int dtype, void* stream) {
+                      int ps_perm, void* workspace, size_t ws_bytes, int dtype, void* stream) {
   if (!x || !dy || !dw) return FSR_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == FSR_BF16) return wgrad_dispatch<__nv_bfloat16>(x, dy, dw, N, H, W, cin, cout, stride, ps_perm, dtype, st);
-  return wgrad_dispatch<__half>(x, dy, dw, N, H, W, cin, cout, stride, ps_perm, dtype, st);
+  float* dws[1] = {dw};
+  if (dtype == FSR_BF16) return wgrad_dispatch<__nv_bfloat16>(x, dy, dws, 1, 0, 0, N, H, W, cin, cout, stride, ps_perm, (float*)workspace, ws_bytes, dtype, st);
+  return wgrad_dispatch<__half>(x, dy, dws, 1, 0, 0, N, H, W, cin, cout, stride, ps_perm, (float*)workspace, ws_bytes, dtype, st);
+}
+
+int fsr_conv3x3_wgrad_grouped(const void* x_arena, const void* dy_arena, float* const* dw_list_host, int groups,
+                              long long x_group_stride, long long dy_group_stride, int N, int H, int W, int cin, int cout,
+                              void* workspace, size_t ws_bytes, int dtype, void* stream) {
+  if (!x_arena || !dy_arena || !dw_list_host) return FSR_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == FSR_BF16)
+    return wgrad_dispatch<__nv_bfloat16>(x_arena, dy_arena, dw_list_host, groups, x_group_stride, dy_group_stride, N, H, W, cin, cout, 1, 0,
+                                         (float*)workspace, ws_bytes, dtype, st);
+  return wgrad_dispatch<__half>(x_arena, dy_arena, dw_list_host, groups, x_group_stride, dy_group_stride, N, H, W, cin, cout, 1, 0,
+                                (float*)workspace, ws_bytes, dtype, st);
 }
 
 int fsr_parity_layout(const void* in, void* out, int N, int H, int W, int C, int to_parity, int dtype, void* stream) {
@@ -1062,10 +1118,18 @@ int fsr_smooth_l1(const void* a, const void* b, size_t n, float* loss_acc, void*
 
 int fsr_instnorm_bwd(const void* raw, const int64_t* stats, const void* dy, float* red, void* draw, const float* alpha,
                      float* dalpha, int N, int HW, int C, int act, float slope, float eps, int dtype, void* stream) {
-  if (!raw || !stats || !dy || !red || !draw || C % 8 || 256 % (C / 8)) return FSR_ERR_BAD_ARG;
+  if (!raw || !stats || !dy || !draw || C % 8 || 256 % (C / 8)) return FSR_ERR_BAD_ARG;
   if (act == FSR_ACT_PRELU && !alpha) return FSR_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   InBwdParams p{raw, reinterpret_cast<const long long*>(stats), dy, red, draw, alpha, dalpha, slope, act, HW, C, eps};
+  if (C % 64 == 0 && HW <= 4096 && in_bwd_fused_mode()) {
+    // training shapes: one launch, the per-(n,c) sums stay inside the block (no `red` scratch, no memset, no atomics)
+    LaunchScope scope(FSR_K_NONE - 1, st);
+    FSR_T((instnorm_bwd_fused_kernel<__half><<<dim3(C / 64, N), 256, 0, st>>>(p)),
+          (instnorm_bwd_fused_kernel<__nv_bfloat16><<<dim3(C / 64, N), 256, 0, st>>>(p)));
+    return cuda_rc(cudaGetLastError());
+  }
+  if (!red) return FSR_ERR_BAD_ARG;
   const size_t nvec = (size_t)HW * (C / 8);
   int bpi = (int)((nvec + 256 * 8 - 1) / (256 * 8));
   const int cap = (num_sms() * 4 + N - 1) / N;

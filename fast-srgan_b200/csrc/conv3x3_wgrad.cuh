@@ -11,8 +11,18 @@
 // (M = 128 = 2 taps x 64 input channels): the second 64-row block of the A descriptor starts LBO bytes
 // after the first = the distance between the two shifted views of the same halo tile.  9 taps = 5 pairs
 // (the last pair duplicates tap 8) -> 5 accumulators [128 x 64] fp32 in TMEM (320 columns) that live for
-// the CTA's whole pixel range; one atomicAdd epilogue into the fp32 OIHW gradient at the end (split-K).
+// the CTA's whole pixel range (split-K over the CTAs of a (cin chunk, cout slice) pair).
 // Out-of-image pixels need no masking: TMA zero-fills both operands.
+//
+// Two stages, no atomics (round 2): every CTA stores its partial [5][128][64] fp32 tile to a workspace slot with
+// coalesced 256-byte rows; wgrad_reduce_kernel then sums the partials of each pair IN FIXED ORDER and adds the
+// result into the fp32 OIHW gradient through a shared-memory transpose (576 contiguous floats per output channel).
+// Round 1's epilogue issued 40960 scattered fp32 atomicAdds per CTA: ~50 us per launch whatever the layer size
+// (the 17 generator layers: 0.17 GFLOP each, 50 us each) and run-to-run different sums.  The weight gradient is now
+// bitwise reproducible.
+// GROUPED form: `groups` independent problems of identical shape (the generator's 17 64->64 convs) run as ONE
+// launch - their activations / output gradients sit in two arenas, addressed through the outermost (5th) tensor-map
+// dimension, and the work item becomes (group, pair, tile range).
 #pragma once
 #include "conv3x3_tc.cuh"
 
@@ -28,8 +38,20 @@ struct WgradParams {
   int dx, dy;               // X box origin relative to the tile
   int tap_row[10];          // absolute first row (pixel) of tap t's view inside the stage's X region; [9] = dup of [8]
   int tap_id[10];           // r*3+s of the tap
-  float* dw;                // fp32 OIHW [cout][cin][3][3], accumulated (+=)
+  float* partial;           // workspace: [gridDim.x][5][128][64] fp32, one slot per CTA
+  int groups;               // independent problems stacked along the 5th tensor-map dimension
   int ps_perm;              // dY columns are in pixel-shuffle-permuted order (UpSamplingBlock convs)
+};
+
+constexpr int kWgradMaxGroups = 40;
+struct WgradReduceParams {
+  const float* partial;     // [grid][5][128][64]
+  float* dw[kWgradMaxGroups];   // per group: fp32 OIHW [cout][cin][3][3], accumulated (+=)
+  int cin, cout;
+  int npairs_all;           // groups * (cin/64) * (cout/64): partial slot of split c of pair q = q + c * npairs_all
+  int ctas_per_pair;
+  int slot_of_tap[9];       // accumulator slot (2*pr + half) holding tap t
+  int ps_perm;
 };
 
 struct WgradCfg {
@@ -62,9 +84,11 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_con
   // work item = (input-channel chunk kc, output-channel slice) pair; the CTAs of a pair split the pixel tiles
   const int KC = p.cin >> 6, NSL = p.cout >> 6;
   const int npairs = KC * NSL;
-  const int pair = blockIdx.x % npairs;
-  const int cta_in_pair = blockIdx.x / npairs;
-  const int ctas_per_pair = gridDim.x / npairs;
+  const int npairs_all = npairs * p.groups;
+  const int pair_all = blockIdx.x % npairs_all;
+  const int grp = pair_all / npairs, pair = pair_all % npairs;
+  const int cta_in_pair = blockIdx.x / npairs_all;
+  const int ctas_per_pair = gridDim.x / npairs_all;
   const int kc = pair / NSL, sl = pair % NSL;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
   const int t_begin = (int)(((long long)cta_in_pair * p.num_tiles) / ctas_per_pair);
@@ -98,9 +122,9 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_con
         mbar_arrive_expect_tx(&full_bar[stage], p.nplanes * p.box_rows * 128 + Cfg::kDyBytes);
         for (int pl = 0; pl < p.nplanes; ++pl) {
           const CUtensorMap* tm = pl == 0 ? &tm_x0 : pl == 1 ? &tm_x1 : pl == 2 ? &tm_x2 : &tm_x3;
-          tma_load_4d(sx + pl * p.plane_bytes, tm, &full_bar[stage], kc * 64, x0 + p.dx, y0 + p.dy, n);
+          tma_load_5d(sx + pl * p.plane_bytes, tm, &full_bar[stage], kc * 64, x0 + p.dx, y0 + p.dy, n, grp);
         }
-        tma_load_4d(sx + Cfg::kXBytes, &tm_dy, &full_bar[stage], sl * 64, x0, y0, n);
+        tma_load_5d(sx + Cfg::kXBytes, &tm_dy, &full_bar[stage], sl * 64, x0, y0, n, grp);
       }
       __syncwarp();
       if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
@@ -141,36 +165,67 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_con
     if (elect_one()) umma_commit(done_bar);
     __syncwarp();
   } else {
-    // =============================== epilogue: TMEM -> atomicAdd into fp32 OIHW ===============================
+    // =============================== epilogue: TMEM -> this CTA's partial slot (coalesced rows, no atomics)
     const int q = warp & 3;
     const int m = q * 32 + lane;          // accumulator row: (tap within pair) * 64 + local input channel
-    const int half = m >> 6, ci = kc * 64 + (m & 63);
+    float4* dst = reinterpret_cast<float4*>(p.partial + ((size_t)blockIdx.x * 5 * 128 + m) * 64);
     if (t_end > t_begin) {
       mbar_wait(done_bar, 0);
       tc_fence_after();
+    }
 #pragma unroll 1
-      for (int pr = 0; pr < 5; ++pr) {
-        uint32_t r0[32], r1[32];
+    for (int pr = 0; pr < 5; ++pr) {
+      uint32_t r0[32], r1[32];
+      if (t_end > t_begin) {
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + pr * 64;
         tmem_ld32(t_row, r0);
         tmem_ld32(t_row + 32, r1);
         tmem_ld_wait();
-        if (pr == 4 && half == 1) continue;              // duplicate of tap 8
-        const int tap = p.tap_id[2 * pr + half];
+      } else {                             // more CTAs than tiles: this slot still takes part in the fixed-order sum
 #pragma unroll
-        for (int j = 0; j < 64; ++j) {
-          const int col = sl * 64 + j;                    // GEMM column = dY channel
-          int co = col;
-          if (p.ps_perm) { const int cq = p.cout >> 2; co = 4 * (col % cq) + col / cq; }
-          const float v = __uint_as_float(j < 32 ? r0[j] : r1[j - 32]);
-          atomicAdd(p.dw + ((size_t)co * p.cin + ci) * 9 + tap, v);
-        }
+        for (int j = 0; j < 32; ++j) { r0[j] = 0u; r1[j] = 0u; }
+      }
+      float4* d = dst + (size_t)pr * 128 * 16;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        d[j] = make_float4(__uint_as_float(r0[4 * j]), __uint_as_float(r0[4 * j + 1]), __uint_as_float(r0[4 * j + 2]), __uint_as_float(r0[4 * j + 3]));
+        d[8 + j] = make_float4(__uint_as_float(r1[4 * j]), __uint_as_float(r1[4 * j + 1]), __uint_as_float(r1[4 * j + 2]), __uint_as_float(r1[4 * j + 3]));
       }
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+}
+
+// Stage 2: dw[group][co][ci][tap] += sum over the pair's CTAs (fixed order) of their partial tiles.
+// grid (npairs_all, 8): block = one (group, cin chunk, cout slice) pair x 8 output channels; gathers [9 taps][64 ci][8 co]
+// into smem, then writes 8 runs of 576 contiguous floats.
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const __grid_constant__ WgradReduceParams p) {
+  __shared__ float sm[8][577];
+  const int pair_all = blockIdx.x, co0 = blockIdx.y * 8;
+  const int KC = p.cin >> 6, NSL = p.cout >> 6;
+  const int npairs = KC * NSL;
+  const int grp = pair_all / npairs, pair = pair_all % npairs;
+  const int kc = pair / NSL, sl = pair % NSL;
+  for (int idx = threadIdx.x; idx < 9 * 64 * 8; idx += 256) {
+    const int j = idx & 7, ci = (idx >> 3) & 63, tap = idx >> 9;
+    const int slot = p.slot_of_tap[tap];
+    const size_t off = (((size_t)(slot >> 1)) * 128 + (slot & 1) * 64 + ci) * 64 + co0 + j;
+    float acc = 0.f;
+    for (int c = 0; c < p.ctas_per_pair; ++c)
+      acc += p.partial[((size_t)(pair_all + c * p.npairs_all)) * (5 * 128 * 64) + off];
+    sm[j][ci * 9 + tap] = acc;
+  }
+  __syncthreads();
+  float* dw = p.dw[grp];
+  for (int idx = threadIdx.x; idx < 8 * 576; idx += 256) {
+    const int j = idx / 576, e = idx - j * 576;
+    const int col = sl * 64 + co0 + j;                // GEMM column = dY channel
+    int co = col;
+    if (p.ps_perm) { const int cq = p.cout >> 2; co = 4 * (col % cq) + col / cq; }
+    dw[((size_t)co * p.cin + kc * 64) * 9 + e] += sm[j][e];
+  }
 }
 
 }  // namespace fsr

@@ -31,6 +31,35 @@ def vgg_conv_indices() -> List[int]:
     return idx
 
 
+class ZeroArena:
+    """InstanceNorm statistics buffers ([N,C,2] int64, accumulated with atomics by the conv epilogues) must start at zero.
+    One `torch.zeros` per conv was 38 fill launches per step; the arena hands out slices of ONE buffer that the step zeroes
+    once.  Sizes are learned during the first (eager) step, which falls back to individual allocations."""
+
+    def __init__(self):
+        self.buf: Optional[torch.Tensor] = None
+        self.off = 0
+        self.need = 0
+
+    def reset(self, device):
+        if self.buf is None or self.buf.numel() < self.need:
+            self.buf = torch.zeros(max(self.need, 1), dtype=torch.int64, device=device) if self.need else None
+        elif self.off:
+            self.buf[:self.off].zero_()
+        self.off = 0
+
+    def take(self, N: int, C: int, device) -> torch.Tensor:
+        n = N * C * 2
+        if self.buf is None or self.off + n > self.buf.numel():
+            self.need = max(self.need, self.off + n)
+            self.off += n
+            return torch.zeros((N, C, 2), dtype=torch.int64, device=device)
+        out = self.buf[self.off:self.off + n].view(N, C, 2)
+        self.off += n
+        self.need = max(self.need, self.off)
+        return out
+
+
 class FlatParams:
     """All parameters of a module re-pointed into one flat fp32 buffer (+ flat grad / Adam moments)."""
 
@@ -128,6 +157,10 @@ class GeneratorNet:
         self._packed_version = -1
         self._bwd_version = -1
         self.P: Dict[str, torch.Tensor] = {}
+        self.arena: Optional[ZeroArena] = None             # set by GANEngine: statistics buffers zeroed once per step
+
+    def _stats(self, x, cout=64):
+        return self.arena.take(x.shape[0], cout, x.device) if self.arena is not None else None
 
     def _convs64(self):
         names = []
@@ -166,30 +199,39 @@ class GeneratorNet:
             self._bwd_version = self.fp.version
         self._packed_version = self.fp.version
 
-    def forward(self, lr_img: torch.Tensor, save: bool):
+    def forward(self, lr_img: torch.Tensor, save: bool, out: Optional[torch.Tensor] = None):
+        """out: optional fp32 NCHW [N,3,4h,4w] destination of sr (a slice of the step's [sr; hr] image batch).
+        save: the inputs of the 2L+1 64->64 convs are written into ONE arena [2L+1][N,h,w,64] (slot 2i = input of block i's
+        conv1, 2i+1 = input of its conv2, 2L = input of the bottleneck conv) so that their weight gradients run as a
+        single grouped launch in backward()."""
         self.pack(need_bwd=save)
         p, P, dt = self.fp.p, self.P, self.dt
-        a0 = ops.neck_conv3x3(lr_img, p["neck.0.weight"], p["neck.0.bias"], dt, act=L.ACT_PRELU, alpha=p["neck.1.weight"])
+        N, _, h, w = lr_img.shape
+        Lb = self.L
+        xa = torch.empty((2 * Lb + 1, N, h, w, 64), dtype=dt, device=lr_img.device) if save else None
+        slot = (lambda k: xa[k]) if save else (lambda k: None)
+        a0 = ops.neck_conv3x3(lr_img, p["neck.0.weight"], p["neck.0.bias"], dt, act=L.ACT_PRELU, alpha=p["neck.1.weight"], out=slot(0))
         cur, blocks = a0, []
-        for i in range(self.L):
-            raw1, st1 = ops.conv3x3_c64_raw_stats(cur, P[f"stem.{i}.conv1.weight"])
-            y1 = ops.instnorm_apply(raw1, st1, act=L.ACT_PRELU, alpha=p[f"stem.{i}.relu1.weight"])
-            raw2, st2 = ops.conv3x3_c64_raw_stats(y1, P[f"stem.{i}.conv2.weight"])
-            out = ops.instnorm_apply(raw2, st2, residual=cur)
+        for i in range(Lb):
+            raw1, st1 = ops.conv3x3_c64_raw_stats(cur, P[f"stem.{i}.conv1.weight"], stats=self._stats(cur))
+            y1 = ops.instnorm_apply(raw1, st1, act=L.ACT_PRELU, alpha=p[f"stem.{i}.relu1.weight"], out=slot(2 * i + 1))
+            raw2, st2 = ops.conv3x3_c64_raw_stats(y1, P[f"stem.{i}.conv2.weight"], stats=self._stats(y1))
+            nxt = ops.instnorm_apply(raw2, st2, residual=cur, out=slot(2 * i + 2))
             if save:
-                blocks.append((cur, raw1, st1, y1, raw2, st2))
-            cur = out
-        rawb, stb = ops.conv3x3_c64_raw_stats(cur, P["bottleneck.0.weight"])
+                blocks.append((raw1, st1, raw2, st2))
+            cur = nxt
+        rawb, stb = ops.conv3x3_c64_raw_stats(cur, P["bottleneck.0.weight"], stats=self._stats(cur))
         xb = ops.instnorm_apply(rawb, stb, residual=a0)
         U0 = ops.conv3x3_c64_ps_prelu(xb, P["up0.w"], P["up0.b"], p["upsampling.0.relu.weight"])
         U1 = ops.conv3x3_c64_ps_prelu(U0, P["up1.w"], P["up1.b"], p["upsampling.1.relu.weight"])
-        sr = ops.conv3x3_c64_head(U1, P["head.w"], P["head.b"])
-        ctx = dict(lr=lr_img, a0=a0, blocks=blocks, x_last=cur, rawb=rawb, stb=stb, xb=xb, U0=U0, U1=U1, sr=sr) if save else None
+        sr = ops.conv3x3_c64_head(U1, P["head.w"], P["head.b"], out=out)
+        ctx = dict(lr=lr_img, a0=a0, xa=xa, blocks=blocks, rawb=rawb, stb=stb, xb=xb, U0=U0, U1=U1, sr=sr) if save else None
         return sr, ctx
 
     def backward(self, ctx, d_sr: torch.Tensor):
         """d_sr: fp32 NCHW gradient w.r.t. the generator output; accumulates into fp.g."""
         p, g, P, dt = self.fp.p, self.fp.g, self.P, self.dt
+        Lb = self.L
         dpre = ops.tanh_bwd(ctx["sr"], d_sr)                                           # model.py:109
         ops.wgrad_c3(dpre, ctx["U1"], g["head.0.weight"], flip=True, layout=1)
         ops.bias_grad_nchw(dpre, g["head.0.bias"])
@@ -200,19 +242,21 @@ class GeneratorNet:
             ops.bias_grad(dconv, g[f"upsampling.{i}.conv.bias"], ps_perm=True)
             dU = ops.conv3x3_gen(dconv, P[f"up{i}.t"], 64, mode=1)
         dxb = dU
-        drawb = ops.instnorm_bwd(ctx["rawb"], ctx["stb"], dxb)                          # model.py:94
-        ops.conv3x3_wgrad(ctx["x_last"], drawb, g["bottleneck.0.weight"])
-        dcur = ops.conv3x3_c64_bias_act(drawb, P["bottleneck.0.weight.t"], None)
-        for i in reversed(range(self.L)):                                               # model.py:67-69
-            xin, raw1, st1, y1, raw2, st2 = ctx["blocks"][i]
-            draw2 = ops.instnorm_bwd(raw2, st2, dcur)
-            ops.conv3x3_wgrad(y1, draw2, g[f"stem.{i}.conv2.weight"])
-            dy1 = ops.conv3x3_c64_bias_act(draw2, P[f"stem.{i}.conv2.weight.t"], None)
-            draw1 = ops.instnorm_bwd(raw1, st1, dy1, act=L.ACT_PRELU, alpha=p[f"stem.{i}.relu1.weight"],
-                                     dalpha=g[f"stem.{i}.relu1.weight"])
-            ops.conv3x3_wgrad(xin, draw1, g[f"stem.{i}.conv1.weight"])
-            din = ops.conv3x3_c64_bias_act(draw1, P[f"stem.{i}.conv1.weight.t"], None)
+        # output gradients of the 2L+1 64->64 convs, same slot order as the input arena of forward()
+        xa = ctx["xa"]
+        da = torch.empty_like(xa)
+        ops.instnorm_bwd(ctx["rawb"], ctx["stb"], dxb, out=da[2 * Lb])                  # model.py:94
+        dcur = ops.conv3x3_c64_bias_act(da[2 * Lb], P["bottleneck.0.weight.t"], None)
+        for i in reversed(range(Lb)):                                                   # model.py:67-69
+            raw1, st1, raw2, st2 = ctx["blocks"][i]
+            ops.instnorm_bwd(raw2, st2, dcur, out=da[2 * i + 1])
+            dy1 = ops.conv3x3_c64_bias_act(da[2 * i + 1], P[f"stem.{i}.conv2.weight.t"], None)
+            ops.instnorm_bwd(raw1, st1, dy1, act=L.ACT_PRELU, alpha=p[f"stem.{i}.relu1.weight"],
+                             dalpha=g[f"stem.{i}.relu1.weight"], out=da[2 * i])
+            din = ops.conv3x3_c64_bias_act(da[2 * i], P[f"stem.{i}.conv1.weight.t"], None)
             dcur = ops.add(din, dcur)                                                   # + skip (model.py:69)
+        # all 2L+1 weight gradients of the residual chain: ONE grouped tcgen05 launch + its fixed-order reduction
+        ops.conv3x3_wgrad_grouped(xa, da, [g[n] for n in self._convs64()])
         da0 = ops.add(dcur, dxb)                                                        # + long skip (model.py:115)
         dv = ops.act_bwd(ctx["a0"], da0, L.ACT_PRELU, alpha=p["neck.1.weight"], dalpha=g["neck.1.weight"])
         ops.wgrad_c3(ctx["lr"], dv, g["neck.0.weight"], flip=False, layout=2)           # model.py:76
@@ -230,6 +274,7 @@ class DiscriminatorNet:
         self._packed_version = -1
         self._bwd_version = -1
         self.P: Dict[str, torch.Tensor] = {}
+        self.arena: Optional[ZeroArena] = None
 
     def pack(self, need_bwd: bool, force: bool = False):
         """(Re)pack into persistent buffers (CUDA-graph safe, see GeneratorNet.pack)."""
@@ -256,7 +301,8 @@ class DiscriminatorNet:
         for i, s in enumerate(D_STRIDES):
             cout = self.widths[i][1]
             xin = ops.parity_layout(cur, True) if s == 2 else cur
-            raw, st = ops.conv3x3_gen(xin, P[f"w{i}"], cout, stride=s, epilogue=L.EPI_RAW_STATS)
+            raw, st = ops.conv3x3_gen(xin, P[f"w{i}"], cout, stride=s, epilogue=L.EPI_RAW_STATS,
+                                      stats=self.arena.take(img.shape[0], cout, img.device) if self.arena is not None else None)
             act = ops.instnorm_apply(raw, st, act=L.ACT_LRELU, slope=0.01)
             if save:
                 layers.append((xin, raw, st))
@@ -347,13 +393,17 @@ class VGGNet:
         return cur, (dict(acts=acts) if save else None)
 
     def backward(self, ctx, dfeat: torch.Tensor, d_img: torch.Tensor):
-        """dfeat: gradient w.r.t. relu5_3 features (NHWC dtype); accumulates the image gradient into d_img (fp32 NCHW)."""
+        """dfeat: gradient w.r.t. relu5_3 features (NHWC dtype) of the FIRST dfeat.shape[0] images of the forward batch
+        (the step runs VGG once on [sr; hr] and differentiates the sr half only); accumulates the image gradient into
+        d_img (fp32 NCHW)."""
         P = self.P
         acts = ctx["acts"]
         widths = [v for v in VGG_PLAN if v != "M"]
         dcur = dfeat
+        nb = dfeat.shape[0]
         for j in reversed(range(len(acts))):
             a, pooled = acts[j]
+            a = a[:nb]
             da = ops.maxpool2_relu_bwd(a, dcur) if pooled else ops.relu_bwd(a, dcur)
             if j == 0:
                 ops.conv3x3_c64_head(da, P["t0"], None, out_u8=3, out=d_img)
@@ -393,6 +443,8 @@ class GANEngine:
         self.overlap = os.environ.get("FSR_TRAIN_OVERLAP", "1") != "0"
         self._graphs: Dict = {}
         self._side: Optional[torch.cuda.Stream] = None
+        self.arena = ZeroArena()
+        self.G.arena = self.D.arena = self.arena
         self.comm = None                                    # distributed.FlatComm: NCCL through the C ABI
         self.world = 1
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
@@ -488,16 +540,21 @@ class GANEngine:
         self._losses = losses = torch.zeros(4, dtype=torch.float32, device=lr_img.device)   # real, fake, adv bce, content sum
         self.dp.zero_grad()
         self.gp.zero_grad()
+        self.arena.reset(lr_img.device)                                 # every InstanceNorm statistics buffer of the step
         self.G.pack(need_bwd=True, force=True)                          # G changed at the end of the previous step
-        self._sr, self._ctx_g = self.G.forward(lr_img, save=True)      # :173 == :185 (see class docstring)
-        sr = self._sr
-        z_real, ctx_r = self.D.forward(hr_img, save=True)               # :172
-        z_fake, ctx_f = self.D.forward(sr, save=True)                   # :174
-        dz_r, dz_f = torch.empty_like(z_real), torch.empty_like(z_fake)
-        ops.bce_logits(z_real, n_real, 0.3, 0.8, losses[0:1], dz_r, grad_scale=0.5 * S)      # :175,177,179
-        ops.bce_logits(z_fake, n_fake, 0.3, 0.0, losses[1:2], dz_f, grad_scale=0.5 * S)      # :176,178,179
-        self.D.backward(ctx_r, dz_r, wgrad=True, d_img=None)            # :180
-        self.D.backward(ctx_f, dz_f, wgrad=True, d_img=None)
+        # ONE image batch X = [sr; hr] feeds the discriminator step and the VGG pass: D(hr) and D(sr) share their weights
+        # (:172, :174) and so do VGG(sr) and VGG(hr) (:190-191), every op is per-sample (InstanceNorm included), so one
+        # launch over 2B images is the same arithmetic as two launches over B - with half the launches
+        B = lr_img.shape[0]
+        X = torch.empty((2 * B,) + tuple(hr_img.shape[1:]), dtype=torch.float32, device=hr_img.device)
+        self._X = X
+        self._sr, self._ctx_g = self.G.forward(lr_img, save=True, out=X[:B])      # :173 == :185 (see class docstring)
+        X[B:].copy_(hr_img)
+        z, ctx = self.D.forward(X, save=True)                           # :172 (second half) and :174 (first half)
+        dz = torch.empty_like(z)
+        ops.bce_logits(z[B:], n_real, 0.3, 0.8, losses[0:1], dz[B:], grad_scale=0.5 * S)     # :175,177,179
+        ops.bce_logits(z[:B], n_fake, 0.3, 0.0, losses[1:2], dz[:B], grad_scale=0.5 * S)     # :176,178,179
+        self.D.backward(ctx, dz, wgrad=True, d_img=None)                # :180
 
     def _seg_d_update(self):
         """gradient exchange + discriminator AdamW (trainer.py:181) + re-pack of its weights (side stream)."""
@@ -507,10 +564,10 @@ class GANEngine:
 
     def _seg_content(self, ins):
         """content loss and its gradient w.r.t. sr (trainer.py:190-192 and their part of :195)."""
-        _, hr_img, _, _, _ = ins
         S, losses, sr = self.S, self._losses, self._sr
-        fake_f, ctx_v = self.V.forward(sr, save=True)                   # :190
-        real_f, _ = self.V.forward(hr_img, save=False)                  # :191
+        B = sr.shape[0]
+        feats, ctx_v = self.V.forward(self._X, save=True)               # :190 (first half) and :191 (second half)
+        fake_f, real_f = feats[:B], feats[B:]
         dfeat = torch.empty_like(fake_f)
         ops.smooth_l1(fake_f, real_f, losses[3:4], dfeat, grad_scale=0.5 * S / fake_f.numel())   # :192,194
         self._d_sr = torch.zeros_like(sr)
@@ -537,6 +594,7 @@ class GANEngine:
         S = self.S
         lr_img, hr_img = lr_img.contiguous().float(), hr_img.contiguous().float()
         self.gp.zero_grad()
+        self.arena.reset(lr_img.device)
         sr, ctx = self.G.forward(lr_img, save=True)
         loss = torch.zeros(1, dtype=torch.float32, device=lr_img.device)
         d_sr = torch.empty_like(sr)

@@ -133,7 +133,7 @@ def conv3x3_c64_head(x, w_packed, bias_packed, out_u8=False, out=None):
     return out
 
 
-def neck_conv3x3(x, weight, bias, dtype, act=L.ACT_PRELU, slope=0.0, alpha=None, vgg_norm=False):
+def neck_conv3x3(x, weight, bias, dtype, act=L.ACT_PRELU, slope=0.0, alpha=None, vgg_norm=False, out=None):
     """x fp32 NCHW [N,3,H,W] or uint8 NHWC [N,H,W,3] -> NHWC `dtype` [N,H,W,cout]."""
     _cuda(x, weight, bias, alpha)
     in_u8 = x.dtype == torch.uint8
@@ -145,7 +145,8 @@ def neck_conv3x3(x, weight, bias, dtype, act=L.ACT_PRELU, slope=0.0, alpha=None,
     cout = weight.shape[0]
     w = weight.detach().float().contiguous()
     b = bias.detach().float().contiguous() if bias is not None else None
-    out = torch.empty((N, H, W, cout), dtype=dtype, device=x.device)
+    if out is None:
+        out = torch.empty((N, H, W, cout), dtype=dtype, device=x.device)
     L.check(L.load().fsr_neck_conv3x3(x.data_ptr(), w.data_ptr(), L.ptr(b), L.ptr(alpha), out.data_ptr(), N, H, W, cout,
                                       act, slope, int(in_u8), int(vgg_norm), L.dtype_code(dtype),
                                       L.stream_ptr(x.device)), "neck conv")
@@ -239,6 +240,18 @@ def conv3x3_gen(x, w_packed, cout, stride=1, mode=0, epilogue=L.EPI_BIAS_ACT, bi
     return (out, stats) if epilogue == L.EPI_RAW_STATS else out
 
 
+_WGRAD_WS = {}
+
+
+def wgrad_workspace(device) -> torch.Tensor:
+    """Per-device scratch for the split-K partial tiles of the weight-gradient kernels (24 MB; contents never persist
+    between calls, calls on one stream are ordered)."""
+    key = str(device)
+    if key not in _WGRAD_WS:
+        _WGRAD_WS[key] = torch.empty(L.load().fsr_wgrad_workspace_bytes(), dtype=torch.uint8, device=device)
+    return _WGRAD_WS[key]
+
+
 def conv3x3_wgrad(x, dy, dw, stride=1, ps_perm=False):
     """dw (fp32 OIHW, accumulated) += wgrad(x, dy).  stride 2: x in parity planes [N,4,H/2,W/2,cin]."""
     _cuda(x, dy, dw)
@@ -248,9 +261,24 @@ def conv3x3_wgrad(x, dy, dw, stride=1, ps_perm=False):
         N, _, H2, W2, cin = x.shape
         H, W = 2 * H2, 2 * W2
     cout = dy.shape[-1]
+    ws = wgrad_workspace(x.device)
     L.check(L.load().fsr_conv3x3_wgrad(x.data_ptr(), dy.data_ptr(), dw.data_ptr(), N, H, W, cin, cout, stride, int(ps_perm),
-                                       L.dtype_code(x.dtype), L.stream_ptr(x.device)), "wgrad")
+                                       ws.data_ptr(), ws.numel(), L.dtype_code(x.dtype), L.stream_ptr(x.device)), "wgrad")
     return dw
+
+
+def conv3x3_wgrad_grouped(x_arena, dy_arena, dws):
+    """ONE launch for len(dws) weight gradients of identical shape: x_arena / dy_arena [G,N,H,W,C] NHWC, dws[g] fp32 OIHW (+=)."""
+    import ctypes
+    _cuda(x_arena, dy_arena, *dws)
+    G, N, H, W, cin = x_arena.shape
+    cout = dy_arena.shape[-1]
+    assert len(dws) == G and x_arena.is_contiguous() and dy_arena.is_contiguous()
+    ptrs = (ctypes.c_void_p * G)(*[d.data_ptr() for d in dws])
+    ws = wgrad_workspace(x_arena.device)
+    L.check(L.load().fsr_conv3x3_wgrad_grouped(x_arena.data_ptr(), dy_arena.data_ptr(), ptrs, G, x_arena.stride(0), dy_arena.stride(0),
+                                               N, H, W, cin, cout, ws.data_ptr(), ws.numel(), L.dtype_code(x_arena.dtype),
+                                               L.stream_ptr(x_arena.device)), "wgrad grouped")
 
 
 def parity_layout(x, to_parity=True):
@@ -333,11 +361,11 @@ def smooth_l1(a, b, loss_acc, da=None, grad_scale=1.0):
     return loss_acc
 
 
-def instnorm_bwd(raw, stats, dy, act=L.ACT_NONE, slope=0.0, alpha=None, dalpha=None, eps=1e-5):
+def instnorm_bwd(raw, stats, dy, act=L.ACT_NONE, slope=0.0, alpha=None, dalpha=None, eps=1e-5, out=None):
     _cuda(raw, stats, dy, alpha, dalpha)
     N, H, W, C = raw.shape
     red = torch.empty((N, C, 2), dtype=torch.float32, device=raw.device)
-    draw = torch.empty_like(raw)
+    draw = out if out is not None else torch.empty_like(raw)
     L.check(L.load().fsr_instnorm_bwd(raw.data_ptr(), stats.data_ptr(), dy.data_ptr(), red.data_ptr(), draw.data_ptr(), L.ptr(alpha),
                                       L.ptr(dalpha), N, H * W, C, act, slope, eps, L.dtype_code(raw.dtype), L.stream_ptr(raw.device)),
             "instnorm bwd")

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define FSR_ABI_VERSION 1
+#define FSR_ABI_VERSION 2
 #define FSR_MAX_LAYERS 32
 
 enum { FSR_F16 = 0, FSR_BF16 = 1 };
@@ -116,11 +116,20 @@ int fsr_nhwc_to_nchw_f32(const void* in, float* out, int N, int C, int HW, int d
 int fsr_pack_conv3x3_weight_t(const float* w_oihw, void* w_packed, int cout, int cin, int ps_perm, int flip, int row_pad,
                               const float* row_scale, int dtype, void* stream);
 
-/* Weight gradient of a 3x3/pad-1 conv on tcgen05 (autograd convolution_backward, weight part):
+/* Weight gradient of a 3x3/pad-1 conv on tcgen05 (autograd convolution_backward, weight part; trainer.py:180,195):
  * dw[co,ci,r,s] += sum dY[n,y,x,co] * X[n, stride*y+r-1, stride*x+s-1, ci].  H, W = X spatial size;
- * stride 2: X in parity-plane layout.  ps_perm: dY columns are pixel-shuffle-permuted (UpSamplingBlock). */
+ * stride 2: X in parity-plane layout.  ps_perm: dY columns are pixel-shuffle-permuted (UpSamplingBlock).
+ * Two stages without atomics (split-K partial tiles in `workspace`, then a fixed-order reduction): the result is
+ * bitwise reproducible.  workspace: >= fsr_wgrad_workspace_bytes() bytes of device memory (contents are scratch). */
+size_t fsr_wgrad_workspace_bytes(void);
 int fsr_conv3x3_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int cin, int cout, int stride,
-                      int ps_perm, int dtype, void* stream);
+                      int ps_perm, void* workspace, size_t ws_bytes, int dtype, void* stream);
+/* `groups` (<= 40) weight gradients of IDENTICAL shape (stride 1) in ONE launch - the generator's 2L+1 64->64 convs
+ * (model.py:47-64, 87-93): the conv inputs sit in x_arena [groups][N,H,W,cin] and the output gradients in dy_arena
+ * [groups][N,H,W,cout] (group strides in elements); dw_list_host[g] (HOST array of device pointers) receives group g. */
+int fsr_conv3x3_wgrad_grouped(const void* x_arena, const void* dy_arena, float* const* dw_list_host, int groups,
+                              long long x_group_stride, long long dy_group_stride, int N, int H, int W, int cin, int cout,
+                              void* workspace, size_t ws_bytes, int dtype, void* stream);
 
 /* NHWC [N,H,W,C] <-> parity planes [N][4][H/2][W/2][C] (input layout of stride-2 convs, model.py:124-131). */
 int fsr_parity_layout(const void* in, void* out, int N, int H, int W, int C, int to_parity, int dtype, void* stream);

@@ -109,6 +109,28 @@ def test_conv_wgrad(dt, cin, cout, shape, stride):
 
 
 @pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("G,shape", [(1, (2, 24, 24)), (5, (3, 24, 24)), (17, (4, 24, 24)), (3, (2, 13, 21))])
+def test_conv_wgrad_grouped_and_deterministic(dt, G, shape):
+    """ONE grouped launch for G weight gradients of identical shape (the generator's 2L+1 residual-chain convs) ==
+    G separate launches == PyTorch autograd; and the two-stage (no atomics) reduction is bitwise reproducible."""
+    from fast_srgan_b200 import ops
+    N, H, W = shape
+    xa = torch.stack([nhwc(rnd((N, 64, H, W), 20 + g), dt) for g in range(G)])
+    da = torch.stack([nhwc(rnd((N, 64, H, W), 60 + g), dt) for g in range(G)])
+    dws = [torch.zeros((64, 64, 3, 3), device="cuda") for _ in range(G)]
+    ops.conv3x3_wgrad_grouped(xa, da, dws)
+    again = [torch.zeros((64, 64, 3, 3), device="cuda") for _ in range(G)]
+    ops.conv3x3_wgrad_grouped(xa, da, again)
+    for g in range(G):
+        wr = torch.zeros((64, 64, 3, 3), device="cuda", requires_grad=True)
+        F.conv2d(nchw(xa[g]), wr, padding=1).backward(nchw(da[g]))
+        single = torch.zeros((64, 64, 3, 3), device="cuda")
+        ops.conv3x3_wgrad(xa[g], da[g], single)
+        assert rel_err(dws[g], wr.grad) <= 1e-4 and rel_err(single, wr.grad) <= 1e-4
+        assert torch.equal(dws[g], again[g])            # fixed-order reduction: run-to-run identical
+
+
+@pytest.mark.parametrize("dt", DT)
 def test_conv_wgrad_ps_perm(dt):
     from fast_srgan_b200 import ops
     N, H, W = 2, 12, 16
