@@ -24,6 +24,63 @@ def _default_dtype() -> torch.dtype:
     return torch.bfloat16 if os.environ.get("FSR_DTYPE", "fp16").lower() in ("bf16", "bfloat16") else torch.float16
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# Autograd bridge (SURVEY.md 8b "Callers": trainer.py:110,180,195 call loss.backward() THROUGH the modules).
+# forward() saves the engine's activation context, backward() runs the engine's hand-written reverse walk (every FLOP in
+# libfsr_b200) and hands the parameter gradients to autograd, so a reference-style loop
+#     loss = criterion(discriminator(generator(lr)), labels); loss.backward(); optimizer.step()
+# with stock torch.optim.AdamW over module.parameters() runs unmodified.  Trainer.train_step (engine.GANEngine) remains
+# the fast path: one CUDA graph, flat AdamW, no per-parameter gradient copies.
+class _NetFn(torch.autograd.Function):
+    """Generator / Discriminator: inputs (x, *parameters) so that autograd routes gradients to the parameters."""
+
+    @staticmethod
+    def forward(ctx, module, x, *params):
+        net = module._net_for_autograd()
+        net.fp.version += 1                  # an external optimizer may have stepped the (aliased) parameters in place
+        y, c = net.forward(x.contiguous().float(), save=True)
+        ctx.net, ctx.c, ctx.kind = net, c, module._fsr_kind
+        ctx.need_dx = x.requires_grad
+        ctx.x_shape = tuple(x.shape)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        net = ctx.net
+        net.fp.zero_grad()
+        dy = dy.contiguous().float()
+        dx = None
+        if ctx.kind == "G":
+            net.backward(ctx.c, dy)          # image gradient of the generator input is never needed (model.py:75: leaf)
+        else:
+            if ctx.need_dx:
+                dx = torch.zeros(ctx.x_shape, dtype=torch.float32, device=dy.device)
+            net.backward(ctx.c, dy, wgrad=True, d_img=dx)
+        grads = tuple(net.fp.g[n].clone() for n in net.fp.names)
+        return (None, dx) + grads
+
+
+class _VggFn(torch.autograd.Function):
+    """VGG19[:34] is frozen (model.py:9-10): only the image gradient flows back (trainer.py:195 -> sr)."""
+
+    @staticmethod
+    def forward(ctx, module, x):
+        net = module._engine()
+        feat, c = net.forward(x.contiguous().float(), save=x.requires_grad)
+        ctx.net, ctx.c, ctx.x_shape = net, c, tuple(x.shape)
+        from . import ops
+        return ops.nhwc_to_nchw(feat)
+
+    @staticmethod
+    def backward(ctx, dfeat):
+        from . import ops
+        if ctx.c is None:
+            return None, None
+        dx = torch.zeros(ctx.x_shape, dtype=torch.float32, device=dfeat.device)
+        ctx.net.backward(ctx.c, ops.nchw_to_nhwc(dfeat.contiguous().float(), ctx.net.dt), dx)
+        return None, dx
+
+
 class _Conv(torch.nn.Module):
     """Parameter holder with torch.nn.Conv2d's names, shapes and default init (kaiming_uniform a=sqrt(5))."""
 
@@ -255,11 +312,24 @@ class Generator(torch.nn.Module):
         if not x.is_cuda:
             raise RuntimeError("fast_srgan_b200.Generator runs on CUDA (sm_100a) tensors only - no CPU fallback")
 
+    _fsr_kind = "G"
+
+    def _net_for_autograd(self):
+        from .engine import FlatParams, GeneratorNet
+        fp = getattr(self, "_fsr_flat", None)
+        if fp is None or not fp.aliases(self):               # first use, or .to(device) re-allocated the parameters
+            fp = FlatParams(self, with_optimizer=False)
+            self._train_net = None
+        if getattr(self, "_train_net", None) is None or self._train_net.fp is not fp:
+            dt = self.compute_dtype if self.compute_dtype != torch.float32 else torch.bfloat16
+            self._train_net = GeneratorNet(self, fp, dt)
+        return self._train_net
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         self._require_cuda(x)
-        if torch.is_grad_enabled() and x.requires_grad:
-            raise RuntimeError("autograd through fast_srgan_b200 modules is not supported: use Trainer.train_step / "
-                               "pretrain_step (hand-written backward kernels, trainer.py:104-111, 168-196)")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            # training through autograd (trainer.py:108,185): hand-written forward + backward kernels behind a Function
+            return _NetFn.apply(self, x, *self.parameters())
         x = x.contiguous().float()
         N, C, H, W = x.shape
         if C != 3:
@@ -315,11 +385,15 @@ class Discriminator(torch.nn.Module):
             self._net = DiscriminatorNet(self, fp, self.compute_dtype)
         return self._net
 
+    _fsr_kind = "D"
+
+    def _net_for_autograd(self):
+        return self._engine()
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         Generator._require_cuda(x)
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and x.requires_grad:
-            raise RuntimeError("autograd through fast_srgan_b200 modules is not supported: use Trainer.train_step "
-                               "(hand-written backward kernels, trainer.py:168-196)")
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            return _NetFn.apply(self, x, *self.parameters()).unsqueeze(1)      # trainer.py:172,174,186
         net = self._engine()
         net.fp.version += 1            # parameters may have been changed by the caller (load_state_dict / optimizer)
         z, _ = net.forward(x.contiguous().float(), save=False)
@@ -373,6 +447,8 @@ class VGG19(torch.nn.Module):
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         Generator._require_cuda(x)
+        if torch.is_grad_enabled() and x.requires_grad:
+            return _VggFn.apply(self, x)                                         # trainer.py:190
         feat, _ = self._engine().forward(x.contiguous().float(), save=False)
         from . import ops
         return ops.nhwc_to_nchw(feat)

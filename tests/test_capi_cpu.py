@@ -35,7 +35,7 @@ def test_binding_covers_header():
 
 def test_abi_version_and_errors(lib):
     lib.fsr_abi_version.restype = ctypes.c_int
-    assert lib.fsr_abi_version() == 1
+    assert lib.fsr_abi_version() == 2
     lib.fsr_error_string.restype = ctypes.c_char_p
     assert lib.fsr_error_string(0) == b"ok"
     assert b"workspace" in lib.fsr_error_string(-4)
