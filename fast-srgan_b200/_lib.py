@@ -60,6 +60,7 @@ _SIGS = {
     "fsr_conv3x3_head": (_i, [_vp, _vp, _vp, _fp, _i, _i, _i, _i, _i, _i, _vp]),
     "fsr_neck_conv3x3": (_i, [_vp, _fp, _fp, _fp, _vp, _i, _i, _i, _i, _i, _f, _i, _i, _i, _vp]),
     "fsr_instnorm_apply": (_i, [_vp, _fp, _vp, _vp, _fp, _i, _i, _i, _i, _f, _f, _i, _vp]),
+    "fsr_instnorm_apply_parity": (_i, [_vp, _fp, _vp, _fp, _i, _i, _i, _i, _i, _f, _f, _i, _vp]),
     "fsr_pixel_shuffle2": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "fsr_nchw_f32_to_nhwc": (_i, [_fp, _vp, _i, _i, _i, _i, _vp]),
     "fsr_nhwc_to_nchw_f32": (_i, [_vp, _fp, _i, _i, _i, _i, _vp]),
@@ -73,6 +74,7 @@ _SIGS = {
     "fsr_set_ws_mode": (_i, [_i]),
     "fsr_set_small_mma": (_i, [_i]),
     "fsr_set_gen_ws": (_i, [_i]),
+    "fsr_set_gen_2cta": (_i, [_i]),
     "fsr_set_fuse_in": (_i, [_i]),
     "fsr_conv3x3_c64_in": (_i, [_vp, _vp, _fp, _f, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "fsr_conv3x3_c64_res_in": (_i, [_vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),

@@ -4,6 +4,7 @@
 #include "conv3x3_up_2cta.cuh"
 #include "conv3x3_gen.cuh"
 #include "conv3x3_gen_ws.cuh"
+#include "conv3x3_gen_2cta.cuh"
 #include "conv3x3_head.cuh"
 #include "conv3x3_wgrad.cuh"
 #include "train_kernels.cuh"
@@ -356,9 +357,41 @@ int gen_ws_mode() {
   return g_gen_ws;
 }
 
+int g_gen_2cta = -1;   // general conv, Cout % 128 == 0: 1 = CTA-pair kernel with 128-wide slices (conv3x3_gen_2cta.cuh)
+int gen_2cta_mode() {
+  if (g_gen_2cta < 0) {
+    const char* e = getenv("FSR_GEN_2CTA");
+    g_gen_2cta = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_gen_2cta;
+}
+
 template <int EPI, typename T, int MAXTAPS>
-int launch_gen(const CUtensorMap* maps, const CUtensorMap& tmw, GenParams& p, cudaStream_t st) {
+int launch_gen(const CUtensorMap* maps, const CUtensorMap& tmw, GenParams& p, cudaStream_t st, int dtype) {
   using Cfg = GenCfg<MAXTAPS>;
+  if (gen_2cta_mode() && p.cout_total % 128 == 0 && !p.ps) {
+    using C2 = Gen2Cfg<MAXTAPS>;
+    auto k2 = conv3x3_gen_2cta_kernel<EPI, T, MAXTAPS>;
+    static bool attr2_done = false;
+    if (!attr2_done) {
+      FSR_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, C2::kSmemBytes));
+      attr2_done = true;
+    }
+    GenParams p2 = p;
+    p2.num_slices = p.cout_total / 128;
+    CUtensorMap tmo;
+    int rc = make_act_map_strided(&tmo, p.out, p.N, p.Ho, p.Wo, p.cout_total, p.out_img_stride, 8, 4, dtype);
+    if (rc) return rc;
+    const int pairs = (p.num_tiles + 1) / 2;
+    int cps = (num_sms() / 2) / p2.num_slices;      // clusters per 128-wide slice
+    if (cps < 1) cps = 1;
+    if (cps > pairs) cps = pairs;
+    int ntaps2 = 0;
+    for (int k = 0; k < p.nkinds; ++k) ntaps2 += p.kinds[k].ntaps;
+    LaunchScope scope(FSR_K_CONV_GEN, st, 2.0 * p.N * p.Ho * p.Wo * (double)p.cout_total * p.cin * ntaps2);
+    k2<<<2 * cps * p2.num_slices, C2::kThreads, C2::kSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], tmw, tmo, p2);
+    return cuda_rc(cudaGetLastError());
+  }
   int ctas_per_slice = num_sms() / p.num_slices;
   if (ctas_per_slice < 1) ctas_per_slice = 1;
   if (ctas_per_slice > p.num_tiles) ctas_per_slice = p.num_tiles;
@@ -415,8 +448,8 @@ int gen_dispatch(const void* x, const void* w_packed, void* out, const float* bi
     p.Ho = Ho; p.Wo = Wo; p.out = o; p.out_img_stride = img_stride;
     p.tiles_x = (Wo + 7) / 8; p.tiles_y = (Ho + 15) / 16; p.num_tiles = N * p.tiles_x * p.tiles_y;
     if (epilogue == FSR_EPI_RAW_STATS)
-      return taps9 ? launch_gen<EPI_RAW_STATS, T, 9>(maps, tmw, p, st) : launch_gen<EPI_RAW_STATS, T, 4>(maps, tmw, p, st);
-    return taps9 ? launch_gen<EPI_BIAS_ACT, T, 9>(maps, tmw, p, st) : launch_gen<EPI_BIAS_ACT, T, 4>(maps, tmw, p, st);
+      return taps9 ? launch_gen<EPI_RAW_STATS, T, 9>(maps, tmw, p, st, dtype) : launch_gen<EPI_RAW_STATS, T, 4>(maps, tmw, p, st, dtype);
+    return taps9 ? launch_gen<EPI_BIAS_ACT, T, 9>(maps, tmw, p, st, dtype) : launch_gen<EPI_BIAS_ACT, T, 4>(maps, tmw, p, st, dtype);
   };
   if (stride == 1) {
     // forward: out[y,x] += W[r,s] x[y+r-1, x+s-1];  dgrad (transposed, unflipped pack): dX[y,x] += W[r,s]^T dY[y+1-r, x+1-s]
@@ -722,11 +755,12 @@ int fsr_neck_conv3x3(const void* x, const float* w, const float* bias, const flo
   return cuda_rc(cudaGetLastError());
 }
 
-int fsr_instnorm_apply(const void* raw, const int64_t* stats, const void* residual, void* out, const float* alpha,
-                       int N, int HW, int C, int act, float slope, float eps, int dtype, void* stream) {
+static int instnorm_apply_impl(const void* raw, const int64_t* stats, const void* residual, void* out, const float* alpha,
+                               int N, int HW, int C, int act, float slope, float eps, int parity_w, int dtype, void* stream) {
   if (!raw || !stats || !out || C % 8 || N <= 0 || HW <= 0) return FSR_ERR_BAD_ARG;
   if (act == FSR_ACT_PRELU && !alpha) return FSR_ERR_BAD_ARG;
-  InApplyParams p{raw, reinterpret_cast<const long long*>(stats), residual, out, alpha, slope, act, HW, C, eps};
+  if (parity_w < 0 || (parity_w > 0 && ((parity_w & 1) || HW % parity_w || ((HW / parity_w) & 1) || out == raw))) return FSR_ERR_BAD_SHAPE;
+  InApplyParams p{raw, reinterpret_cast<const long long*>(stats), residual, out, alpha, slope, act, HW, C, eps, parity_w};
   const size_t nvec = (size_t)HW * (C / 8);
   int bpi = (int)((nvec + 256 * 4 - 1) / (256 * 4));   // ~4 vectors per thread
   const int cap = (num_sms() * 8 + N - 1) / N;
@@ -739,6 +773,16 @@ int fsr_instnorm_apply(const void* raw, const int64_t* stats, const void* residu
   if (dtype == FSR_BF16) instnorm_apply_kernel<__nv_bfloat16><<<grid, 256, sm, st>>>(p);
   else instnorm_apply_kernel<__half><<<grid, 256, sm, st>>>(p);
   return cuda_rc(cudaGetLastError());
+}
+
+int fsr_instnorm_apply(const void* raw, const int64_t* stats, const void* residual, void* out, const float* alpha,
+                       int N, int HW, int C, int act, float slope, float eps, int dtype, void* stream) {
+  return instnorm_apply_impl(raw, stats, residual, out, alpha, N, HW, C, act, slope, eps, 0, dtype, stream);
+}
+
+int fsr_instnorm_apply_parity(const void* raw, const int64_t* stats, void* out, const float* alpha, int N, int H, int W, int C,
+                              int act, float slope, float eps, int dtype, void* stream) {
+  return instnorm_apply_impl(raw, stats, nullptr, out, alpha, N, H * W, C, act, slope, eps, W, dtype, stream);
 }
 
 int fsr_pixel_shuffle2(const void* in, void* out, int N, int H, int W, int C, int dtype, void* stream) {
@@ -814,6 +858,11 @@ unsigned long long fsr_launch_count(void) { return g_launches.load(); }
 
 int fsr_set_ws_mode(int weight_stationary) {
   g_ws = weight_stationary < 0 ? -1 : (weight_stationary ? 1 : 0);   // -1: back to the environment default
+  return FSR_OK;
+}
+
+int fsr_set_gen_2cta(int on) {
+  g_gen_2cta = on < 0 ? -1 : (on ? 1 : 0);   // -1: back to the environment default (FSR_GEN_2CTA)
   return FSR_OK;
 }
 
@@ -1122,11 +1171,11 @@ int fsr_instnorm_bwd(const void* raw, const int64_t* stats, const void* dy, floa
   if (act == FSR_ACT_PRELU && !alpha) return FSR_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   InBwdParams p{raw, reinterpret_cast<const long long*>(stats), dy, red, draw, alpha, dalpha, slope, act, HW, C, eps};
-  if (C % 64 == 0 && HW <= 4096 && in_bwd_fused_mode()) {
+  if (C % 16 == 0 && HW <= 4096 && in_bwd_fused_mode()) {
     // training shapes: one launch, the per-(n,c) sums stay inside the block (no `red` scratch, no memset, no atomics)
     LaunchScope scope(FSR_K_NONE - 1, st);
-    FSR_T((instnorm_bwd_fused_kernel<__half><<<dim3(C / 64, N), 256, 0, st>>>(p)),
-          (instnorm_bwd_fused_kernel<__nv_bfloat16><<<dim3(C / 64, N), 256, 0, st>>>(p)));
+    FSR_T((instnorm_bwd_fused_kernel<__half><<<dim3(C / 16, N), 256, 0, st>>>(p)),
+          (instnorm_bwd_fused_kernel<__nv_bfloat16><<<dim3(C / 16, N), 256, 0, st>>>(p)));
     return cuda_rc(cudaGetLastError());
   }
   if (!red) return FSR_ERR_BAD_ARG;

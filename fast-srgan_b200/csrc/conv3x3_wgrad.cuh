@@ -199,25 +199,39 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_con
 }
 
 // Stage 2: dw[group][co][ci][tap] += sum over the pair's CTAs (fixed order) of their partial tiles.
-// grid (npairs_all, 8): block = one (group, cin chunk, cout slice) pair x 8 output channels; gathers [9 taps][64 ci][8 co]
-// into smem, then writes 8 runs of 576 contiguous floats.
+// grid (npairs_all, 8): block = one (group, cin chunk, cout slice) pair x 8 output channels.  256 threads = 64 input
+// channels x 4 split slices: slice s sums partials s, s+4, s+8, ... (independent loads in flight), the four slice sums
+// are added in fixed order through smem -> [9 taps][64 ci][8 co] in smem -> 8 runs of 576 contiguous floats.
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const __grid_constant__ WgradReduceParams p) {
   __shared__ float sm[8][577];
+  __shared__ float part[4][64][9];
   const int pair_all = blockIdx.x, co0 = blockIdx.y * 8;
   const int KC = p.cin >> 6, NSL = p.cout >> 6;
   const int npairs = KC * NSL;
   const int grp = pair_all / npairs, pair = pair_all % npairs;
   const int kc = pair / NSL, sl = pair % NSL;
-  for (int idx = threadIdx.x; idx < 9 * 64 * 8; idx += 256) {
-    const int j = idx & 7, ci = (idx >> 3) & 63, tap = idx >> 9;
+  const int ci = threadIdx.x & 63, s4 = threadIdx.x >> 6;
+  const size_t slot_stride = (size_t)5 * 128 * 64;
+#pragma unroll 1
+  for (int tap = 0; tap < 9; ++tap) {
     const int slot = p.slot_of_tap[tap];
-    const size_t off = (((size_t)(slot >> 1)) * 128 + (slot & 1) * 64 + ci) * 64 + co0 + j;
-    float acc = 0.f;
-    for (int c = 0; c < p.ctas_per_pair; ++c)
-      acc += p.partial[((size_t)(pair_all + c * p.npairs_all)) * (5 * 128 * 64) + off];
-    sm[j][ci * 9 + tap] = acc;
+    const float* src = p.partial + (((size_t)(slot >> 1)) * 128 + (slot & 1) * 64 + ci) * 64 + co0;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int c = s4; c < p.ctas_per_pair; c += 4) {
+      const float4* q = reinterpret_cast<const float4*>(src + (size_t)(pair_all + c * p.npairs_all) * slot_stride);
+      const float4 a = q[0], b = q[1];
+      acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+      acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) part[s4][ci][j] = acc[j];
+    __syncthreads();
+    if (s4 == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sm[j][ci * 9 + tap] = ((part[0][ci][j] + part[1][ci][j]) + part[2][ci][j]) + part[3][ci][j];
+    }
+    __syncthreads();
   }
-  __syncthreads();
   float* dw = p.dw[grp];
   for (int idx = threadIdx.x; idx < 8 * 576; idx += 256) {
     const int j = idx / 576, e = idx - j * 576;

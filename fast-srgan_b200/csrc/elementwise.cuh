@@ -114,6 +114,8 @@ struct InApplyParams {
   int act;
   int HW, C;
   float eps;
+  int parity_w;          // > 0: write `out` in the parity-plane layout [N][4][H/2][W/2][C] the stride-2 convs read
+                         //      (image width W = parity_w; saves the separate re-layout pass of the discriminator)
 };
 
 template <typename T>
@@ -154,7 +156,14 @@ __global__ void __launch_bounds__(256) instnorm_apply_kernel(const InApplyParams
       }
       ou[k] = Cvt<T>::pack2(a, b);
     }
-    out[i] = make_uint4(ou[0], ou[1], ou[2], ou[3]);
+    size_t o = i;
+    if (p.parity_w > 0) {
+      const int pix = (int)(i / vec_per_pix), v = (int)(i - (size_t)pix * vec_per_pix);
+      const int y = pix / p.parity_w, x = pix - y * p.parity_w;
+      const int W2 = p.parity_w >> 1, H2 = (p.HW / p.parity_w) >> 1;
+      o = ((size_t)(((y & 1) * 2 + (x & 1)) * H2 + (y >> 1)) * W2 + (x >> 1)) * vec_per_pix + v;
+    }
+    out[o] = make_uint4(ou[0], ou[1], ou[2], ou[3]);
   }
 }
 

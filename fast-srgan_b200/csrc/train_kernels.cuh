@@ -332,33 +332,32 @@ __global__ void __launch_bounds__(256) instnorm_bwd_kernel(const InBwdParams p) 
   }
 }
 
-// Single-launch form for the small planes of the training shapes (HW <= 4096): one block owns one sample's 64-channel
-// group, sweeps the plane twice (the second sweep hits L1/L2: a 24x24x64 plane is 74 KB) - pass 1 sums, pass 2 writes
-// dRaw.  Replaces 2 launches + 1 memset per call (76 launches of ~12 us on 4.7 MB tensors in the GAN step were pure
-// launch latency) and makes the per-(n,c) sums order-independent: they never leave the block, no atomics.
+// Single-launch form for the small planes of the training shapes (HW <= 4096): one block owns one sample's 16-channel
+// group (a full 32-byte sector per pixel), sweeps the plane twice (the second sweep hits L1/L2) - pass 1 sums, pass 2
+// writes dRaw.  Replaces 2 launches + 1 memset per call and keeps the per-(n,c) sums inside the block (fixed-order
+// reduction, no atomics): the InstanceNorm backward is bitwise reproducible.
 template <typename T>
 __global__ void __launch_bounds__(256) instnorm_bwd_fused_kernel(const InBwdParams p) {
-  __shared__ float s_mean[64], s_rstd[64], s_m1[64], s_m2[64];
-  __shared__ float s_red[32][8][17];                 // [pixel lane][channel vector][a1 0..7, a2 0..7] (+1 pad)
+  __shared__ float s_red[8][2][16];                  // [warp][vector of the pixel][a1 0..7, a2 0..7]
+  __shared__ float s_m[2][16];                       // mean(g), mean(g*xhat) per (vector, channel)
   __shared__ float s_da[8];
-  const int n = blockIdx.y, cg = blockIdx.x;          // sample, 64-channel group
-  const int vec = threadIdx.x & 7, pl = threadIdx.x >> 3;
-  if (threadIdx.x < 64)
-    stat_mean_rstd(p.stats + ((size_t)n * p.C + cg * 64 + threadIdx.x) * 2, 1.0 / (double)p.HW, p.eps, s_mean[threadIdx.x], s_rstd[threadIdx.x]);
-  __syncthreads();
+  const int n = blockIdx.y, cg = blockIdx.x;          // sample, 16-channel group
+  const int vec = threadIdx.x & 1, pl = threadIdx.x >> 1;   // 128 pixel lanes x 2 vectors of 8 channels
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c0 = cg * 16 + vec * 8;
+  float mean[8], rstd[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) stat_mean_rstd(p.stats + ((size_t)n * p.C + c0 + k) * 2, 1.0 / (double)p.HW, p.eps, mean[k], rstd[k]);
   const float slope = (p.act == ACT_PRELU) ? __ldg(p.alpha) : p.slope;
   const bool has_act = (p.act == ACT_PRELU || p.act == ACT_LRELU);
-  const size_t base = ((size_t)n * p.HW) * p.C + cg * 64 + vec * 8;
+  const size_t base = ((size_t)n * p.HW) * p.C + c0;
   const T* raw = reinterpret_cast<const T*>(p.raw) + base;
   const T* dy = reinterpret_cast<const T*>(p.dy) + base;
   T* draw = reinterpret_cast<T*>(p.draw) + base;
-  float mean[8], rstd[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) { mean[k] = s_mean[vec * 8 + k]; rstd[k] = s_rstd[vec * 8 + k]; }
   float a1[8], a2[8], da = 0.f;
 #pragma unroll
   for (int k = 0; k < 8; ++k) { a1[k] = 0.f; a2[k] = 0.f; }
-  for (int px = pl; px < p.HW; px += 32) {
+  for (int px = pl; px < p.HW; px += 128) {
     const uint4 r = *reinterpret_cast<const uint4*>(raw + (size_t)px * p.C), g4 = *reinterpret_cast<const uint4*>(dy + (size_t)px * p.C);
     const uint32_t ru[4] = {r.x, r.y, r.z, r.w}, gu[4] = {g4.x, g4.y, g4.z, g4.w};
 #pragma unroll
@@ -374,21 +373,32 @@ __global__ void __launch_bounds__(256) instnorm_bwd_fused_kernel(const InBwdPara
       a1[2 * k + 1] += g1; a2[2 * k + 1] = fmaf(g1, xh1, a2[2 * k + 1]);
     }
   }
+  // warp: lanes of equal parity hold the same channel vector -> butterfly over lane bits 1..4, then 8 warps through smem
 #pragma unroll
-  for (int k = 0; k < 8; ++k) { s_red[pl][vec][k] = a1[k]; s_red[pl][vec][8 + k] = a2[k]; }
+  for (int k = 0; k < 8; ++k) {
+#pragma unroll
+    for (int o = 16; o >= 2; o >>= 1) {
+      a1[k] += __shfl_xor_sync(0xffffffffu, a1[k], o);
+      a2[k] += __shfl_xor_sync(0xffffffffu, a2[k], o);
+    }
+  }
+  if (lane < 2) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { s_red[warp][lane][k] = a1[k]; s_red[warp][lane][8 + k] = a2[k]; }
+  }
   if (p.act == ACT_PRELU && p.dalpha) {
     da = warp_sum(da);
-    if ((threadIdx.x & 31) == 0) s_da[threadIdx.x >> 5] = da;
+    if (lane == 0) s_da[warp] = da;
   }
   __syncthreads();
-  if (threadIdx.x < 128) {                             // thread = (channel 0..63, which sum): fixed-order sum over the 32 pixel lanes
-    const int c = threadIdx.x & 63, which = threadIdx.x >> 6;
+  if (threadIdx.x < 32) {                              // thread = (vector, which sum, channel): fixed-order sum over the 8 warps
+    const int v = threadIdx.x >> 4, i = threadIdx.x & 15;
     float t = 0.f;
-#pragma unroll 8
-    for (int i = 0; i < 32; ++i) t += s_red[i][c >> 3][which * 8 + (c & 7)];
-    (which ? s_m2 : s_m1)[c] = t / (float)p.HW;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += s_red[w][v][i];
+    s_m[v][i] = t / (float)p.HW;
   }
-  if (threadIdx.x == 0 && p.act == ACT_PRELU && p.dalpha) {
+  if (threadIdx.x == 32 && p.act == ACT_PRELU && p.dalpha) {
     float t = 0.f;
     for (int i = 0; i < 8; ++i) t += s_da[i];
     atomicAdd(p.dalpha, t);
@@ -396,8 +406,8 @@ __global__ void __launch_bounds__(256) instnorm_bwd_fused_kernel(const InBwdPara
   __syncthreads();
   float m1[8], m2[8];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) { m1[k] = s_m1[vec * 8 + k]; m2[k] = s_m2[vec * 8 + k]; }
-  for (int px = pl; px < p.HW; px += 32) {
+  for (int k = 0; k < 8; ++k) { m1[k] = s_m[vec][k]; m2[k] = s_m[vec][8 + k]; }
+  for (int px = pl; px < p.HW; px += 128) {
     const uint4 r = *reinterpret_cast<const uint4*>(raw + (size_t)px * p.C), g4 = *reinterpret_cast<const uint4*>(dy + (size_t)px * p.C);
     const uint32_t ru[4] = {r.x, r.y, r.z, r.w}, gu[4] = {g4.x, g4.y, g4.z, g4.w};
     uint32_t ou[4];

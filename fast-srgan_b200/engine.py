@@ -298,12 +298,18 @@ class DiscriminatorNet:
         p, P, dt = self.fp.p, self.P, self.dt
         d0 = ops.neck_conv3x3(img, p["neck.0.weight"], p["neck.0.bias"], dt, act=L.ACT_LRELU, slope=0.2)
         cur, layers = d0, []
+        cur_is_parity = False
         for i, s in enumerate(D_STRIDES):
             cout = self.widths[i][1]
-            xin = ops.parity_layout(cur, True) if s == 2 else cur
+            xin = cur if (s == 1 or cur_is_parity) else ops.parity_layout(cur, True)
             raw, st = ops.conv3x3_gen(xin, P[f"w{i}"], cout, stride=s, epilogue=L.EPI_RAW_STATS,
                                       stats=self.arena.take(img.shape[0], cout, img.device) if self.arena is not None else None)
-            act = ops.instnorm_apply(raw, st, act=L.ACT_LRELU, slope=0.01)
+            # the next stride-2 block reads its input in parity-plane layout: written directly by the normalise pass
+            cur_is_parity = i + 1 < len(D_STRIDES) and D_STRIDES[i + 1] == 2
+            if cur_is_parity:
+                act = ops.instnorm_apply_parity(raw, st, act=L.ACT_LRELU, slope=0.01)
+            else:
+                act = ops.instnorm_apply(raw, st, act=L.ACT_LRELU, slope=0.01)
             if save:
                 layers.append((xin, raw, st))
             cur = act

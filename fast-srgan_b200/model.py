@@ -40,7 +40,6 @@ class _NetFn(torch.autograd.Function):
         net.fp.version += 1                  # an external optimizer may have stepped the (aliased) parameters in place
         y, c = net.forward(x.contiguous().float(), save=True)
         ctx.net, ctx.c, ctx.kind = net, c, module._fsr_kind
-        ctx.need_dx = x.requires_grad
         ctx.x_shape = tuple(x.shape)
         return y
 
@@ -53,7 +52,7 @@ class _NetFn(torch.autograd.Function):
         if ctx.kind == "G":
             net.backward(ctx.c, dy)          # image gradient of the generator input is never needed (model.py:75: leaf)
         else:
-            if ctx.need_dx:
+            if ctx.needs_input_grad[1]:
                 dx = torch.zeros(ctx.x_shape, dtype=torch.float32, device=dy.device)
             net.backward(ctx.c, dy, wgrad=True, d_img=dx)
         grads = tuple(net.fp.g[n].clone() for n in net.fp.names)
@@ -327,7 +326,7 @@ class Generator(torch.nn.Module):
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         self._require_cuda(x)
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             # training through autograd (trainer.py:108,185): hand-written forward + backward kernels behind a Function
             return _NetFn.apply(self, x, *self.parameters())
         x = x.contiguous().float()
@@ -392,7 +391,7 @@ class Discriminator(torch.nn.Module):
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         Generator._require_cuda(x)
-        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+        if torch.is_grad_enabled() and (x.requires_grad or (self.training and any(p.requires_grad for p in self.parameters()))):
             return _NetFn.apply(self, x, *self.parameters()).unsqueeze(1)      # trainer.py:172,174,186
         net = self._engine()
         net.fp.version += 1            # parameters may have been changed by the caller (load_state_dict / optimizer)

@@ -164,6 +164,16 @@ def instnorm_apply(raw, stats, act=L.ACT_NONE, slope=0.0, alpha=None, residual=N
     return out
 
 
+def instnorm_apply_parity(raw, stats, act=L.ACT_NONE, slope=0.0, alpha=None, eps=1e-5):
+    """instnorm_apply whose output is written directly in the parity-plane layout [N,4,H/2,W/2,C] (input of a stride-2 conv)."""
+    _cuda(raw, stats, alpha)
+    N, H, W, C = raw.shape
+    out = torch.empty((N, 4, H // 2, W // 2, C), dtype=raw.dtype, device=raw.device)
+    L.check(L.load().fsr_instnorm_apply_parity(raw.data_ptr(), stats.data_ptr(), out.data_ptr(), L.ptr(alpha), N, H, W, C, act, slope,
+                                               eps, L.dtype_code(raw.dtype), L.stream_ptr(raw.device)), "instnorm apply (parity out)")
+    return out
+
+
 def pixel_shuffle2(x):
     """NHWC [N,H,W,4C] (reference channel order) -> [N,2H,2W,C]  (model.py:36)."""
     _cuda(x)

@@ -98,6 +98,11 @@ int fsr_neck_conv3x3(const void* x, const float* w, const float* bias, const flo
  * :132-133 (SimpleBlock bn + LeakyReLU).  raw/out/residual NHWC dtype [N,HW,C]; stats [N,C,2] int64 fixed point. */
 int fsr_instnorm_apply(const void* raw, const int64_t* stats, const void* residual, void* out, const float* alpha,
                        int N, int HW, int C, int act, float slope, float eps, int dtype, void* stream);
+/* same normalise + activation, output written in the parity-plane layout [N][4][H/2][W/2][C] that the stride-2
+ * fsr_conv3x3_gen reads (SimpleBlock with stride 2, model.py:148-183): folds fsr_parity_layout into this pass.
+ * H, W even; out must not alias raw. */
+int fsr_instnorm_apply_parity(const void* raw, const int64_t* stats, void* out, const float* alpha, int N, int H, int W, int C,
+                              int act, float slope, float eps, int dtype, void* stream);
 
 /* torch.nn.PixelShuffle(2) (model.py:36) on NHWC: in [N,H,W,4C] (reference channel order) -> out [N,2H,2W,C]. */
 int fsr_pixel_shuffle2(const void* in, void* out, int N, int H, int W, int C, int dtype, void* stream);
@@ -292,6 +297,10 @@ int fsr_set_fuse_in(int on);
  * and group instead of per tile: 2.3x less L2->smem traffic, same results bit for bit); 0: per-tile weight streaming;
  * -1: environment default (FSR_GEN_WS). */
 int fsr_set_gen_ws(int on);
+/* 1 (default): fsr_conv3x3_gen with Cout % 128 == 0 runs as a CTA-pair kernel (tcgen05 cta_group::2, M = 256, 128-wide
+ * output-channel slices: half the shared-memory operand traffic per MMA); 0: the 64-wide single-CTA kernels;
+ * -1: environment default (FSR_GEN_2CTA).  Same results bit for bit. */
+int fsr_set_gen_2cta(int on);
 
 /* 1 (default): the 3-channel-sided convs (fsr_neck_conv3x3, fsr_wgrad_c3) run on warp-level tensor-core MMAs
  * (mma.sync m16n8k16, fp32 operand split hi+lo: fp32-input accuracy); 0: the CUDA-core kernels (A/B and tests);

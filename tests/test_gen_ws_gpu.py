@@ -16,8 +16,10 @@ def _setup():
     from fast_srgan_b200 import _lib
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
+    _lib.load().fsr_set_gen_2cta(0)          # this file compares the two single-CTA kernels (the CTA-pair kernel: test_gen_2cta_gpu.py)
     yield
     _lib.load().fsr_set_gen_ws(-1)
+    _lib.load().fsr_set_gen_2cta(-1)
 
 
 def rnd(shape, seed, scale=1.0):
