@@ -15,6 +15,9 @@ EPI_RAW_STATS, EPI_BIAS_ACT, EPI_PS_PRELU, EPI_HEAD_TANH, EPI_F32 = 0, 1, 2, 3, 
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_PRELU = 0, 1, 2, 3
 K_NONE, K_NECK, K_CONV_RES, K_IN_APPLY, K_CONV_UP, K_CONV_HEAD, K_CONV_BIAS_ACT, K_CONV_GEN, K_CONV_WGRAD = -1, 0, 1, 2, 3, 4, 5, 6, 7
 
+(OPT_HALO1, OPT_WS, OPT_FUSE_IN, OPT_FUSE_RES, OPT_UP_2CTA, OPT_GEN_WS, OPT_GEN_2CTA, OPT_SMALL_MMA, OPT_IN_BWD_FUSED,
+ OPT_OVERLAP_STREAMS) = range(10)
+
 _vp, _fp, _i, _f, _sz = C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_size_t
 
 
@@ -83,6 +86,10 @@ _SIGS = {
     "fsr_psnr_ssim": (_i, [_fp, _fp, _i, _i, _i, _i, _f, _f, _f, _vp, _vp, _vp, _vp]),
     "fsr_crop_resize_aa": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _fp, _fp, _vp]),
     "fsr_set_overlap_streams": (_i, [_i]),
+    "fsr_ctx_create": (_i, [C.POINTER(_vp)]),
+    "fsr_ctx_destroy": (_i, [_vp]),
+    "fsr_ctx_set": (_i, [_vp, _i, _i]),
+    "fsr_ctx_bind": (_i, [_vp]),
     "fsr_split_f32": (_i, [_fp, _vp, _vp, _sz, _vp]),
     "fsr_neck_conv3x3_f32": (_i, [_fp, _fp, _fp, _fp, _fp, _i, _i, _i, _vp]),
     "fsr_in_stats_f32": (_i, [_fp, _vp, _i, _i, _vp]),

@@ -20,11 +20,25 @@
 #include <cstring>
 #include <cmath>
 #include <mutex>
+#include <new>
 #include <vector>
 
 using namespace fsr;
 
 namespace {
+
+// Caller-owned context (include/fsr_b200.h "contexts"): option overrides + the side streams / events of the sub-batch
+// overlap.  Bound per THREAD (fsr_ctx_bind); an unbound thread uses the process-wide defaults below.
+enum { kOptHalo1 = 0, kOptWs, kOptFuseIn, kOptFuseRes, kOptUp2Cta, kOptGenWs, kOptGen2Cta, kOptSmallMma, kOptInBwdFused,
+       kOptOverlapStreams, kOptCount };
+struct FsrCtxImpl {
+  int opt[kOptCount];
+  cudaStream_t side[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t fork = nullptr, join[4] = {nullptr, nullptr, nullptr, nullptr};
+  FsrCtxImpl() { for (int& o : opt) o = -1; }
+};
+thread_local FsrCtxImpl* tl_ctx = nullptr;
+inline int ctx_opt(int key) { return tl_ctx ? tl_ctx->opt[key] : -1; }
 
 std::atomic<unsigned long long> g_launches{0};
 unsigned g_prof_mask = 0;            // bit k set: launches of kernel id k are bracketed with an event pair
@@ -144,6 +158,7 @@ int num_sms() {
 
 int g_halo1 = -1;   // A-operand staging: 0 = 3 column-shifted halo tiles, 1 = single halo tile (see conv3x3_tc.cuh)
 int halo_mode() {
+  if (ctx_opt(kOptHalo1) >= 0) return ctx_opt(kOptHalo1);
   if (g_halo1 < 0) {
     const char* e = getenv("FSR_HALO1");
     g_halo1 = (e && e[0] == '0') ? 0 : 1;   // default: single halo tile
@@ -153,6 +168,7 @@ int halo_mode() {
 
 int g_ws = -1;
 int ws_mode() {
+  if (ctx_opt(kOptWs) >= 0) return ctx_opt(kOptWs);
   if (g_ws < 0) {
     const char* e = getenv("FSR_WS");
     g_ws = (e && e[0] == '0') ? 0 : 1;   // default on: B200-measured ~5 % on the 64->64 conv, bit-identical results
@@ -162,6 +178,7 @@ int ws_mode() {
 
 int g_fuse_in = -1;   // Generator.forward: 1 = the res-block's first InstanceNorm + PReLU is applied inside conv2's load path
 int fuse_in_mode() {
+  if (ctx_opt(kOptFuseIn) >= 0) return ctx_opt(kOptFuseIn);
   if (g_fuse_in < 0) {
     const char* e = getenv("FSR_FUSE_IN");
     g_fuse_in = (e && e[0] == '0') ? 0 : 1;   // default ON: 3832 vs 3707 frames/s on the same box
@@ -171,6 +188,7 @@ int fuse_in_mode() {
 
 int g_fuse_res = -1;   // Generator.forward: 1 = bn2 + skip of block l is applied inside conv1 of block l+1 (XF == 2)
 int fuse_res_mode() {
+  if (ctx_opt(kOptFuseRes) >= 0) return ctx_opt(kOptFuseRes);
   if (g_fuse_res < 0) {
     const char* e = getenv("FSR_FUSE_RES");
     g_fuse_res = (e && e[0] == '1') ? 1 : 0;   // default OFF: measured 578 us vs 172 + 109 us unfused (profiles/r02)
@@ -180,6 +198,7 @@ int fuse_res_mode() {
 
 int g_up_2cta = -1;    // 64 -> 256 upsampling conv: 1 = CTA-pair kernel (tcgen05 cta_group::2, conv3x3_up_2cta.cuh)
 int up_2cta_mode() {
+  if (ctx_opt(kOptUp2Cta) >= 0) return ctx_opt(kOptUp2Cta);
   if (g_up_2cta < 0) {
     const char* e = getenv("FSR_UP_2CTA");
     g_up_2cta = (e && e[0] == '0') ? 0 : 1;
@@ -189,6 +208,7 @@ int up_2cta_mode() {
 
 int g_in_bwd_fused = -1;   // InstanceNorm backward: 1 = single-launch kernel for planes <= 64x64 (train_kernels.cuh)
 int in_bwd_fused_mode() {
+  if (ctx_opt(kOptInBwdFused) >= 0) return ctx_opt(kOptInBwdFused);
   if (g_in_bwd_fused < 0) {
     const char* e = getenv("FSR_IN_BWD_FUSED");
     g_in_bwd_fused = (e && e[0] == '0') ? 0 : 1;
@@ -198,6 +218,7 @@ int in_bwd_fused_mode() {
 
 int g_small_mma = -1;   // 3-channel-sided convs (neck / wgrad_c3): 1 = mma.sync tensor-core kernels (small_mma.cuh), 0 = CUDA cores
 int small_mma_mode() {
+  if (ctx_opt(kOptSmallMma) >= 0) return ctx_opt(kOptSmallMma);
   if (g_small_mma < 0) {
     const char* e = getenv("FSR_SMALL_MMA");
     g_small_mma = (e && e[0] == '0') ? 0 : 1;
@@ -350,6 +371,7 @@ int conv_dispatch(const void* x, const void* w_packed, void* out, const float* b
 // ------------------------------------------------------------------ general conv (conv3x3_gen.cuh)
 int g_gen_ws = -1;   // general conv: 1 = weight-stationary over 4-tile groups (conv3x3_gen_ws.cuh), 0 = per-tile weight streaming
 int gen_ws_mode() {
+  if (ctx_opt(kOptGenWs) >= 0) return ctx_opt(kOptGenWs);
   if (g_gen_ws < 0) {
     const char* e = getenv("FSR_GEN_WS");
     g_gen_ws = (e && e[0] == '0') ? 0 : 1;
@@ -359,6 +381,7 @@ int gen_ws_mode() {
 
 int g_gen_2cta = -1;   // general conv, Cout % 128 == 0: 1 = CTA-pair kernel with 128-wide slices (conv3x3_gen_2cta.cuh)
 int gen_2cta_mode() {
+  if (ctx_opt(kOptGen2Cta) >= 0) return ctx_opt(kOptGen2Cta);
   if (g_gen_2cta < 0) {
     const char* e = getenv("FSR_GEN_2CTA");
     g_gen_2cta = (e && e[0] == '0') ? 0 : 1;
@@ -897,6 +920,7 @@ int g_overlap = -1;
 cudaStream_t g_side[4] = {nullptr, nullptr, nullptr, nullptr};
 cudaEvent_t g_fork = nullptr, g_join[4] = {nullptr, nullptr, nullptr, nullptr};
 int overlap_parts() {
+  if (ctx_opt(kOptOverlapStreams) >= 1) return ctx_opt(kOptOverlapStreams) > 4 ? 4 : ctx_opt(kOptOverlapStreams);
   if (g_overlap < 0) {
     const char* e = getenv("FSR_STREAMS");
     g_overlap = e ? atoi(e) : 1;   // measured on B200 (power-capped): 2-4 sub-batches overlap but do not shorten the step
@@ -1002,15 +1026,20 @@ int fsr_generator_forward(const FsrGeneratorParams* prm, const void* x, void* y,
   if (group > 0 && group < N) { per = group; }
   else { parts = overlap_parts(); if (parts > N) parts = N; per = (N + parts - 1) / parts; }
   const bool concurrent = !(group > 0 && group < N) && parts > 1;
+  // the bound context owns its side streams / events (two generators on two streams never share them); unbound callers
+  // share the process-wide set and must not run fsr_generator_forward concurrently with overlap_streams > 1
+  cudaStream_t* side = tl_ctx ? tl_ctx->side : g_side;
+  cudaEvent_t* join = tl_ctx ? tl_ctx->join : g_join;
+  cudaEvent_t& fork = tl_ctx ? tl_ctx->fork : g_fork;
   if (concurrent) {
-    if (!g_fork) {
-      FSR_CUDA(cudaEventCreateWithFlags(&g_fork, cudaEventDisableTiming));
+    if (!fork) {
+      FSR_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
       for (int i = 0; i < 4; ++i) {
-        FSR_CUDA(cudaStreamCreateWithFlags(&g_side[i], cudaStreamNonBlocking));
-        FSR_CUDA(cudaEventCreateWithFlags(&g_join[i], cudaEventDisableTiming));
+        FSR_CUDA(cudaStreamCreateWithFlags(&side[i], cudaStreamNonBlocking));
+        FSR_CUDA(cudaEventCreateWithFlags(&join[i], cudaEventDisableTiming));
       }
     }
-    FSR_CUDA(cudaEventRecord(g_fork, st));
+    FSR_CUDA(cudaEventRecord(fork, st));
   }
   const size_t img_bytes = (size_t)H * W * F * 2;
   const size_t in_img = in_u8 ? (size_t)H * W * 3 : (size_t)H * W * 3 * sizeof(float);
@@ -1020,8 +1049,8 @@ int fsr_generator_forward(const FsrGeneratorParams* prm, const void* x, void* y,
     const int nb = (N - n0 < per) ? (N - n0) : per;
     cudaStream_t s = st;
     if (concurrent && part > 0) {
-      s = g_side[part - 1];
-      FSR_CUDA(cudaStreamWaitEvent(s, g_fork, 0));
+      s = side[part - 1];
+      FSR_CUDA(cudaStreamWaitEvent(s, fork, 0));
     }
     rc = generator_chain(prm, reinterpret_cast<const uint8_t*>(x) + n0 * in_img, reinterpret_cast<uint8_t*>(y) + n0 * out_img,
                          b_res + n0 * img_bytes, b_x + n0 * img_bytes, b_x2 + n0 * img_bytes, b_raw + n0 * img_bytes, b_y + n0 * img_bytes,
@@ -1029,8 +1058,8 @@ int fsr_generator_forward(const FsrGeneratorParams* prm, const void* x, void* y,
                          nb, H, W, in_u8, out_u8, s);
     if (rc) return rc;
     if (concurrent && part > 0) {
-      FSR_CUDA(cudaEventRecord(g_join[part - 1], s));
-      FSR_CUDA(cudaStreamWaitEvent(st, g_join[part - 1], 0));
+      FSR_CUDA(cudaEventRecord(join[part - 1], s));
+      FSR_CUDA(cudaStreamWaitEvent(st, join[part - 1], 0));
     }
   }
   return FSR_OK;
@@ -1336,6 +1365,38 @@ int fsr_crop_resize_aa(const uint8_t* cache, const int64_t* img_off, const int32
   LaunchScope scope(FSR_K_NONE - 1, st);
   crop_resize_aa_kernel<<<dim3((unsigned)B, 3), 256, smem, st>>>(p);
   return cuda_rc(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------ contexts
+int fsr_ctx_create(void** ctx_out) {
+  if (!ctx_out) return FSR_ERR_BAD_ARG;
+  *ctx_out = new (std::nothrow) FsrCtxImpl();
+  return *ctx_out ? FSR_OK : FSR_ERR_BAD_ARG;
+}
+
+int fsr_ctx_destroy(void* ctx) {
+  auto* c = reinterpret_cast<FsrCtxImpl*>(ctx);
+  if (!c) return FSR_OK;
+  if (tl_ctx == c) tl_ctx = nullptr;
+  if (c->fork) cudaEventDestroy(c->fork);
+  for (int i = 0; i < 4; ++i) {
+    if (c->side[i]) cudaStreamDestroy(c->side[i]);
+    if (c->join[i]) cudaEventDestroy(c->join[i]);
+  }
+  delete c;
+  return FSR_OK;
+}
+
+int fsr_ctx_set(void* ctx, int option, int value) {
+  auto* c = reinterpret_cast<FsrCtxImpl*>(ctx);
+  if (!c || option < 0 || option >= kOptCount) return FSR_ERR_BAD_ARG;
+  c->opt[option] = value < 0 ? -1 : value;
+  return FSR_OK;
+}
+
+int fsr_ctx_bind(void* ctx) {
+  tl_ctx = reinterpret_cast<FsrCtxImpl*>(ctx);
+  return FSR_OK;
 }
 
 // ------------------------------------------------------------------ precise generator forward (precise.cuh)

@@ -307,6 +307,19 @@ int fsr_set_gen_2cta(int on);
  * -1: environment default (FSR_SMALL_MMA). */
 int fsr_set_small_mma(int on);
 
+/* ---- contexts: caller-owned option overrides + internal side streams (re-entrancy across host threads / streams).
+ * The fsr_set_* switches above are PROCESS-wide defaults.  A context carries its own values of the same switches and
+ * its own side streams / events for the sub-batch overlap of fsr_generator_forward; fsr_ctx_bind makes it the calling
+ * THREAD's current context for every later fsr_* call of that thread (NULL unbinds).  Two host threads, each with its
+ * own context, stream, workspace and buffers, may drive the library concurrently (tests/test_capi_ctx_gpu.py).
+ * fsr_ctx_set(ctx, option, value): value -1 = inherit the process default. */
+enum { FSR_OPT_HALO1 = 0, FSR_OPT_WS = 1, FSR_OPT_FUSE_IN = 2, FSR_OPT_FUSE_RES = 3, FSR_OPT_UP_2CTA = 4, FSR_OPT_GEN_WS = 5,
+       FSR_OPT_GEN_2CTA = 6, FSR_OPT_SMALL_MMA = 7, FSR_OPT_IN_BWD_FUSED = 8, FSR_OPT_OVERLAP_STREAMS = 9 };
+int fsr_ctx_create(void** ctx_out);
+int fsr_ctx_destroy(void* ctx);
+int fsr_ctx_set(void* ctx, int option, int value);
+int fsr_ctx_bind(void* ctx);
+
 /* ---- PRECISE generator forward (Generator(compute_dtype=torch.float32); model.py:112-117 at ~fp32 accuracy).
  * The shipped checkpoint needs more than 16-bit operands for north_star's 1e-3 (fp16 measures 3.4e-3):
  * activations are stored fp32 NHWC and split a = a_hi + a_lo into two fp16 planes (fsr_split_f32 or the hi/lo outputs
