@@ -53,7 +53,7 @@ _SIGS = {
     "fsr_smooth_l1": (_i, [_vp, _vp, _sz, _fp, _vp, _f, _i, _vp]),
     "fsr_instnorm_bwd": (_i, [_vp, _fp, _vp, _fp, _vp, _fp, _fp, _i, _i, _i, _i, _f, _f, _i, _vp]),
     "fsr_act_bwd": (_i, [_vp, _vp, _vp, _sz, _fp, _f, _i, _fp, _i, _vp]),
-    "fsr_ps_prelu_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _fp, _fp, _i, _vp]),
+    "fsr_ps_prelu_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _fp, _fp, _i, _vp]),
     "fsr_tanh_bwd": (_i, [_fp, _fp, _fp, _sz, _vp]),
     "fsr_wgrad_c3": (_i, [_fp, _vp, _fp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "fsr_bias_grad": (_i, [_vp, _fp, _sz, _i, _i, _i, _vp]),

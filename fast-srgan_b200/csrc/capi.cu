@@ -1238,14 +1238,14 @@ int fsr_act_bwd(const void* y, const void* dy, void* dv, size_t n_elems, const f
   return cuda_rc(cudaGetLastError());
 }
 
-int fsr_ps_prelu_bwd(const void* U, const void* dU, void* dconv, int N, int H, int W, const float* alpha, float* dalpha,
+int fsr_ps_prelu_bwd(const void* U, const void* dU, void* dconv, int N, int H, int W, int F, const float* alpha, float* dalpha,
                      int dtype, void* stream) {
-  if (!U || !dU || !dconv || !alpha) return FSR_ERR_BAD_ARG;
+  if (!U || !dU || !dconv || !alpha || F <= 0 || F % 8) return FSR_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t total = (size_t)N * H * W * 32;
+  const size_t total = (size_t)N * H * W * 4 * (F / 8);
   LaunchScope scope(FSR_K_NONE - 1, st);
-  FSR_T((ps_prelu_bwd_kernel<__half><<<ew_blocks(total), 256, 0, st>>>((const __half*)U, (const __half*)dU, (__half*)dconv, N, H, W, alpha, dalpha)),
-        (ps_prelu_bwd_kernel<__nv_bfloat16><<<ew_blocks(total), 256, 0, st>>>((const __nv_bfloat16*)U, (const __nv_bfloat16*)dU, (__nv_bfloat16*)dconv, N, H, W, alpha, dalpha)));
+  FSR_T((ps_prelu_bwd_kernel<__half><<<ew_blocks(total), 256, 0, st>>>((const __half*)U, (const __half*)dU, (__half*)dconv, N, H, W, F, alpha, dalpha)),
+        (ps_prelu_bwd_kernel<__nv_bfloat16><<<ew_blocks(total), 256, 0, st>>>((const __nv_bfloat16*)U, (const __nv_bfloat16*)dU, (__nv_bfloat16*)dconv, N, H, W, F, alpha, dalpha)));
   return cuda_rc(cudaGetLastError());
 }
 

@@ -457,24 +457,27 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const uint4* __restrict__ 
 }
 
 // ------------------------------------------------------------------ UpSamplingBlock backward glue (model.py:39-40)
-// U = PReLU(PixelShuffle(conv + bias)) stored NHWC [N,2H,2W,64]; dU same shape.
-// dConv[n,y,x,q*64+c] = dU[n,2y+i,2x+j,c] * (U >= 0 ? 1 : alpha)   (q = 2i+j: the packed/permuted column order)
+// U = PReLU(PixelShuffle(conv + bias)) stored NHWC [N,2H,2W,F]; dU same shape.
+// dConv[n,y,x,q*F+c] = dU[n,2y+i,2x+j,c] * (U >= 0 ? 1 : alpha)   (q = 2i+j: the packed/permuted column order)
+// (the sign of the pre-activation is taken from the stored output: valid for a positive slope, which is what
+//  torch.nn.PReLU's 0.25 init stays at in practice; DESIGN.md section 9 lists this limitation)
 template <typename T>
 __global__ void __launch_bounds__(256) ps_prelu_bwd_kernel(const T* __restrict__ U, const T* __restrict__ dU,
-                                                           T* __restrict__ dconv, int N, int H, int W,
+                                                           T* __restrict__ dconv, int N, int H, int W, int F,
                                                            const float* __restrict__ alpha, float* dalpha) {
   const float slope = __ldg(alpha);
   const float inv = slope != 0.f ? 1.0f / slope : 0.f;
-  const size_t total = (size_t)N * H * W * 4 * 8;   // (pixel, q, 8-channel vector)
+  const int vpc = F >> 3;                           // 8-channel vectors per output pixel
+  const size_t total = (size_t)N * H * W * 4 * vpc;   // (pixel, q, 8-channel vector)
   float da = 0.f;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-    const int cv = (int)(idx & 7);
-    const int q = (int)((idx >> 3) & 3);
-    const size_t pix = idx >> 5;
+    const int cv = (int)(idx % vpc);
+    const int q = (int)((idx / vpc) & 3);
+    const size_t pix = idx / (4 * (size_t)vpc);
     const int x = (int)(pix % W);
     const int y = (int)((pix / W) % H);
     const int n = (int)(pix / ((size_t)W * H));
-    const size_t src = (((size_t)n * 2 * H + 2 * y + (q >> 1)) * (2 * W) + 2 * x + (q & 1)) * 64 + cv * 8;
+    const size_t src = (((size_t)n * 2 * H + 2 * y + (q >> 1)) * (2 * W) + 2 * x + (q & 1)) * F + cv * 8;
     const uint4 a = *reinterpret_cast<const uint4*>(U + src), g = *reinterpret_cast<const uint4*>(dU + src);
     const uint32_t au[4] = {a.x, a.y, a.z, a.w}, gu[4] = {g.x, g.y, g.z, g.w};
     uint32_t o[4];
@@ -486,7 +489,7 @@ __global__ void __launch_bounds__(256) ps_prelu_bwd_kernel(const T* __restrict__
       if (f.y < 0.f) { da += d.y * f.y * inv; g1 *= slope; }
       o[k] = Cvt<T>::pack2(g0, g1);
     }
-    *reinterpret_cast<uint4*>(dconv + pix * 256 + q * 64 + cv * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<uint4*>(dconv + pix * 4 * F + q * F + cv * 8) = make_uint4(o[0], o[1], o[2], o[3]);
   }
   if (dalpha) {
     da = warp_sum(da);

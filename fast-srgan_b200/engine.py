@@ -146,21 +146,25 @@ class FlatParams:
 
 # ====================================================================================== Generator
 class GeneratorNet:
-    """model.py:72-117 forward (saving activations) and backward."""
+    """model.py:72-117 forward (saving activations) and backward.  n_filters = 64 (the reference default) runs on the
+    resident-weight 64-channel kernels; n_filters = 128, 192, ... (multiples of 64; BASELINE config #5) on the general
+    convs (CTA-pair kernel for the 128-wide slices)."""
 
     def __init__(self, module, fp: FlatParams, dtype: torch.dtype):
-        if module.n_filters != 64:
-            raise RuntimeError("the training engine (backward kernels) is built for generator.n_filters == 64; "
-                               "other widths are supported for inference only")
+        if module.n_filters % 64:
+            raise RuntimeError("the training engine (backward kernels) is built for generator.n_filters in {64, 128, 192, ...}; "
+                               "other widths (e.g. 32) are supported for inference only")
         self.m, self.fp, self.dt = module, fp, dtype
         self.L = module.n_layers
+        self.F = module.n_filters
+        self.c64 = self.F == 64
         self._packed_version = -1
         self._bwd_version = -1
         self.P: Dict[str, torch.Tensor] = {}
         self.arena: Optional[ZeroArena] = None             # set by GANEngine: statistics buffers zeroed once per step
 
-    def _stats(self, x, cout=64):
-        return self.arena.take(x.shape[0], cout, x.device) if self.arena is not None else None
+    def _stats(self, x, cout=None):
+        return self.arena.take(x.shape[0], cout or self.F, x.device) if self.arena is not None else None
 
     def _convs64(self):
         names = []
@@ -181,7 +185,9 @@ class GeneratorNet:
             if fwd_stale:
                 P[n], _ = ops.pack_conv3x3(p[n], None, dt, out_w=P.get(n))
             if need_bwd:
-                P[n + ".t"] = ops.pack_conv3x3_t(p[n], dt, flip=True, out=P.get(n + ".t"))          # c64-kernel dgrad
+                # data-gradient pack: the 64-channel kernel takes flipped taps (forward tap table), the general kernel its own
+                # dgrad tap table (mode 1) on the unflipped transposed pack
+                P[n + ".t"] = ops.pack_conv3x3_t(p[n], dt, flip=self.c64, out=P.get(n + ".t"))
         for i in range(2):
             w, b = p[f"upsampling.{i}.conv.weight"], p[f"upsampling.{i}.conv.bias"]
             if fwd_stale:
@@ -192,45 +198,65 @@ class GeneratorNet:
             P["head.w"], P["head.b"] = ops.pack_conv3x3(p["head.0.weight"], p["head.0.bias"], dt, cout_pad=16,
                                                         out_w=P.get("head.w"), out_b=P.get("head.b"))
         if need_bwd:
-            # head dgrad = direct 3->64 conv with transposed, flipped weights (K = 27: CUDA cores)
+            # head dgrad = direct 3->F conv with transposed, flipped weights (K = 27)
             if "head.t" not in P:
-                P["head.t"] = torch.empty((64, 3, 3, 3), dtype=torch.float32, device=p["head.0.weight"].device)
+                P["head.t"] = torch.empty((self.F, 3, 3, 3), dtype=torch.float32, device=p["head.0.weight"].device)
             P["head.t"].copy_(p["head.0.weight"].permute(1, 0, 2, 3).flip(2, 3))
             self._bwd_version = self.fp.version
         self._packed_version = self.fp.version
 
+    # ---- the width-dependent kernels
+    def _conv_raw(self, x, w):
+        if self.c64:
+            return ops.conv3x3_c64_raw_stats(x, w, stats=self._stats(x))
+        return ops.conv3x3_gen(x, w, self.F, epilogue=L.EPI_RAW_STATS, stats=self._stats(x))
+
+    def _conv_up(self, x, i):
+        p, P = self.fp.p, self.P
+        if self.c64:
+            return ops.conv3x3_c64_ps_prelu(x, P[f"up{i}.w"], P[f"up{i}.b"], p[f"upsampling.{i}.relu.weight"])
+        return ops.conv3x3_gen(x, P[f"up{i}.w"], 4 * self.F, epilogue=L.EPI_PS_PRELU, bias=P[f"up{i}.b"], alpha=p[f"upsampling.{i}.relu.weight"])
+
+    def _dgrad(self, dy, name):
+        if self.c64:
+            return ops.conv3x3_c64_bias_act(dy, self.P[name + ".t"], None)
+        return ops.conv3x3_gen(dy, self.P[name + ".t"], self.F, mode=1)
+
     def forward(self, lr_img: torch.Tensor, save: bool, out: Optional[torch.Tensor] = None):
         """out: optional fp32 NCHW [N,3,4h,4w] destination of sr (a slice of the step's [sr; hr] image batch).
-        save: the inputs of the 2L+1 64->64 convs are written into ONE arena [2L+1][N,h,w,64] (slot 2i = input of block i's
+        save: the inputs of the 2L+1 F->F convs are written into ONE arena [2L+1][N,h,w,F] (slot 2i = input of block i's
         conv1, 2i+1 = input of its conv2, 2L = input of the bottleneck conv) so that their weight gradients run as a
         single grouped launch in backward()."""
         self.pack(need_bwd=save)
-        p, P, dt = self.fp.p, self.P, self.dt
+        p, P, dt, Fm = self.fp.p, self.P, self.dt, self.F
         N, _, h, w = lr_img.shape
         Lb = self.L
-        xa = torch.empty((2 * Lb + 1, N, h, w, 64), dtype=dt, device=lr_img.device) if save else None
+        xa = torch.empty((2 * Lb + 1, N, h, w, Fm), dtype=dt, device=lr_img.device) if save else None
         slot = (lambda k: xa[k]) if save else (lambda k: None)
         a0 = ops.neck_conv3x3(lr_img, p["neck.0.weight"], p["neck.0.bias"], dt, act=L.ACT_PRELU, alpha=p["neck.1.weight"], out=slot(0))
         cur, blocks = a0, []
         for i in range(Lb):
-            raw1, st1 = ops.conv3x3_c64_raw_stats(cur, P[f"stem.{i}.conv1.weight"], stats=self._stats(cur))
+            raw1, st1 = self._conv_raw(cur, P[f"stem.{i}.conv1.weight"])
             y1 = ops.instnorm_apply(raw1, st1, act=L.ACT_PRELU, alpha=p[f"stem.{i}.relu1.weight"], out=slot(2 * i + 1))
-            raw2, st2 = ops.conv3x3_c64_raw_stats(y1, P[f"stem.{i}.conv2.weight"], stats=self._stats(y1))
+            raw2, st2 = self._conv_raw(y1, P[f"stem.{i}.conv2.weight"])
             nxt = ops.instnorm_apply(raw2, st2, residual=cur, out=slot(2 * i + 2))
             if save:
                 blocks.append((raw1, st1, raw2, st2))
             cur = nxt
-        rawb, stb = ops.conv3x3_c64_raw_stats(cur, P["bottleneck.0.weight"], stats=self._stats(cur))
+        rawb, stb = self._conv_raw(cur, P["bottleneck.0.weight"])
         xb = ops.instnorm_apply(rawb, stb, residual=a0)
-        U0 = ops.conv3x3_c64_ps_prelu(xb, P["up0.w"], P["up0.b"], p["upsampling.0.relu.weight"])
-        U1 = ops.conv3x3_c64_ps_prelu(U0, P["up1.w"], P["up1.b"], p["upsampling.1.relu.weight"])
-        sr = ops.conv3x3_c64_head(U1, P["head.w"], P["head.b"], out=out)
+        U0 = self._conv_up(xb, 0)
+        U1 = self._conv_up(U0, 1)
+        if self.c64:
+            sr = ops.conv3x3_c64_head(U1, P["head.w"], P["head.b"], out=out)
+        else:
+            sr = ops.conv3x3_head(U1, P["head.w"], P["head.b"], out_mode=0, out=out)
         ctx = dict(lr=lr_img, a0=a0, xa=xa, blocks=blocks, rawb=rawb, stb=stb, xb=xb, U0=U0, U1=U1, sr=sr) if save else None
         return sr, ctx
 
     def backward(self, ctx, d_sr: torch.Tensor):
         """d_sr: fp32 NCHW gradient w.r.t. the generator output; accumulates into fp.g."""
-        p, g, P, dt = self.fp.p, self.fp.g, self.P, self.dt
+        p, g, P, dt, Fm = self.fp.p, self.fp.g, self.P, self.dt, self.F
         Lb = self.L
         dpre = ops.tanh_bwd(ctx["sr"], d_sr)                                           # model.py:109
         ops.wgrad_c3(dpre, ctx["U1"], g["head.0.weight"], flip=True, layout=1)
@@ -240,23 +266,26 @@ class GeneratorNet:
             dconv = ops.ps_prelu_bwd(U, dU, p[f"upsampling.{i}.relu.weight"], g[f"upsampling.{i}.relu.weight"])
             ops.conv3x3_wgrad(xin, dconv, g[f"upsampling.{i}.conv.weight"], ps_perm=True)
             ops.bias_grad(dconv, g[f"upsampling.{i}.conv.bias"], ps_perm=True)
-            dU = ops.conv3x3_gen(dconv, P[f"up{i}.t"], 64, mode=1)
+            dU = ops.conv3x3_gen(dconv, P[f"up{i}.t"], Fm, mode=1)
         dxb = dU
-        # output gradients of the 2L+1 64->64 convs, same slot order as the input arena of forward()
+        # output gradients of the 2L+1 F->F convs, same slot order as the input arena of forward()
         xa = ctx["xa"]
         da = torch.empty_like(xa)
         ops.instnorm_bwd(ctx["rawb"], ctx["stb"], dxb, out=da[2 * Lb])                  # model.py:94
-        dcur = ops.conv3x3_c64_bias_act(da[2 * Lb], P["bottleneck.0.weight.t"], None)
+        dcur = self._dgrad(da[2 * Lb], "bottleneck.0.weight")
         for i in reversed(range(Lb)):                                                   # model.py:67-69
             raw1, st1, raw2, st2 = ctx["blocks"][i]
             ops.instnorm_bwd(raw2, st2, dcur, out=da[2 * i + 1])
-            dy1 = ops.conv3x3_c64_bias_act(da[2 * i + 1], P[f"stem.{i}.conv2.weight.t"], None)
+            dy1 = self._dgrad(da[2 * i + 1], f"stem.{i}.conv2.weight")
             ops.instnorm_bwd(raw1, st1, dy1, act=L.ACT_PRELU, alpha=p[f"stem.{i}.relu1.weight"],
                              dalpha=g[f"stem.{i}.relu1.weight"], out=da[2 * i])
-            din = ops.conv3x3_c64_bias_act(da[2 * i], P[f"stem.{i}.conv1.weight.t"], None)
+            din = self._dgrad(da[2 * i], f"stem.{i}.conv1.weight")
             dcur = ops.add(din, dcur)                                                   # + skip (model.py:69)
-        # all 2L+1 weight gradients of the residual chain: ONE grouped tcgen05 launch + its fixed-order reduction
-        ops.conv3x3_wgrad_grouped(xa, da, [g[n] for n in self._convs64()])
+        # all 2L+1 weight gradients of the residual chain: grouped tcgen05 launches (<= 148 (group, cin, cout) pairs each)
+        names = self._convs64()
+        per = max(1, 148 // ((Fm // 64) ** 2))
+        for k0 in range(0, len(names), per):
+            ops.conv3x3_wgrad_grouped(xa[k0:k0 + per], da[k0:k0 + per], [g[n] for n in names[k0:k0 + per]])
         da0 = ops.add(dcur, dxb)                                                        # + long skip (model.py:115)
         dv = ops.act_bwd(ctx["a0"], da0, L.ACT_PRELU, alpha=p["neck.1.weight"], dalpha=g["neck.1.weight"])
         ops.wgrad_c3(ctx["lr"], dv, g["neck.0.weight"], flip=False, layout=2)           # model.py:76

@@ -394,8 +394,8 @@ def ps_prelu_bwd(U, dU, alpha, dalpha=None):
     _cuda(U, dU, alpha, dalpha)
     N, H2, W2, C = U.shape
     H, W = H2 // 2, W2 // 2
-    dconv = torch.empty((N, H, W, 256), dtype=U.dtype, device=U.device)
-    L.check(L.load().fsr_ps_prelu_bwd(U.data_ptr(), dU.data_ptr(), dconv.data_ptr(), N, H, W, alpha.data_ptr(), L.ptr(dalpha),
+    dconv = torch.empty((N, H, W, 4 * C), dtype=U.dtype, device=U.device)
+    L.check(L.load().fsr_ps_prelu_bwd(U.data_ptr(), dU.data_ptr(), dconv.data_ptr(), N, H, W, C, alpha.data_ptr(), L.ptr(dalpha),
                                       L.dtype_code(U.dtype), L.stream_ptr(U.device)), "ps prelu bwd")
     return dconv
 

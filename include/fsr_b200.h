@@ -165,8 +165,8 @@ int fsr_instnorm_bwd(const void* raw, const int64_t* stats, const void* dy, floa
 /* activation backward from the stored post-activation tensor (neck PReLU / LeakyReLU). */
 int fsr_act_bwd(const void* y, const void* dy, void* dv, size_t n_elems, const float* alpha, float slope, int act,
                 float* dalpha, int dtype, void* stream);
-/* UpSamplingBlock (model.py:39-40) backward glue: dU [N,2H,2W,64] -> dConv [N,H,W,256] (permuted columns). */
-int fsr_ps_prelu_bwd(const void* U, const void* dU, void* dconv, int N, int H, int W, const float* alpha, float* dalpha,
+/* UpSamplingBlock (model.py:39-40) backward glue: dU [N,2H,2W,F] -> dConv [N,H,W,4F] (permuted columns). */
+int fsr_ps_prelu_bwd(const void* U, const void* dU, void* dconv, int N, int H, int W, int F, const float* alpha, float* dalpha,
                      int dtype, void* stream);
 /* head tanh backward (model.py:109): dpre = dy * (1 - y^2), fp32 NCHW. */
 int fsr_tanh_bwd(const float* y, const float* dy, float* dpre, size_t n, void* stream);

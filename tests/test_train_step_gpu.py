@@ -156,6 +156,40 @@ def test_generator_forward_is_identical_before_and_after_the_d_step():
     assert torch.equal(a, b) and torch.equal(e._sr, b)
 
 
+def test_gan_train_step_generator_width_128_vs_fp64_oracle():
+    """BASELINE config #5 widths in TRAINING: generator.n_filters = 128 runs the same step on the general-channel kernels
+    (CTA-pair conv for the 128-wide slices, grouped weight gradients with 4 (cin, cout) pairs per layer, F-channel
+    pixel-shuffle backward).  Losses and generator gradients against the fp64 oracle."""
+    import contextlib
+    from fast_srgan_b200.trainer import Trainer
+    dt, B, Fm, Lb = torch.float16, 2, 128, 2
+    c = lambda sd: {k: v.double().clone() for k, v in sd.items()}
+    og, od, ov = c(O.make_generator_state(Fm, Lb, 77)), c(O.make_discriminator_state(64, 4321)), c(O.make_vgg19_state(99))
+    lr_img, hr_img = seeded((B, 3, 24, 24), 21), seeded((B, 3, 96, 96), 22)
+    gn = torch.Generator().manual_seed(23)
+    noise = {k: torch.rand((B, 1, 6, 6), generator=gn) for k in ("d_real", "d_fake", "g_real")}
+    res = O.gan_step(og, od, ov, lr_img.double(), hr_img.double(), {k: v.double() for k, v in noise.items()},
+                     O.AdamWState(og, 1e-4), O.AdamWState(od, 1e-4))
+    cfg = ns(experiment=ns(name="t", seed=0), generator=ns(n_filters=Fm, n_layers=Lb), discriminator=ns(n_filters=64, n_layers=7),
+             training=ns(device="cuda", generator_lr=1e-4, discriminator_lr=1e-4))
+    tr = Trainer(cfg, compute_dtype=dt, vgg_state_dict=O.make_vgg19_state(99))
+    tr.generator.load_state_dict(O.make_generator_state(Fm, Lb, 77))
+    tr.discriminator.load_state_dict(O.make_discriminator_state(64, 4321))
+    out = tr.train_step(lr_img, hr_img, noise=noise)
+    torch.cuda.synchronize()
+    for k in ("loss_real", "loss_fake", "adv_loss", "content_loss"):
+        print(f"{k}: engine {out[k].item():.6f} oracle {res[k].item():.6f}")
+        assert abs(out[k].item() - res[k].item()) <= 1.5e-3 * max(1.0, abs(res[k].item()))
+    e = tr.engine
+    for k, gref in res["g_grads"].items():
+        got = e.gp.g[k].double().cpu() / e.S
+        if gref.numel() > 1:
+            cos = (got.flatten() @ gref.flatten() / (got.norm() * gref.norm()).clamp_min(1e-30)).item()
+            rel = ((got - gref).norm() / gref.norm().clamp_min(1e-30)).item()
+            print(f"G(F=128) grad {k:28s} rel-L2 {rel:.3e} cos {cos:.4f}")
+            assert cos >= 0.95, (k, cos)
+
+
 def test_train_step_updates_inference_weights():
     """After a step the Generator module (inference path) must see the updated parameters."""
     tr, out, res, og, od = _run_step(torch.bfloat16)

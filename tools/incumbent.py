@@ -21,6 +21,8 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--steps", type=int, default=10)
 ap.add_argument("--no-compile", action="store_true")
 ap.add_argument("--no-train", action="store_true")
+ap.add_argument("--compile-mode", default="max-autotune", help="torch.compile mode; the reference uses max-autotune (trainer.py:23-26)")
+ap.add_argument("--compile-train", action="store_true", help="also time the GAN step with torch.compile'd G / D / VGG (trainer.py:23-26)")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 torch.backends.cudnn.benchmark = True
@@ -107,13 +109,14 @@ for name, dt in (("bf16", torch.bfloat16), ("fp16", torch.float16)):
 if not args.no_compile:
     try:
         t0 = time.time()
-        cg = torch.compile(gen)
+        cg = torch.compile(gen, mode=args.compile_mode)
 
         def run_c():
             with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
                 return cg(x)
         ms = timed(run_c, args.steps)
-        out["generator_compile_bf16"] = {"ms_per_step": round(ms, 3), "fps": round(32 / ms * 1e3, 1), "compile_s": round(time.time() - t0, 1)}
+        out["generator_compile_bf16"] = {"ms_per_step": round(ms, 3), "fps": round(32 / ms * 1e3, 1), "compile_s": round(time.time() - t0, 1),
+                                         "mode": args.compile_mode}
     except Exception as e:  # noqa: BLE001  (inductor needs a C compiler / triton: report, do not fail)
         out["generator_compile_bf16"] = {"error": repr(e)[:200]}
 del x
@@ -156,5 +159,14 @@ if not args.no_train:
         return loss_d
     ms = timed(step, args.steps)
     out["train_step_eager_bf16_b64"] = {"ms_per_step": round(ms, 3), "samples_per_s": round(B / ms * 1e3, 1)}
+    if args.compile_train and not args.no_compile:
+        try:
+            t0 = time.time()
+            G, D, V = (torch.compile(m, mode=args.compile_mode) for m in (G, D, V))    # trainer.py:23-26
+            ms = timed(step, args.steps)
+            out["train_step_compile_bf16_b64"] = {"ms_per_step": round(ms, 3), "samples_per_s": round(B / ms * 1e3, 1),
+                                                  "compile_s": round(time.time() - t0, 1), "mode": args.compile_mode}
+        except Exception as e:  # noqa: BLE001
+            out["train_step_compile_bf16_b64"] = {"error": repr(e)[:200]}
 
 print(json.dumps(out), flush=True)
