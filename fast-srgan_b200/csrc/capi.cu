@@ -617,7 +617,7 @@ int wgrad_dispatch(const void* x, const void* dy, float* const* dw, int groups, 
   FSR_CUDA(cudaGetLastError());
   {
     LaunchScope scope(FSR_K_NONE - 1, st);
-    wgrad_reduce_kernel<<<dim3(npairs_all, 8), 256, 0, st>>>(rp);
+    wgrad_reduce_kernel<<<dim3(npairs_all, 8, 9), 256, 0, st>>>(rp);
   }
   return cuda_rc(cudaGetLastError());
 }

@@ -199,46 +199,54 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_con
 }
 
 // Stage 2: dw[group][co][ci][tap] += sum over the pair's CTAs (fixed order) of their partial tiles.
-// grid (npairs_all, 8): block = one (group, cin chunk, cout slice) pair x 8 output channels.  256 threads = 64 input
-// channels x 4 split slices: slice s sums partials s, s+4, s+8, ... (independent loads in flight), the four slice sums
-// are added in fixed order through smem -> [9 taps][64 ci][8 co] in smem -> 8 runs of 576 contiguous floats.
+// grid (npairs_all, 8, 9): block = one (group, cin chunk, cout slice) pair x 8 output channels x one tap.  256 threads =
+// 64 input channels x 4 split slices: slice s sums partials s, s+4, s+8, ... four at a time (independent loads in
+// flight: a 1-pair layer has up to 148 partials), the four slice sums are then added in fixed order through smem.
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const __grid_constant__ WgradReduceParams p) {
-  __shared__ float sm[8][577];
   __shared__ float part[4][64][9];
-  const int pair_all = blockIdx.x, co0 = blockIdx.y * 8;
+  const int pair_all = blockIdx.x, co0 = blockIdx.y * 8, tap = blockIdx.z;
   const int KC = p.cin >> 6, NSL = p.cout >> 6;
   const int npairs = KC * NSL;
   const int grp = pair_all / npairs, pair = pair_all % npairs;
   const int kc = pair / NSL, sl = pair % NSL;
   const int ci = threadIdx.x & 63, s4 = threadIdx.x >> 6;
   const size_t slot_stride = (size_t)5 * 128 * 64;
-#pragma unroll 1
-  for (int tap = 0; tap < 9; ++tap) {
-    const int slot = p.slot_of_tap[tap];
-    const float* src = p.partial + (((size_t)(slot >> 1)) * 128 + (slot & 1) * 64 + ci) * 64 + co0;
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int c = s4; c < p.ctas_per_pair; c += 4) {
-      const float4* q = reinterpret_cast<const float4*>(src + (size_t)(pair_all + c * p.npairs_all) * slot_stride);
-      const float4 a = q[0], b = q[1];
-      acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
-      acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+  const int slot = p.slot_of_tap[tap];
+  const float* src = p.partial + (size_t)pair_all * slot_stride + (((size_t)(slot >> 1)) * 128 + (slot & 1) * 64 + ci) * 64 + co0;
+  const size_t cstride = (size_t)p.npairs_all * slot_stride;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  int c = s4;
+  for (; c + 12 < p.ctas_per_pair; c += 16) {          // 4 partials per trip: 8 independent 16-byte loads in flight
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float4* q = reinterpret_cast<const float4*>(src + (size_t)(c + 4 * u) * cstride);
+      v[2 * u] = q[0]; v[2 * u + 1] = q[1];
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) part[s4][ci][j] = acc[j];
-    __syncthreads();
-    if (s4 == 0) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) sm[j][ci * 9 + tap] = ((part[0][ci][j] + part[1][ci][j]) + part[2][ci][j]) + part[3][ci][j];
+    for (int u = 0; u < 4; ++u) {                        // fixed order: c, c+4, c+8, c+12
+      acc[0] += v[2 * u].x; acc[1] += v[2 * u].y; acc[2] += v[2 * u].z; acc[3] += v[2 * u].w;
+      acc[4] += v[2 * u + 1].x; acc[5] += v[2 * u + 1].y; acc[6] += v[2 * u + 1].z; acc[7] += v[2 * u + 1].w;
     }
-    __syncthreads();
   }
+  for (; c < p.ctas_per_pair; c += 4) {
+    const float4* q = reinterpret_cast<const float4*>(src + (size_t)c * cstride);
+    const float4 a = q[0], b = q[1];
+    acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+    acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) part[s4][ci][j] = acc[j];
+  __syncthreads();
+  // 512 results (64 ci x 8 co) by 256 threads: two each; dw[(co * cin + ci) * 9 + tap] is owned by exactly one thread
   float* dw = p.dw[grp];
-  for (int idx = threadIdx.x; idx < 8 * 576; idx += 256) {
-    const int j = idx / 576, e = idx - j * 576;
+  for (int idx = threadIdx.x; idx < 512; idx += 256) {
+    const int j = idx >> 6, c2 = idx & 63;
+    const float r = ((part[0][c2][j] + part[1][c2][j]) + part[2][c2][j]) + part[3][c2][j];
     const int col = sl * 64 + co0 + j;                // GEMM column = dY channel
     int co = col;
     if (p.ps_perm) { const int cq = p.cout >> 2; co = 4 * (col % cq) + col / cq; }
-    dw[((size_t)co * p.cin + kc * 64) * 9 + e] += sm[j][e];
+    dw[((size_t)co * p.cin + kc * 64 + c2) * 9 + tap] += r;
   }
 }
 
