@@ -493,6 +493,10 @@ class GANEngine:
                 for buf in (fp.flat, fp.m, fp.v):
                     self.comm.broadcast(buf)
                 fp.version += 1
+            if not self.comm.native:
+                # torch.distributed fallback (FSR_NCCL_CAPI=0 / no libnccl): ProcessGroupNCCL collectives are not captured
+                # into the step graph (measured: capture on a side stream hangs) - the step runs eagerly instead
+                self.use_graph = False
 
     def _allreduce(self, flat_grad: torch.Tensor):
         if self.world > 1:

@@ -22,6 +22,6 @@ def test_two_gpu_train_step_matches_single_gpu(capi):
     port = 29500 + (os.getpid() % 400) + (0 if capi == "1" else 1)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "tests", "diag", "ddp_check.py")]
-    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=240)
     print(r.stdout[-3000:], r.stderr[-3000:])
     assert r.returncode == 0 and "DDP CHECK worst" in r.stdout
