@@ -78,6 +78,9 @@ _SIGS = {
     "fsr_set_small_mma": (_i, [_i]),
     "fsr_set_gen_ws": (_i, [_i]),
     "fsr_set_gen_2cta": (_i, [_i]),
+    "fsr_conv3x3_gen_flat": (_i, [_vp, _vp, _vp, _fp, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp]),
+    "fsr_maxpool2_padded": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "fsr_maxpool2_relu_bwd_padded": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "fsr_set_fuse_in": (_i, [_i]),
     "fsr_conv3x3_c64_in": (_i, [_vp, _vp, _fp, _f, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "fsr_conv3x3_c64_res_in": (_i, [_vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),

@@ -534,6 +534,63 @@ int gen_dispatch(const void* x, const void* w_packed, void* out, const float* bi
 }
 
 
+// ------------------------------------------------------------------ flat (padded-flattened) general conv
+// 2-D map of a [rows][C] matrix (2-byte elements), box {64, box_rows}, 128B swizzle, zero OOB fill
+int make_rows_map(CUtensorMap* tm, const void* ptr, long long rows, int C, int box_rows, int dtype) {
+  auto enc = get_encode_fn();
+  if (!enc) return FSR_ERR_NO_DRIVER;
+  cuuint64_t gdim[2] = {(cuuint64_t)C, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)C * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, tm_dtype(dtype), 2, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? FSR_OK : FSR_ERR_TENSORMAP;
+}
+
+template <typename T>
+int gen_flat_dispatch(const void* x, const void* w_packed, void* out, const float* bias, int N, int H, int W, int cin, int cout,
+                      int mode, int act, float slope, int dtype, cudaStream_t st) {
+  if (N <= 0 || H <= 0 || W <= 0 || cin % 64 || cout % 128) return FSR_ERR_BAD_SHAPE;
+  const int W2 = W + 2, lead = W2 + 1, box_rows = 128 + 2 * W2 + 2;
+  if (box_rows * 128 > Gen2Cfg<9>::kABytes || box_rows > 256) return FSR_ERR_BAD_SHAPE;      // W <= 25
+  const long long Q = (long long)N * (H + 2) * W2;
+  if (Q >= ((long long)1 << 31) - 256) return FSR_ERR_BAD_SHAPE;
+  GenParams p{};
+  p.N = N; p.Ho = H; p.Wo = W; p.cin = cin; p.cout_total = cout; p.num_slices = cout / 128;
+  p.bias = bias; p.act = act; p.slope = slope; p.out = out; p.out_img_stride = (long long)(H + 2) * W2 * cout;
+  p.tiles_x = 1; p.tiles_y = 1; p.num_tiles = (int)((Q + 127) / 128);
+  p.flat = 1; p.flat_q = (int)Q; p.flat_lead = lead;
+  p.nkinds = 1;
+  GenKind& K = p.kinds[0];
+  K.map = 0; K.ntaps = 9; K.box_w = 8; K.box_rows = box_rows; K.dx = 0; K.dy = 0;      // box_w 8: SBO = 1024 B (contiguous rows)
+  for (int r = 0; r < 3; ++r)
+    for (int s2 = 0; s2 < 3; ++s2) {
+      K.taps[r * 3 + s2].wrow = r * 3 + s2;
+      K.taps[r * 3 + s2].a_off = mode == 0 ? r * W2 + s2 : (2 - r) * W2 + (2 - s2);
+    }
+  CUtensorMap maps[4], tmw, tmo;
+  int rc;
+  if ((rc = make_rows_map(&maps[0], x, Q, cin, box_rows, dtype))) return rc;
+  maps[1] = maps[2] = maps[3] = maps[0];
+  if ((rc = make_w_map(&tmw, w_packed, 9 * cout, 64, dtype, cin))) return rc;
+  if ((rc = make_rows_map(&tmo, out, Q, cout, 32, dtype))) return rc;
+  using C2 = Gen2Cfg<9>;
+  auto k2 = conv3x3_gen_2cta_kernel<EPI_BIAS_ACT, T, 9>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    FSR_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, C2::kSmemBytes));
+    attr_done = true;
+  }
+  const int pairs = (p.num_tiles + 1) / 2;
+  int cps = (num_sms() / 2) / p.num_slices;
+  if (cps < 1) cps = 1;
+  if (cps > pairs) cps = pairs;
+  LaunchScope scope(FSR_K_CONV_GEN, st, 2.0 * N * H * W * (double)cout * cin * 9);
+  k2<<<2 * cps * p.num_slices, C2::kThreads, C2::kSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], tmw, tmo, p);
+  return cuda_rc(cudaGetLastError());
+}
+
 // ------------------------------------------------------------------ weight gradient (conv3x3_wgrad.cuh)
 // 5-D activation map [groups][N][H][W][C] (2-byte elements), box {64, bw, bh, 1, 1}; img / group strides in elements
 int make_act_map5(CUtensorMap* tm, const void* ptr, int G, int N, int H, int W, int C, long long img_stride, long long grp_stride,
@@ -728,6 +785,14 @@ int fsr_conv3x3_gen(const void* x, const void* w_packed, void* out, const float*
   if (dtype == FSR_BF16)
     return gen_dispatch<__nv_bfloat16>(x, w_packed, out, bias, reinterpret_cast<long long*>(stats), alpha, N, H, W, cin, cout, stride, mode, epilogue, act, slope, dtype, st);
   return gen_dispatch<__half>(x, w_packed, out, bias, reinterpret_cast<long long*>(stats), alpha, N, H, W, cin, cout, stride, mode, epilogue, act, slope, dtype, st);
+}
+
+int fsr_conv3x3_gen_flat(const void* x_padded, const void* w_packed, void* out_padded, const float* bias, int N, int H, int W,
+                         int cin, int cout, int mode, int act, float slope, int dtype, void* stream) {
+  if (!x_padded || !w_packed || !out_padded || x_padded == out_padded || (mode != 0 && mode != 1)) return FSR_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == FSR_BF16) return gen_flat_dispatch<__nv_bfloat16>(x_padded, w_packed, out_padded, bias, N, H, W, cin, cout, mode, act, slope, dtype, st);
+  return gen_flat_dispatch<__half>(x_padded, w_packed, out_padded, bias, N, H, W, cin, cout, mode, act, slope, dtype, st);
 }
 
 int fsr_conv3x3_head(const void* x, const void* w_packed, void* out, const float* bias, int N, int H, int W, int cin,
@@ -1115,24 +1180,39 @@ int fsr_parity_layout(const void* in, void* out, int N, int H, int W, int C, int
   return cuda_rc(cudaGetLastError());
 }
 
-int fsr_maxpool2(const void* in, void* out, int N, int H, int W, int C, int dtype, void* stream) {
-  if (!in || !out || C % 8 || ((H | W) & 1)) return FSR_ERR_BAD_ARG;
+static int maxpool2_impl(const void* in, void* out, int N, int H, int W, int C, int in_pad, int out_pad, int dtype, void* stream) {
+  if (!in || !out || C % 8 || ((H | W) & 1) || (in_pad & ~1) || (out_pad & ~1)) return FSR_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t total = (size_t)N * (H / 2) * (W / 2) * (C / 8);
   LaunchScope scope(FSR_K_NONE - 1, st);
-  FSR_T((maxpool2_fwd_kernel<__half><<<ew_blocks(total), 256, 0, st>>>((const __half*)in, (__half*)out, N, H, W, C)),
-        (maxpool2_fwd_kernel<__nv_bfloat16><<<ew_blocks(total), 256, 0, st>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, N, H, W, C)));
+  FSR_T((maxpool2_fwd_kernel<__half><<<ew_blocks(total), 256, 0, st>>>((const __half*)in, (__half*)out, N, H, W, C, in_pad, out_pad)),
+        (maxpool2_fwd_kernel<__nv_bfloat16><<<ew_blocks(total), 256, 0, st>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, N, H, W, C, in_pad, out_pad)));
   return cuda_rc(cudaGetLastError());
 }
 
-int fsr_maxpool2_relu_bwd(const void* in, const void* dout, void* din, int N, int H, int W, int C, int dtype, void* stream) {
-  if (!in || !dout || !din || ((H | W) & 1)) return FSR_ERR_BAD_ARG;
+static int maxpool2_relu_bwd_impl(const void* in, const void* dout, void* din, int N, int H, int W, int C, int in_pad, int out_pad,
+                                  int dtype, void* stream) {
+  if (!in || !dout || !din || ((H | W) & 1) || (in_pad & ~1) || (out_pad & ~1)) return FSR_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t total = (size_t)N * (H / 2) * (W / 2) * C;
   LaunchScope scope(FSR_K_NONE - 1, st);
-  FSR_T((maxpool2_relu_bwd_kernel<__half><<<ew_blocks(total), 256, 0, st>>>((const __half*)in, (const __half*)dout, (__half*)din, N, H, W, C)),
-        (maxpool2_relu_bwd_kernel<__nv_bfloat16><<<ew_blocks(total), 256, 0, st>>>((const __nv_bfloat16*)in, (const __nv_bfloat16*)dout, (__nv_bfloat16*)din, N, H, W, C)));
+  FSR_T((maxpool2_relu_bwd_kernel<__half><<<ew_blocks(total), 256, 0, st>>>((const __half*)in, (const __half*)dout, (__half*)din, N, H, W, C, in_pad, out_pad)),
+        (maxpool2_relu_bwd_kernel<__nv_bfloat16><<<ew_blocks(total), 256, 0, st>>>((const __nv_bfloat16*)in, (const __nv_bfloat16*)dout, (__nv_bfloat16*)din, N, H, W, C, in_pad, out_pad)));
   return cuda_rc(cudaGetLastError());
+}
+
+int fsr_maxpool2(const void* in, void* out, int N, int H, int W, int C, int dtype, void* stream) {
+  return maxpool2_impl(in, out, N, H, W, C, 0, 0, dtype, stream);
+}
+int fsr_maxpool2_relu_bwd(const void* in, const void* dout, void* din, int N, int H, int W, int C, int dtype, void* stream) {
+  return maxpool2_relu_bwd_impl(in, dout, din, N, H, W, C, 0, 0, dtype, stream);
+}
+int fsr_maxpool2_padded(const void* in, void* out, int N, int H, int W, int C, int in_pad, int out_pad, int dtype, void* stream) {
+  return maxpool2_impl(in, out, N, H, W, C, in_pad, out_pad, dtype, stream);
+}
+int fsr_maxpool2_relu_bwd_padded(const void* in, const void* dout, void* din, int N, int H, int W, int C, int in_pad, int out_pad,
+                                 int dtype, void* stream) {
+  return maxpool2_relu_bwd_impl(in, dout, din, N, H, W, C, in_pad, out_pad, dtype, stream);
 }
 
 int fsr_relu_bwd(const void* y, const void* dy, void* dx, size_t n_elems, int dtype, void* stream) {

@@ -52,6 +52,13 @@ struct GenParams {
   int act;
   int ps;                   // 1: PixelShuffle(2) scatter store (UpSamplingBlock with F != 64): GEMM columns are packed
                             //    (2i+j)*F + c, out = [N, 2Ho, 2Wo, F = cout_total/4]
+  // FLAT mode (conv3x3_gen_2cta.cuh only): input and output are zero-bordered PADDED tensors [N][Ho+2][Wo+2][C]; an M tile
+  // is 128 CONSECUTIVE positions of the flattened (n, y', x') index, whatever image they belong to (the <= 12x12 layers
+  // of VGG19: 73 % / 56 % of every tile is image instead of 56 % / 28 % with 16x8 tiles).  Tap (r,s) is the row offset
+  // r*(Wo+2)+s inside a plain 2-D box of the [Q][Cin] matrix; border positions are written as zeros.
+  int flat;                 // 0 | 1
+  int flat_q;               // Q = N * (Ho+2) * (Wo+2)
+  int flat_lead;            // rows of the box before the tile's first position: (Wo+2) + 1
 };
 
 template <int MAXTAPS>

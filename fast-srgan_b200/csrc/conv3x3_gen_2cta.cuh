@@ -124,7 +124,10 @@ conv3x3_gen_2cta_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_
           if (elect_one()) {
             const uint32_t full_leader = mapa_cluster(smem_u32(&afull[stage]), 0);
             mbar_arrive_expect_tx_cluster(full_leader, K.box_rows * 128);
-            tma_load_4d_pair(smem_a + stage * Cfg::kABytes, tm, full_leader, kc * 64, tx * TW + K.dx, ty * TH + K.dy, n);
+            if (p.flat)        // rows [t*128 - lead, ...) of the flattened padded tensor; rows outside [0, Q) are zero-filled
+              tma_load_2d_pair(smem_a + stage * Cfg::kABytes, tm, full_leader, kc * 64, t * 128 - p.flat_lead);
+            else
+              tma_load_4d_pair(smem_a + stage * Cfg::kABytes, tm, full_leader, kc * 64, tx * TW + K.dx, ty * TH + K.dy, n);
           }
           __syncwarp();
           if (++stage == Cfg::kAStages) { stage = 0; phase ^= 1; }
@@ -251,6 +254,13 @@ conv3x3_gen_2cta_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_
         const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
         const int x0 = tx * TW, y0 = ty * TH;
         const bool interior = (y0 + TH <= p.Ho) && (x0 + TW <= p.Wo);
+        bool row_live = true;               // flat mode: this thread's position is an image pixel (not border / tail padding)
+        if (p.flat) {
+          const int pos = t * 128 + q * 32 + lane;
+          const int W2 = p.Wo + 2, per = (p.Ho + 2) * W2;
+          const int rm = pos % per, yy = rm / W2, xx = rm - yy * W2;
+          row_live = pos < p.flat_q && yy >= 1 && yy <= p.Ho && xx >= 1 && xx <= p.Wo;
+        }
         if (EPI == EPI_RAW_STATS && tile_valid && n != st_n) { flush_stats(st_n); st_n = n; }
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(set * TG + i) * Cfg::NS + hcol * 64;
         uint32_t pk[32];
@@ -274,8 +284,8 @@ conv3x3_gen_2cta_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_
               b0 = apply_act(b0 + bs[32 + 2 * c], p.act, slope);
               b1 = apply_act(b1 + bs[32 + 2 * c + 1], p.act, slope);
             }
-            pk[c] = Cvt<T>::pack2(a0, a1);
-            pk[16 + c] = Cvt<T>::pack2(b0, b1);
+            pk[c] = row_live ? Cvt<T>::pack2(a0, a1) : 0u;      // flat mode keeps the zero border of the padded layout
+            pk[16 + c] = row_live ? Cvt<T>::pack2(b0, b1) : 0u;
           }
         }
         if (lane == 0) tma_store_wait_read();           // the previous TMA store has finished reading this warp's buffer
@@ -287,7 +297,8 @@ conv3x3_gen_2cta_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_
         __syncwarp();
         if (lane == 0 && tile_valid) {
           // NHWC [N][Ho][Wo][cout_total] (image stride may be a parity-plane stride): 32 pixels x 64 channels of this warp
-          tma_store_4d(&tm_out, smem_stg + ew * 4096, col0, x0, y0 + (q * 32) / TW, n);
+          if (p.flat) tma_store_2d(&tm_out, smem_stg + ew * 4096, col0, t * 128 + q * 32);   // [Q][cout_total], tail clipped
+          else tma_store_4d(&tm_out, smem_stg + ew * 4096, col0, x0, y0 + (q * 32) / TW, n);
           tma_store_commit();
         }
         if constexpr (EPI == EPI_RAW_STATS) {

@@ -41,8 +41,11 @@ __global__ void __launch_bounds__(256) parity_layout_kernel(const uint4* __restr
 // ------------------------------------------------------------------ 2x2 max-pool (VGG idx 4,9,18,27), NHWC
 template <typename T>
 __global__ void __launch_bounds__(256) maxpool2_fwd_kernel(const T* __restrict__ in, T* __restrict__ out, int N, int H,
-                                                           int W, int C) {
+                                                           int W, int C, int ip = 0, int op = 0) {
+  // ip / op = 1: `in` / `out` are in the zero-bordered PADDED layout [N][H+2][W+2][C] of the flat conv kernels
+  // (conv3x3_gen_2cta.cuh, flat mode); only interior pixels are read / written (the caller zero-fills a padded `out`)
   const int Ho = H >> 1, Wo = W >> 1, CV = C / 8;
+  const int Wi = W + 2 * ip, Hi = H + 2 * ip, Wq = Wo + 2 * op, Hq = Ho + 2 * op;
   const size_t total = (size_t)N * Ho * Wo * CV;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int cv = (int)(i % CV);
@@ -50,7 +53,7 @@ __global__ void __launch_bounds__(256) maxpool2_fwd_kernel(const T* __restrict__
     const int x = (int)(pix % Wo);
     const int y = (int)((pix / Wo) % Ho);
     const int n = (int)(pix / ((size_t)Wo * Ho));
-    const T* base = in + (((size_t)n * H + 2 * y) * W + 2 * x) * C + cv * 8;
+    const T* base = in + (((size_t)n * Hi + 2 * y + ip) * Wi + 2 * x + ip) * C + cv * 8;
     float m[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) m[k] = -INFINITY;
@@ -58,7 +61,7 @@ __global__ void __launch_bounds__(256) maxpool2_fwd_kernel(const T* __restrict__
     for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
       for (int dx = 0; dx < 2; ++dx) {
-        const uint4 v = *reinterpret_cast<const uint4*>(base + ((size_t)dy * W + dx) * C);
+        const uint4 v = *reinterpret_cast<const uint4*>(base + ((size_t)dy * Wi + dx) * C);
         const uint32_t u[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -70,7 +73,7 @@ __global__ void __launch_bounds__(256) maxpool2_fwd_kernel(const T* __restrict__
     uint4 o;
     o.x = Cvt<T>::pack2(m[0], m[1]); o.y = Cvt<T>::pack2(m[2], m[3]);
     o.z = Cvt<T>::pack2(m[4], m[5]); o.w = Cvt<T>::pack2(m[6], m[7]);
-    *reinterpret_cast<uint4*>(out + (((size_t)n * Ho + y) * Wo + x) * C + cv * 8) = o;
+    *reinterpret_cast<uint4*>(out + (((size_t)n * Hq + y + op) * Wq + x + op) * C + cv * 8) = o;
   }
 }
 
@@ -78,8 +81,10 @@ __global__ void __launch_bounds__(256) maxpool2_fwd_kernel(const T* __restrict__
 // mask of the pre-pool activation (in > 0) is applied in the same pass.
 template <typename T>
 __global__ void __launch_bounds__(256) maxpool2_relu_bwd_kernel(const T* __restrict__ in, const T* __restrict__ dout,
-                                                                T* __restrict__ din, int N, int H, int W, int C) {
+                                                                T* __restrict__ din, int N, int H, int W, int C, int ip = 0, int op = 0) {
+  // ip = 1: `in` and `din` are in the padded layout [N][H+2][W+2][C]; op = 1: `dout` is [N][H/2+2][W/2+2][C]
   const int Ho = H >> 1, Wo = W >> 1;
+  const int Wi = W + 2 * ip, Hi = H + 2 * ip, Wq = Wo + 2 * op, Hq = Ho + 2 * op;
   const size_t total = (size_t)N * Ho * Wo * C;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
@@ -87,8 +92,8 @@ __global__ void __launch_bounds__(256) maxpool2_relu_bwd_kernel(const T* __restr
     const int x = (int)(pix % Wo);
     const int y = (int)((pix / Wo) % Ho);
     const int n = (int)(pix / ((size_t)Wo * Ho));
-    const size_t b = (((size_t)n * H + 2 * y) * W + 2 * x) * C + c;
-    const size_t idx[4] = {b, b + C, b + (size_t)W * C, b + (size_t)W * C + C};
+    const size_t b = (((size_t)n * Hi + 2 * y + ip) * Wi + 2 * x + ip) * C + c;
+    const size_t idx[4] = {b, b + C, b + (size_t)Wi * C, b + (size_t)Wi * C + C};
     float v[4];
     int am = 0;
 #pragma unroll
@@ -96,7 +101,7 @@ __global__ void __launch_bounds__(256) maxpool2_relu_bwd_kernel(const T* __restr
       v[k] = Cvt<T>::to_f(in[idx[k]]);
       if (v[k] > v[am]) am = k;
     }
-    const float g = Cvt<T>::to_f(dout[i]);
+    const float g = Cvt<T>::to_f(dout[(((size_t)n * Hq + y + op) * Wq + x + op) * C + c]);
 #pragma unroll
     for (int k = 0; k < 4; ++k) din[idx[k]] = Cvt<T>::from_f((k == am && v[k] > 0.f) ? g : 0.f);
   }

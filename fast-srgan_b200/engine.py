@@ -8,6 +8,7 @@ what the NCCL all-reduce and the fused AdamW consume.
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -406,44 +407,63 @@ class VGGNet:
             P["bwd"] = torch.empty(0)
         self._packed = True
 
+    FLAT_MAX_W = 25          # conv3x3_gen_flat: the padded-flattened tile mapping needs W + 2 <= 27 rows of lead / tail per box
+
     def forward(self, img: torch.Tensor, save: bool):
+        """-> (features, ctx).  From the first pooled resolution with W <= 25 on (12x12 and 6x6 at the training shape:
+        conv4_x, conv5_x) activations are kept in the zero-bordered PADDED layout [N,H+2,W+2,C] and the convs run in the
+        flat tile mapping (fsr_conv3x3_gen_flat); `self.feat_pad` tells whether the returned features are padded."""
         self.pack(need_bwd=save)
         P, dt = self.P, self.dt
         acts, j = [], 0
         cur = None
+        pad = False
+        use_flat = os.environ.get("FSR_VGG_FLAT", "1") != "0"
         for v in VGG_PLAN:
             if v == "M":
-                pooled = ops.maxpool2(cur)
+                wo = (cur.shape[2] - (2 if pad else 0)) // 2
+                out_pad = use_flat and wo <= self.FLAT_MAX_W and cur.shape[3] % 128 == 0
+                pooled = ops.maxpool2_padded(cur, pad, out_pad) if (pad or out_pad) else ops.maxpool2(cur)
                 if save:
-                    acts[-1] = (acts[-1][0], True)
-                cur = pooled
+                    acts[-1] = (acts[-1][0], True, acts[-1][2])
+                cur, pad = pooled, out_pad
             else:
                 if j == 0:
                     cur = ops.neck_conv3x3(img, P["w0"], P["b0"], dt, act=L.ACT_RELU, vgg_norm=True)
+                elif pad:
+                    cur = ops.conv3x3_gen_flat(cur, P[f"w{j}"], v, mode=0, bias=P[f"b{j}"], act=L.ACT_RELU)
                 else:
                     cur = ops.conv3x3_gen(cur, P[f"w{j}"], v, bias=P[f"b{j}"], act=L.ACT_RELU)
                 if save:
-                    acts.append((cur, False))
+                    acts.append((cur, False, pad))
                 j += 1
+        self.feat_pad = pad
         return cur, (dict(acts=acts) if save else None)
 
     def backward(self, ctx, dfeat: torch.Tensor, d_img: torch.Tensor):
-        """dfeat: gradient w.r.t. relu5_3 features (NHWC dtype) of the FIRST dfeat.shape[0] images of the forward batch
-        (the step runs VGG once on [sr; hr] and differentiates the sr half only); accumulates the image gradient into
-        d_img (fp32 NCHW)."""
+        """dfeat: gradient w.r.t. relu5_3 features (NHWC dtype; padded iff the forward returned padded features) of the
+        FIRST dfeat.shape[0] images of the forward batch (the step runs VGG once on [sr; hr] and differentiates the sr half
+        only); accumulates the image gradient into d_img (fp32 NCHW)."""
         P = self.P
         acts = ctx["acts"]
         widths = [v for v in VGG_PLAN if v != "M"]
         dcur = dfeat
         nb = dfeat.shape[0]
+        dcur_pad = acts[-1][2]
         for j in reversed(range(len(acts))):
-            a, pooled = acts[j]
+            a, pooled, a_pad = acts[j]
             a = a[:nb]
-            da = ops.maxpool2_relu_bwd(a, dcur) if pooled else ops.relu_bwd(a, dcur)
+            if pooled:
+                da = ops.maxpool2_relu_bwd_padded(a, dcur, a_pad, dcur_pad) if (a_pad or dcur_pad) else ops.maxpool2_relu_bwd(a, dcur)
+            else:
+                da = ops.relu_bwd(a, dcur)
             if j == 0:
                 ops.conv3x3_c64_head(da, P["t0"], None, out_u8=3, out=d_img)
+            elif a_pad:
+                dcur = ops.conv3x3_gen_flat(da, P[f"t{j}"], widths[j - 1], mode=1)
             else:
                 dcur = ops.conv3x3_gen(da, P[f"t{j}"], widths[j - 1], mode=1)
+            dcur_pad = a_pad
 
 
 # ====================================================================================== GAN step
@@ -607,11 +627,15 @@ class GANEngine:
         B = sr.shape[0]
         feats, ctx_v = self.V.forward(self._X, save=True)               # :190 (first half) and :191 (second half)
         fake_f, real_f = feats[:B], feats[B:]
+        # padded features (flat tile mapping of the <= 12x12 layers): both halves carry the same zero border, which adds
+        # nothing to the SmoothL1 sum or its gradient; the mean is taken over the REAL element count
+        pd = 2 if self.V.feat_pad else 0
+        nfeat = fake_f.shape[0] * (fake_f.shape[1] - pd) * (fake_f.shape[2] - pd) * fake_f.shape[3]
         dfeat = torch.empty_like(fake_f)
-        ops.smooth_l1(fake_f, real_f, losses[3:4], dfeat, grad_scale=0.5 * S / fake_f.numel())   # :192,194
+        ops.smooth_l1(fake_f, real_f, losses[3:4], dfeat, grad_scale=0.5 * S / nfeat)   # :192,194
         self._d_sr = torch.zeros_like(sr)
         self.V.backward(ctx_v, dfeat, self._d_sr)                       # :195 (VGG branch)
-        self._nfeat = float(fake_f.numel())
+        self._nfeat = float(nfeat)
 
     def _seg_adv_and_g(self, ins):
         """adversarial loss through the UPDATED discriminator and the generator backward (trainer.py:186-188, :195)."""

@@ -66,8 +66,10 @@ class _VggFn(torch.autograd.Function):
     def forward(ctx, module, x):
         net = module._engine()
         feat, c = net.forward(x.contiguous().float(), save=x.requires_grad)
-        ctx.net, ctx.c, ctx.x_shape = net, c, tuple(x.shape)
+        ctx.net, ctx.c, ctx.x_shape, ctx.pad = net, c, tuple(x.shape), net.feat_pad
         from . import ops
+        if net.feat_pad:                                   # flat tile mapping: drop the zero border of the padded layout
+            feat = feat[:, 1:-1, 1:-1, :].contiguous()
         return ops.nhwc_to_nchw(feat)
 
     @staticmethod
@@ -76,7 +78,12 @@ class _VggFn(torch.autograd.Function):
         if ctx.c is None:
             return None, None
         dx = torch.zeros(ctx.x_shape, dtype=torch.float32, device=dfeat.device)
-        ctx.net.backward(ctx.c, ops.nchw_to_nhwc(dfeat.contiguous().float(), ctx.net.dt), dx)
+        d = ops.nchw_to_nhwc(dfeat.contiguous().float(), ctx.net.dt)
+        if ctx.pad:
+            dp = torch.zeros((d.shape[0], d.shape[1] + 2, d.shape[2] + 2, d.shape[3]), dtype=d.dtype, device=d.device)
+            dp[:, 1:-1, 1:-1, :] = d
+            d = dp
+        ctx.net.backward(ctx.c, d, dx)
         return None, dx
 
 
@@ -448,6 +455,9 @@ class VGG19(torch.nn.Module):
         Generator._require_cuda(x)
         if torch.is_grad_enabled() and x.requires_grad:
             return _VggFn.apply(self, x)                                         # trainer.py:190
-        feat, _ = self._engine().forward(x.contiguous().float(), save=False)
+        net = self._engine()
+        feat, _ = net.forward(x.contiguous().float(), save=False)
         from . import ops
+        if net.feat_pad:
+            feat = feat[:, 1:-1, 1:-1, :].contiguous()
         return ops.nhwc_to_nchw(feat)

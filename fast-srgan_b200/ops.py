@@ -262,6 +262,41 @@ def wgrad_workspace(device) -> torch.Tensor:
     return _WGRAD_WS[key]
 
 
+def conv3x3_gen_flat(xp, w_packed, cout, mode=0, bias=None, act=L.ACT_NONE, slope=0.0):
+    """General conv on zero-bordered padded tensors: xp [N,H+2,W+2,cin] -> [N,H+2,W+2,cout] (borders written as zero).
+    mode 0 forward, mode 1 data gradient.  See include/fsr_b200.h: fsr_conv3x3_gen_flat."""
+    _cuda(xp, w_packed, bias)
+    N, Hp, Wp, cin = xp.shape
+    assert xp.is_contiguous()
+    out = torch.empty((N, Hp, Wp, cout), dtype=xp.dtype, device=xp.device)
+    L.check(L.load().fsr_conv3x3_gen_flat(xp.data_ptr(), w_packed.data_ptr(), out.data_ptr(), L.ptr(bias), N, Hp - 2, Wp - 2, cin, cout,
+                                          mode, act, slope, L.dtype_code(xp.dtype), L.stream_ptr(xp.device)), "conv3x3_gen_flat")
+    return out
+
+
+def maxpool2_padded(x, in_pad: bool, out_pad: bool):
+    """2x2 max-pool between plain [N,H,W,C] and padded [N,H+2,W+2,C] layouts (either side)."""
+    _cuda(x)
+    N, Hx, Wx, C = x.shape
+    H, W = (Hx - 2, Wx - 2) if in_pad else (Hx, Wx)
+    shape = (N, H // 2 + 2, W // 2 + 2, C) if out_pad else (N, H // 2, W // 2, C)
+    out = torch.zeros(shape, dtype=x.dtype, device=x.device) if out_pad else torch.empty(shape, dtype=x.dtype, device=x.device)
+    L.check(L.load().fsr_maxpool2_padded(x.data_ptr(), out.data_ptr(), N, H, W, C, int(in_pad), int(out_pad), L.dtype_code(x.dtype),
+                                         L.stream_ptr(x.device)), "maxpool (padded)")
+    return out
+
+
+def maxpool2_relu_bwd_padded(x, dout, in_pad: bool, out_pad: bool):
+    """backward of [ReLU -> maxpool]: x = pre-pool activation (plain or padded), dout = pooled gradient (plain or padded)."""
+    _cuda(x, dout)
+    N, Hx, Wx, C = x.shape
+    H, W = (Hx - 2, Wx - 2) if in_pad else (Hx, Wx)
+    din = torch.zeros_like(x) if in_pad else torch.empty_like(x)
+    L.check(L.load().fsr_maxpool2_relu_bwd_padded(x.data_ptr(), dout.data_ptr(), din.data_ptr(), N, H, W, C, int(in_pad), int(out_pad),
+                                                  L.dtype_code(x.dtype), L.stream_ptr(x.device)), "maxpool bwd (padded)")
+    return din
+
+
 def conv3x3_wgrad(x, dy, dw, stride=1, ps_perm=False):
     """dw (fp32 OIHW, accumulated) += wgrad(x, dy).  stride 2: x in parity planes [N,4,H/2,W/2,cin]."""
     _cuda(x, dy, dw)

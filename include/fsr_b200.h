@@ -297,6 +297,18 @@ int fsr_set_fuse_in(int on);
  * and group instead of per tile: 2.3x less L2->smem traffic, same results bit for bit); 0: per-tile weight streaming;
  * -1: environment default (FSR_GEN_WS). */
 int fsr_set_gen_ws(int on);
+/* The same conv (stride 1, bias + activation epilogue, Cout % 128 == 0, W <= 25) on zero-bordered PADDED tensors
+ * [N][H+2][W+2][C]: an M tile is 128 CONSECUTIVE positions of the flattened (n, y', x') index, so the <= 12x12 layers of
+ * VGG19 (conv4_x, conv5_x behind model.py:8) fill 73 % / 56 % of every 128-row tile instead of 56 % / 28 % with 16x8
+ * tiles.  Border positions of `out_padded` are written as zeros (the layout stays valid for the next layer).
+ * mode 0 forward, mode 1 data gradient (weights packed with fsr_pack_conv3x3_weight_t).  fsr_maxpool2_padded /
+ * fsr_maxpool2_relu_bwd_padded convert between the plain and the padded layout on the way (in_pad / out_pad = 0 | 1;
+ * a padded output must be zero-filled by the caller: only interior pixels are written). */
+int fsr_conv3x3_gen_flat(const void* x_padded, const void* w_packed, void* out_padded, const float* bias, int N, int H, int W,
+                         int cin, int cout, int mode, int act, float slope, int dtype, void* stream);
+int fsr_maxpool2_padded(const void* in, void* out, int N, int H, int W, int C, int in_pad, int out_pad, int dtype, void* stream);
+int fsr_maxpool2_relu_bwd_padded(const void* in, const void* dout, void* din, int N, int H, int W, int C, int in_pad, int out_pad,
+                                 int dtype, void* stream);
 /* 1 (default): fsr_conv3x3_gen with Cout % 128 == 0 runs as a CTA-pair kernel (tcgen05 cta_group::2, M = 256, 128-wide
  * output-channel slices: half the shared-memory operand traffic per MMA); 0: the 64-wide single-CTA kernels;
  * -1: environment default (FSR_GEN_2CTA).  Same results bit for bit. */
