@@ -240,6 +240,11 @@ int launch_conv(const void* x, const void* w_packed, int w_rows, ConvParams p, i
   p.tiles_y = (p.H + Geo::TH - 1) / Geo::TH;
   p.num_tiles = p.N * p.tiles_x * p.tiles_y;
   p.ws = ws_mode();
+  {
+    static int backoff = -1;
+    if (backoff < 0) { const char* e = getenv("FSR_BACKOFF_NS"); backoff = e ? atoi(e) : 0; }
+    p.backoff_ns = backoff;
+  }
   CUtensorMap tmx, tmw, tmo;
   int rc = make_act_map(&tmx, x, p.N, p.H, p.W, 64, Geo::kBoxW, Geo::kBoxH, dtype);
   if (rc) return rc;

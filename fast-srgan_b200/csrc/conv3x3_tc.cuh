@@ -65,6 +65,7 @@ struct ConvParams {
   // (model.py:65 + :69) is formed on the staged tile and the tile's own pixels of x_next are written to x_out
   const void* in_res;         // x_prev [N,H,W,64] NHWC T
   void* x_out;                // x_next [N,H,W,64] NHWC T (aliases neither in_res nor the raw input)
+  int backoff_ns;             // nanosleep between mbarrier polls of the producer / epilogue / transform warps (0 = spin)
 };
 
 template <bool HALO1>
@@ -201,7 +202,7 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
       const int x0 = tx * TW, y0 = ty * TH;
 #pragma unroll
       for (int s = 0; s < Geo::kLoads; ++s) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_wait_backoff(&empty_bar[stage], phase ^ 1, p.backoff_ns);
         if (elect_one()) {
           mbar_arrive_expect_tx(&full_bar[stage], Geo::kTxBytes);
           tma_load_4d(smem_a + stage * Geo::kStageBytes, &tm_x, &full_bar[stage], 0,
@@ -330,7 +331,7 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
           cur_n = n;
         }
         const bool inside = (y0 >= 1) && (x0 >= 1) && (y0 + TH + 1 <= p.H) && (x0 + TW + 1 <= p.W);   // whole halo box in the image
-        mbar_wait(&full_bar[stage], phase);
+        mbar_wait_backoff(&full_bar[stage], phase, p.backoff_ns);
         const uint32_t base = smem_u32(smem_a + stage * Geo::kStageBytes);
         // ROLLED loop (two rows in flight per thread): a fully unrolled, branch-free version measured no faster than two
         // warps with a branch per row (358 us either way) while the kernel's SASS grew to 64 KB and 27 % of the stall samples
@@ -480,7 +481,7 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
       const bool pvalid = (y < p.H) && (x < p.W);
       const bool interior = (y0 + TH <= p.H) && (x0 + TW <= p.W);   // warp-uniform
       if (EPI == EPI_RAW_STATS && n != st_n) { flush_stats(st_n); st_n = n; }
-      mbar_wait(&tfull_bar[acc], acc_phase);
+      mbar_wait_backoff(&tfull_bar[acc], acc_phase, p.backoff_ns);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * NS;
 

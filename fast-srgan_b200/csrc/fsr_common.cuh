@@ -61,6 +61,18 @@ FSR_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Waiters that are NOT on the critical path (TMA producer waiting for a free stage, epilogue warps waiting for an
+// accumulator) back off between polls: a blocked try_wait keeps re-reading the barrier through the shared-memory data
+// pipe - the pipe the tensor core fetches its operands through (profiles/r02: 684 LSU wavefronts per tile in the 64->64
+// conv, of which only 137 are the epilogue's staging stores).
+FSR_DEVINL void mbar_wait_backoff(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (ns) __nanosleep(ns);
+    if (++spins > (1u << 26)) { asm volatile("trap;"); }
+  }
+}
+
 // ---------------------------------------------------------------- explicit shared-space access
 FSR_DEVINL void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");

@@ -255,6 +255,45 @@ def test_cuda_graph_train_step_matches_eager():
     assert (ge - gg).abs().max().item() <= 5 * 2.05e-4 and (de - dg).abs().max().item() <= 5 * 2.05e-4
 
 
+def test_backward_is_bitwise_reproducible_in_its_large_reductions():
+    """Round 2: the weight gradients (two-stage split-K reduction in fixed order) and the InstanceNorm backward (in-block
+    sums) no longer use floating-point atomics, and the forward was already bitwise deterministic - so every 3x3 conv
+    weight gradient of the discriminator and of the generator's residual chain is IDENTICAL run to run.  (What still
+    uses fp32 atomics: bias gradients, the 3-channel first-layer weight gradients and the PReLU slope gradients - scalars
+    and small vectors that feed nothing else.)"""
+    from fast_srgan_b200.trainer import Trainer
+    cfg = ns(experiment=ns(name="t", seed=0), generator=ns(n_filters=64, n_layers=3), discriminator=ns(n_filters=64, n_layers=7),
+             training=ns(device="cuda", generator_lr=1e-4, discriminator_lr=1e-4))
+    tr = Trainer(cfg, compute_dtype=torch.bfloat16, vgg_state_dict=O.make_vgg19_state(99))
+    tr.generator.load_state_dict(O.make_generator_state(64, 3, 1234))
+    tr.discriminator.load_state_dict(O.make_discriminator_state(64, 4321))
+    e = tr.engine
+    e.use_graph = False
+    B = 8
+    g = torch.Generator().manual_seed(5)
+    lr = (torch.rand((B, 3, 24, 24), generator=g) * 2 - 1).cuda()
+    hr = (torch.rand((B, 3, 96, 96), generator=g) * 2 - 1).cuda()
+    noise = [torch.rand((B, 36), generator=g).cuda() for _ in range(3)]
+    ins = (lr, hr, noise[0], noise[1], noise[2])
+
+    def grads():
+        e._seg_d(ins)
+        e._seg_content(ins)
+        e._seg_adv_and_g(ins)                       # no optimizer step: parameters stay put, gradients are recomputed
+        torch.cuda.synchronize()
+        return e.dp.grad.clone(), e.gp.grad.clone()
+
+    d1, g1 = grads()
+    d2, g2 = grads()
+    for i in range(7):
+        k = f"stem.{i}.conv.weight"
+        o, n = e.dp.offsets[k], e.dp.p[k].numel()
+        assert torch.equal(d1[o:o + n], d2[o:o + n]), k
+    for k in e.G._convs64() + ["upsampling.0.conv.weight", "upsampling.1.conv.weight"]:
+        o, n = e.gp.offsets[k], e.gp.p[k].numel()
+        assert torch.equal(g1[o:o + n], g2[o:o + n]), k
+
+
 def test_gradients_shard_exactly_over_batch():
     """Size-independent property behind the multi-GPU path: every op is per-sample, losses are batch means,
     so grad(full batch) == mean over shards of grad(shard).  Checked on the discriminator step at BASELINE-like size."""
