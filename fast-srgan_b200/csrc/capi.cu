@@ -120,11 +120,12 @@ int make_act_map_strided(CUtensorMap* tm, const void* ptr, int N, int H, int W, 
 
 // PixelShuffle(2) output [N,2H,2W,64] viewed as [N][H][i:2][W][(j,c):128] (the up conv's store target): one box
 // {64 ch, 8 px, 1, 4 rows, 1} = the 32 pixels of an epilogue warp at sub-position (i, j), start coordinate j*64 in dim 0
-int make_ps_out_map(CUtensorMap* tm, const void* ptr, int N, int H, int W, int dtype) {
+int make_ps_out_map(CUtensorMap* tm, const void* ptr, int N, int H, int W, int dtype, int F = 64) {
   auto enc = get_encode_fn();
   if (!enc) return FSR_ERR_NO_DRIVER;
-  cuuint64_t gdim[5] = {128, (cuuint64_t)W, 2, (cuuint64_t)H, (cuuint64_t)N};
-  cuuint64_t gstr[4] = {256, (cuuint64_t)2 * W * 128, (cuuint64_t)4 * W * 128, (cuuint64_t)2 * H * 2 * W * 128};
+  const cuuint64_t px = (cuuint64_t)F * 2;      // bytes of one output pixel (F channels)
+  cuuint64_t gdim[5] = {(cuuint64_t)2 * F, (cuuint64_t)W, 2, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t gstr[4] = {2 * px, (cuuint64_t)2 * W * px, (cuuint64_t)4 * W * px, (cuuint64_t)2 * H * 2 * W * px};
   cuuint32_t box[5] = {64, 8, 1, 4, 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = enc(tm, tm_dtype(dtype), 5, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -397,7 +398,7 @@ int gen_2cta_mode() {
 template <int EPI, typename T, int MAXTAPS>
 int launch_gen(const CUtensorMap* maps, const CUtensorMap& tmw, GenParams& p, cudaStream_t st, int dtype) {
   using Cfg = GenCfg<MAXTAPS>;
-  if (gen_2cta_mode() && p.cout_total % 128 == 0 && !p.ps) {
+  if (gen_2cta_mode() && p.cout_total % 128 == 0 && (!p.ps || (p.cout_total / 4) % 128 == 0)) {
     using C2 = Gen2Cfg<MAXTAPS>;
     auto k2 = conv3x3_gen_2cta_kernel<EPI, T, MAXTAPS>;
     static bool attr2_done = false;
@@ -408,7 +409,8 @@ int launch_gen(const CUtensorMap* maps, const CUtensorMap& tmw, GenParams& p, cu
     GenParams p2 = p;
     p2.num_slices = p.cout_total / 128;
     CUtensorMap tmo;
-    int rc = make_act_map_strided(&tmo, p.out, p.N, p.Ho, p.Wo, p.cout_total, p.out_img_stride, 8, 4, dtype);
+    int rc = p.ps ? make_ps_out_map(&tmo, p.out, p.N, p.Ho, p.Wo, dtype, p.cout_total / 4)
+                  : make_act_map_strided(&tmo, p.out, p.N, p.Ho, p.Wo, p.cout_total, p.out_img_stride, 8, 4, dtype);
     if (rc) return rc;
     const int pairs = (p.num_tiles + 1) / 2;
     int cps = (num_sms() / 2) / p2.num_slices;      // clusters per 128-wide slice

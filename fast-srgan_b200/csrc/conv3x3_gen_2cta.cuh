@@ -297,8 +297,17 @@ conv3x3_gen_2cta_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_
         __syncwarp();
         if (lane == 0 && tile_valid) {
           // NHWC [N][Ho][Wo][cout_total] (image stride may be a parity-plane stride): 32 pixels x 64 channels of this warp
-          if (p.flat) tma_store_2d(&tm_out, smem_stg + ew * 4096, col0, t * 128 + q * 32);   // [Q][cout_total], tail clipped
-          else tma_store_4d(&tm_out, smem_stg + ew * 4096, col0, x0, y0 + (q * 32) / TW, n);
+          if (p.flat) {
+            tma_store_2d(&tm_out, smem_stg + ew * 4096, col0, t * 128 + q * 32);   // [Q][cout_total], tail clipped
+          } else if (p.ps) {
+            // UpSamplingBlock with F = cout_total / 4 (a multiple of 128): GEMM column (2i+j)*F + c -> out[n, 2y+i, 2x+j, c];
+            // the output is viewed as [N][Ho][i][Wo][(j,c): 2F] (host: make_ps_out_map), one box per (i, j, 64 channels)
+            const int Fc = p.cout_total >> 2;
+            const int qq = col0 / Fc, c0 = col0 - qq * Fc;
+            tma_store_5d(&tm_out, smem_stg + ew * 4096, (qq & 1) * Fc + c0, x0, qq >> 1, y0 + (q * 32) / TW, n);
+          } else {
+            tma_store_4d(&tm_out, smem_stg + ew * 4096, col0, x0, y0 + (q * 32) / TW, n);
+          }
           tma_store_commit();
         }
         if constexpr (EPI == EPI_RAW_STATS) {

@@ -104,3 +104,20 @@ def test_gen_2cta_dgrad_stride1(dt, cin, cout, N, H, W):
     xr = torch.zeros((N, cin, H, W), device="cuda", requires_grad=True)
     F.conv2d(xr, w, padding=1).backward(nchw(dy))
     assert rel_err(nchw(d1), xr.grad) <= 2 * EPS[dt] + 1e-5
+
+
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("Fm,N,H,W", [(128, 8, 20, 24), (256, 2, 16, 8), (128, 3, 13, 21)])
+def test_gen_2cta_pixel_shuffle_epilogue(dt, Fm, N, H, W):
+    """UpSamplingBlock (model.py:39-40) for n_filters = 128 / 256: bias + PReLU + PixelShuffle through the pair kernel's
+    5-D TMA store, against the single-CTA scatter epilogue (same bits) and PyTorch."""
+    from fast_srgan_b200 import ops, _lib as L
+    x = nhwc(rnd((N, Fm, H, W), 8), dt)
+    wu = rnd((4 * Fm, Fm, 3, 3), 9, (Fm * 9) ** -0.5).to(dt).float()
+    bu = rnd((4 * Fm,), 10, 0.1)
+    alpha = torch.tensor([0.2], device="cuda")
+    wp, bp = ops.pack_conv3x3(wu, bu, dt, ps_perm=True)
+    u1, u0 = both(lambda: ops.conv3x3_gen(x, wp, 4 * Fm, epilogue=L.EPI_PS_PRELU, bias=bp, alpha=alpha))
+    assert torch.equal(u1, u0)
+    ref = F.prelu(F.pixel_shuffle(F.conv2d(nchw(x), wu, bu, padding=1), 2), alpha)
+    assert rel_err(nchw(u1), ref) <= 2 * EPS[dt] + 1e-5
