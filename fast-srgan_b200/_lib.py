@@ -32,10 +32,18 @@ class FsrGeneratorParams(C.Structure):
     ]
 
 
+class FsrPackTask(C.Structure):
+    _fields_ = [("w", _vp), ("out", _vp), ("bias", _vp), ("bias_out", _vp), ("row_scale", _vp),
+                ("cout", _i), ("cin", _i), ("pad", _i), ("flags", _i)]
+
+
+PACK_T, PACK_PS, PACK_FLIP = 1, 2, 4
+
 _SIGS = {
     "fsr_abi_version": (_i, []),
     "fsr_error_string": (C.c_char_p, [_i]),
     "fsr_pack_conv3x3_weight": (_i, [_fp, _fp, _vp, _fp, _i, _i, _i, _i, _i, _vp]),
+    "fsr_pack_multi": (_i, [C.POINTER(FsrPackTask), _i, _i, _vp]),
     "fsr_conv3x3_c64": (_i, [_vp, _vp, _vp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _f, _i, _i, _vp]),
     "fsr_conv3x3_gen": (_i, [_vp, _vp, _vp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp]),
     "fsr_pack_conv3x3_weight_t": (_i, [_fp, _vp, _i, _i, _i, _i, _i, _fp, _i, _vp]),
@@ -52,6 +60,7 @@ _SIGS = {
     "fsr_bce_logits": (_i, [_fp, _fp, _f, _f, _i, _fp, _fp, _f, _vp]),
     "fsr_smooth_l1": (_i, [_vp, _vp, _sz, _fp, _vp, _f, _i, _vp]),
     "fsr_instnorm_bwd": (_i, [_vp, _fp, _vp, _fp, _vp, _fp, _fp, _i, _i, _i, _i, _f, _f, _i, _vp]),
+    "fsr_instnorm_bwd_parity": (_i, [_vp, _fp, _vp, _vp, _fp, _fp, _i, _i, _i, _i, _i, _f, _f, _i, _vp]),
     "fsr_act_bwd": (_i, [_vp, _vp, _vp, _sz, _fp, _f, _i, _fp, _i, _vp]),
     "fsr_ps_prelu_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _fp, _fp, _i, _vp]),
     "fsr_tanh_bwd": (_i, [_fp, _fp, _fp, _sz, _vp]),

@@ -729,6 +729,30 @@ int fsr_pack_conv3x3_weight(const float* w_oihw, const float* bias, void* w_pack
   return cuda_rc(cudaGetLastError());
 }
 
+int fsr_pack_multi(const FsrPackTask* tasks, int n, int dtype, void* stream) {
+  if (!tasks || n <= 0 || n > kPackMaxTasks) return FSR_ERR_BAD_ARG;
+  PackMultiParams p{};
+  p.n = n;
+  int blocks = 0;
+  for (int i = 0; i < n; ++i) {
+    const FsrPackTask& t = tasks[i];
+    if (!t.w || !t.out || t.cout <= 0 || t.cin <= 0 || t.pad < ((t.flags & 1) ? t.cin : t.cout)) return FSR_ERR_BAD_ARG;
+    p.t[i] = PackTaskDev{t.w, t.out, t.bias, t.bias_out, t.row_scale, t.cout, t.cin, t.pad, t.flags};
+    const size_t total = (size_t)9 * t.pad * ((t.flags & 1) ? t.cout : t.cin);
+    int nb = (int)((total + 256 * 8 - 1) / (256 * 8));       // ~8 elements per thread
+    if (nb < 1) nb = 1;
+    if (nb > 64) nb = 64;
+    p.block_begin[i] = blocks;
+    blocks += nb;
+  }
+  p.block_begin[n] = blocks;
+  cudaStream_t st = (cudaStream_t)stream;
+  LaunchScope scope(FSR_K_NONE - 1, st);
+  if (dtype == FSR_BF16) pack_multi_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(p);
+  else pack_multi_kernel<__half><<<blocks, 256, 0, st>>>(p);
+  return cuda_rc(cudaGetLastError());
+}
+
 int fsr_conv3x3_c64(const void* x, const void* w_packed, void* out, const float* bias, int64_t* stats,
                     const float* alpha, int N, int H, int W, int cout, int epilogue, int act, float slope,
                     int out_u8, int dtype, void* stream) {
@@ -1281,13 +1305,15 @@ int fsr_smooth_l1(const void* a, const void* b, size_t n, float* loss_acc, void*
   return cuda_rc(cudaGetLastError());
 }
 
-int fsr_instnorm_bwd(const void* raw, const int64_t* stats, const void* dy, float* red, void* draw, const float* alpha,
-                     float* dalpha, int N, int HW, int C, int act, float slope, float eps, int dtype, void* stream) {
+static int instnorm_bwd_impl(const void* raw, const int64_t* stats, const void* dy, float* red, void* draw, const float* alpha,
+                             float* dalpha, int N, int HW, int C, int act, float slope, float eps, int dy_parity_w, int dtype, void* stream) {
   if (!raw || !stats || !dy || !draw || C % 8 || 256 % (C / 8)) return FSR_ERR_BAD_ARG;
   if (act == FSR_ACT_PRELU && !alpha) return FSR_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  InBwdParams p{raw, reinterpret_cast<const long long*>(stats), dy, red, draw, alpha, dalpha, slope, act, HW, C, eps};
-  if (C % 16 == 0 && HW <= 4096 && in_bwd_fused_mode()) {
+  InBwdParams p{raw, reinterpret_cast<const long long*>(stats), dy, red, draw, alpha, dalpha, slope, act, HW, C, eps, dy_parity_w};
+  const bool fused = C % 16 == 0 && HW <= 4096 && in_bwd_fused_mode();
+  if (dy_parity_w && (!fused || (dy_parity_w & 1) || HW % dy_parity_w || ((HW / dy_parity_w) & 1))) return FSR_ERR_BAD_SHAPE;
+  if (fused) {
     // training shapes: one launch, the per-(n,c) sums stay inside the block (no `red` scratch, no memset, no atomics)
     LaunchScope scope(FSR_K_NONE - 1, st);
     FSR_T((instnorm_bwd_fused_kernel<__half><<<dim3(C / 16, N), 256, 0, st>>>(p)),
@@ -1312,6 +1338,16 @@ int fsr_instnorm_bwd(const void* raw, const int64_t* stats, const void* dy, floa
     FSR_T((instnorm_bwd_kernel<__half, 2><<<grid, 256, sm, st>>>(p)), (instnorm_bwd_kernel<__nv_bfloat16, 2><<<grid, 256, sm, st>>>(p)));
   }
   return cuda_rc(cudaGetLastError());
+}
+
+int fsr_instnorm_bwd(const void* raw, const int64_t* stats, const void* dy, float* red, void* draw, const float* alpha,
+                     float* dalpha, int N, int HW, int C, int act, float slope, float eps, int dtype, void* stream) {
+  return instnorm_bwd_impl(raw, stats, dy, red, draw, alpha, dalpha, N, HW, C, act, slope, eps, 0, dtype, stream);
+}
+
+int fsr_instnorm_bwd_parity(const void* raw, const int64_t* stats, const void* dy_parity, void* draw, const float* alpha, float* dalpha,
+                            int N, int H, int W, int C, int act, float slope, float eps, int dtype, void* stream) {
+  return instnorm_bwd_impl(raw, stats, dy_parity, nullptr, draw, alpha, dalpha, N, H * W, C, act, slope, eps, W, dtype, stream);
 }
 
 int fsr_act_bwd(const void* y, const void* dy, void* dv, size_t n_elems, const float* alpha, float slope, int act,

@@ -307,4 +307,67 @@ __global__ void permute_bias_ps_kernel(const float* __restrict__ b, float* __res
   out[row] = v;
 }
 
+// All weight packs of a network in ONE launch (the training step re-packs every conv of G and D after each AdamW step:
+// 54 launches of ~4 us each).  Task = one fsr_pack_conv3x3_weight / _t call; a block finds its task by a linear scan.
+constexpr int kPackMaxTasks = 48;
+struct PackTaskDev {
+  const float* w; void* out; const float* bias; float* bias_out; const float* row_scale;
+  int cout, cin, pad, flags;        // flags: 1 = transposed (data-gradient) pack, 2 = ps_perm, 4 = flip; pad = cout_pad | row_pad
+};
+struct PackMultiParams {
+  PackTaskDev t[kPackMaxTasks];
+  int block_begin[kPackMaxTasks + 1];
+  int n;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) pack_multi_kernel(const __grid_constant__ PackMultiParams p) {
+  int ti = 0;
+  while (ti + 1 < p.n && (int)blockIdx.x >= p.block_begin[ti + 1]) ++ti;
+  const PackTaskDev& k = p.t[ti];
+  const int nb = p.block_begin[ti + 1] - p.block_begin[ti], b = blockIdx.x - p.block_begin[ti];
+  const int cout = k.cout, cin = k.cin;
+  const bool ps = k.flags & 2, flip = k.flags & 4;
+  T* out = reinterpret_cast<T*>(k.out);
+  if (k.flags & 1) {
+    const int row_pad = k.pad;
+    const size_t total = (size_t)9 * row_pad * cout;
+    for (size_t idx = (size_t)b * 256 + threadIdx.x; idx < total; idx += (size_t)nb * 256) {
+      const int col = (int)(idx % cout), ci = (int)((idx / cout) % row_pad), tap = (int)(idx / ((size_t)cout * row_pad));
+      float v = 0.f;
+      if (ci < cin) {
+        int oc = col;
+        if (ps) { const int cq = cout / 4; oc = 4 * (col % cq) + col / cq; }
+        v = k.w[((size_t)oc * cin + ci) * 9 + (flip ? 8 - tap : tap)];
+        if (k.row_scale) v *= k.row_scale[ci];
+      }
+      out[idx] = Cvt<T>::from_f(v);
+    }
+  } else {
+    const int cout_pad = k.pad;
+    const size_t total = (size_t)9 * cout_pad * cin;
+    for (size_t idx = (size_t)b * 256 + threadIdx.x; idx < total; idx += (size_t)nb * 256) {
+      const int ci = (int)(idx % cin), row = (int)((idx / cin) % cout_pad), tap = (int)(idx / ((size_t)cin * cout_pad));
+      float v = 0.f;
+      if (row < cout) {
+        int oc = row;
+        if (ps) { const int cq = cout / 4; oc = 4 * (row % cq) + row / cq; }
+        v = k.w[((size_t)oc * cin + ci) * 9 + tap];
+      }
+      out[idx] = Cvt<T>::from_f(v);
+    }
+    if (k.bias && k.bias_out) {
+      for (int row = b * 256 + threadIdx.x; row < cout_pad; row += nb * 256) {
+        float v = 0.f;
+        if (row < cout) {
+          int oc = row;
+          if (ps) { const int cq = cout / 4; oc = 4 * (row % cq) + row / cq; }
+          v = k.bias[oc];
+        }
+        k.bias_out[row] = v;
+      }
+    }
+  }
+}
+
 }  // namespace fsr

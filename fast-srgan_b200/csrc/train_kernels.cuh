@@ -247,6 +247,8 @@ struct InBwdParams {
   int act;
   int HW, C;
   float eps;
+  int dy_parity_w;       // > 0: `dy` is in the parity-plane layout [N][4][H/2][W/2][C] a stride-2 data gradient writes
+                         //      (image width W = dy_parity_w): folds fsr_parity_layout(from parity) into this pass (fused kernel)
 };
 
 template <typename T, int PASS>
@@ -359,11 +361,18 @@ __global__ void __launch_bounds__(256) instnorm_bwd_fused_kernel(const InBwdPara
   const T* raw = reinterpret_cast<const T*>(p.raw) + base;
   const T* dy = reinterpret_cast<const T*>(p.dy) + base;
   T* draw = reinterpret_cast<T*>(p.draw) + base;
+  // pixel index of `dy` for NHWC pixel px (identity, or the parity-plane position of (y, x))
+  const int pw = p.dy_parity_w, pw2 = pw >> 1, ph2 = pw ? (p.HW / pw) >> 1 : 0;
+  auto dy_px = [&](int px) -> size_t {
+    if (!pw) return (size_t)px;
+    const int y = px / pw, x = px - y * pw;
+    return (size_t)(((y & 1) * 2 + (x & 1)) * ph2 + (y >> 1)) * pw2 + (x >> 1);
+  };
   float a1[8], a2[8], da = 0.f;
 #pragma unroll
   for (int k = 0; k < 8; ++k) { a1[k] = 0.f; a2[k] = 0.f; }
   for (int px = pl; px < p.HW; px += 128) {
-    const uint4 r = *reinterpret_cast<const uint4*>(raw + (size_t)px * p.C), g4 = *reinterpret_cast<const uint4*>(dy + (size_t)px * p.C);
+    const uint4 r = *reinterpret_cast<const uint4*>(raw + (size_t)px * p.C), g4 = *reinterpret_cast<const uint4*>(dy + dy_px(px) * p.C);
     const uint32_t ru[4] = {r.x, r.y, r.z, r.w}, gu[4] = {g4.x, g4.y, g4.z, g4.w};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -413,7 +422,7 @@ __global__ void __launch_bounds__(256) instnorm_bwd_fused_kernel(const InBwdPara
 #pragma unroll
   for (int k = 0; k < 8; ++k) { m1[k] = s_m[vec][k]; m2[k] = s_m[vec][8 + k]; }
   for (int px = pl; px < p.HW; px += 128) {
-    const uint4 r = *reinterpret_cast<const uint4*>(raw + (size_t)px * p.C), g4 = *reinterpret_cast<const uint4*>(dy + (size_t)px * p.C);
+    const uint4 r = *reinterpret_cast<const uint4*>(raw + (size_t)px * p.C), g4 = *reinterpret_cast<const uint4*>(dy + dy_px(px) * p.C);
     const uint32_t ru[4] = {r.x, r.y, r.z, r.w}, gu[4] = {g4.x, g4.y, g4.z, g4.w};
     uint32_t ou[4];
 #pragma unroll

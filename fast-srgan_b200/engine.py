@@ -173,6 +173,26 @@ class GeneratorNet:
             names += [f"stem.{i}.conv1.weight", f"stem.{i}.conv2.weight"]
         return names + ["bottleneck.0.weight"]
 
+    def _plans(self):
+        """The fixed pack lists (forward / data-gradient layouts): destination buffers are allocated ONCE - a captured CUDA
+        graph keeps reading the right memory - and each list re-packs in ONE launch (ops.PackPlan / fsr_pack_multi)."""
+        if getattr(self, "_plan_fwd", None) is None:
+            p, P, dt = self.fp.p, self.P, self.dt
+            fwd, bwd = ops.PackPlan(dt), ops.PackPlan(dt)
+            for n in self._convs64():
+                P[n], _ = fwd.add(p[n])
+                # data-gradient pack: the 64-channel kernel takes flipped taps (forward tap table), the general kernel its own
+                # dgrad tap table (mode 1) on the unflipped transposed pack
+                P[n + ".t"], _ = bwd.add(p[n], transposed=True, flip=self.c64)
+            for i in range(2):
+                w, b = p[f"upsampling.{i}.conv.weight"], p[f"upsampling.{i}.conv.bias"]
+                P[f"up{i}.w"], P[f"up{i}.b"] = fwd.add(w, b, ps_perm=True)
+                P[f"up{i}.t"], _ = bwd.add(w, transposed=True, ps_perm=True)                      # gen-kernel dgrad
+            P["head.w"], P["head.b"] = fwd.add(p["head.0.weight"], p["head.0.bias"], pad=16)
+            P["head.t"] = torch.empty((self.F, 3, 3, 3), dtype=torch.float32, device=p["head.0.weight"].device)
+            self._plan_fwd, self._plan_bwd = fwd, bwd
+        return self._plan_fwd, self._plan_bwd
+
     def pack(self, need_bwd: bool, force: bool = False):
         """(Re)pack into PERSISTENT buffers (same addresses for the lifetime of the net): a captured CUDA graph keeps
         reading the right memory, and no allocation happens per step.  force: re-pack whatever the version counters
@@ -180,29 +200,14 @@ class GeneratorNet:
         every captured graph, not only of those captured while the Python-side version happened to be stale)."""
         if not force and self._packed_version == self.fp.version and (not need_bwd or self._bwd_version == self.fp.version):
             return
-        p, P, dt = self.fp.p, self.P, self.dt
-        fwd_stale = force or self._packed_version != self.fp.version
-        for n in self._convs64():
-            if fwd_stale:
-                P[n], _ = ops.pack_conv3x3(p[n], None, dt, out_w=P.get(n))
-            if need_bwd:
-                # data-gradient pack: the 64-channel kernel takes flipped taps (forward tap table), the general kernel its own
-                # dgrad tap table (mode 1) on the unflipped transposed pack
-                P[n + ".t"] = ops.pack_conv3x3_t(p[n], dt, flip=self.c64, out=P.get(n + ".t"))
-        for i in range(2):
-            w, b = p[f"upsampling.{i}.conv.weight"], p[f"upsampling.{i}.conv.bias"]
-            if fwd_stale:
-                P[f"up{i}.w"], P[f"up{i}.b"] = ops.pack_conv3x3(w, b, dt, ps_perm=True, out_w=P.get(f"up{i}.w"), out_b=P.get(f"up{i}.b"))
-            if need_bwd:
-                P[f"up{i}.t"] = ops.pack_conv3x3_t(w, dt, ps_perm=True, out=P.get(f"up{i}.t"))      # gen-kernel dgrad
-        if fwd_stale:
-            P["head.w"], P["head.b"] = ops.pack_conv3x3(p["head.0.weight"], p["head.0.bias"], dt, cout_pad=16,
-                                                        out_w=P.get("head.w"), out_b=P.get("head.b"))
+        fwd, bwd = self._plans()
+        dev = self.fp.flat.device
+        if force or self._packed_version != self.fp.version:
+            fwd.run(dev)
         if need_bwd:
+            bwd.run(dev)
             # head dgrad = direct 3->F conv with transposed, flipped weights (K = 27)
-            if "head.t" not in P:
-                P["head.t"] = torch.empty((self.F, 3, 3, 3), dtype=torch.float32, device=p["head.0.weight"].device)
-            P["head.t"].copy_(p["head.0.weight"].permute(1, 0, 2, 3).flip(2, 3))
+            self.P["head.t"].copy_(self.fp.p["head.0.weight"].permute(1, 0, 2, 3).flip(2, 3))
             self._bwd_version = self.fp.version
         self._packed_version = self.fp.version
 
@@ -307,19 +312,23 @@ class DiscriminatorNet:
         self.arena: Optional[ZeroArena] = None
 
     def pack(self, need_bwd: bool, force: bool = False):
-        """(Re)pack into persistent buffers (CUDA-graph safe, see GeneratorNet.pack)."""
+        """(Re)pack into persistent buffers, one launch per layout (CUDA-graph safe, see GeneratorNet.pack)."""
         if not force and self._packed_version == self.fp.version and (not need_bwd or self._bwd_version == self.fp.version):
             return
         p, P, dt = self.fp.p, self.P, self.dt
-        fwd_stale = force or self._packed_version != self.fp.version
-        for i in range(7):
-            w = p[f"stem.{i}.conv.weight"]
-            if fwd_stale:
-                P[f"w{i}"], _ = ops.pack_conv3x3(w, None, dt, out_w=P.get(f"w{i}"))
-            if need_bwd:
-                P[f"t{i}"] = ops.pack_conv3x3_t(w, dt, out=P.get(f"t{i}"))
+        if getattr(self, "_plan_fwd", None) is None:
+            fwd, bwd = ops.PackPlan(dt), ops.PackPlan(dt)
+            for i in range(7):
+                w = p[f"stem.{i}.conv.weight"]
+                P[f"w{i}"], _ = fwd.add(w)
+                P[f"t{i}"], _ = bwd.add(w, transposed=True)
+            P["neck.t"], _ = bwd.add(p["neck.0.weight"], transposed=True, flip=True, pad=16)        # 64 -> 3 image gradient
+            self._plan_fwd, self._plan_bwd = fwd, bwd
+        dev = self.fp.flat.device
+        if force or self._packed_version != self.fp.version:
+            self._plan_fwd.run(dev)
         if need_bwd:
-            P["neck.t"] = ops.pack_conv3x3_t(p["neck.0.weight"], dt, flip=True, row_pad=16, out=P.get("neck.t"))   # 64 -> 3 image gradient
+            self._plan_bwd.run(dev)
             self._bwd_version = self.fp.version
         self._packed_version = self.fp.version
 
@@ -353,16 +362,22 @@ class DiscriminatorNet:
         p, g, P = self.fp.p, self.fp.g, self.P
         dcur = ops.conv1x1_to1_bwd(ctx["act6"], p["stem.7.weight"].view(-1), dz,
                                    g["stem.7.weight"].view(-1) if wgrad else None, g["stem.7.bias"] if wgrad else None)
+        dcur_parity = False
         for i in reversed(range(7)):
             xin, raw, st = ctx["layers"][i]
             s = D_STRIDES[i]
-            draw = ops.instnorm_bwd(raw, st, dcur, act=L.ACT_LRELU, slope=0.01)
+            if dcur_parity:      # gradient from a stride-2 data gradient: read in its parity-plane layout (no re-layout pass)
+                draw = ops.instnorm_bwd_parity(raw, st, dcur, act=L.ACT_LRELU, slope=0.01)
+            else:
+                draw = ops.instnorm_bwd(raw, st, dcur, act=L.ACT_LRELU, slope=0.01)
             if wgrad:
                 ops.conv3x3_wgrad(xin, draw, g[f"stem.{i}.conv.weight"], stride=s)
             if i == 0 and not (wgrad or d_img is not None):
                 break
-            dx = ops.conv3x3_gen(draw, P[f"t{i}"], self.widths[i][0], stride=s, mode=1)
-            dcur = ops.parity_layout(dx, False) if s == 2 else dx
+            dcur = ops.conv3x3_gen(draw, P[f"t{i}"], self.widths[i][0], stride=s, mode=1)
+            dcur_parity = s == 2 and i > 0 and raw.shape[1] * raw.shape[2] * 4 <= 4096    # consumer plane = 4x this layer's output
+            if s == 2 and not dcur_parity:
+                dcur = ops.parity_layout(dcur, False)
         dv = ops.act_bwd(ctx["d0"], dcur, L.ACT_LRELU, slope=0.2)
         if wgrad:
             ops.wgrad_c3(ctx["img"], dv, g["neck.0.weight"], flip=False, layout=2)

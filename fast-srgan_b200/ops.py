@@ -45,6 +45,39 @@ def pack_conv3x3(weight: torch.Tensor, bias: Optional[torch.Tensor], dtype: torc
     return wp, bp
 
 
+class PackPlan:
+    """A fixed list of weight packs executed as ONE launch (fsr_pack_multi).  add() allocates the persistent destination
+    buffer and returns it; run() re-packs everything from the current parameter values."""
+
+    def __init__(self, dtype: torch.dtype):
+        self.dtype = dtype
+        self.tasks = []
+        self._arr = None
+        self._keep = []
+
+    def add(self, weight, bias=None, transposed=False, ps_perm=False, flip=False, pad=None, row_scale=None):
+        _cuda(weight, bias, row_scale)
+        assert weight.dtype == torch.float32 and weight.is_contiguous()
+        cout, cin = weight.shape[0], weight.shape[1]
+        pad = pad or (cin if transposed else cout)
+        shape = (9, pad, cout) if transposed else (9, pad, cin)
+        out = torch.empty(shape, dtype=self.dtype, device=weight.device)
+        bout = torch.empty(pad, dtype=torch.float32, device=weight.device) if (bias is not None and not transposed) else None
+        flags = (L.PACK_T if transposed else 0) | (L.PACK_PS if ps_perm else 0) | (L.PACK_FLIP if flip else 0)
+        self.tasks.append(L.FsrPackTask(weight.data_ptr(), out.data_ptr(), L.ptr(bias), L.ptr(bout), L.ptr(row_scale), cout, cin, pad, flags))
+        self._keep += [weight, bias, row_scale, out, bout]
+        self._arr = None
+        return out, bout
+
+    def run(self, device):
+        if not self.tasks:
+            return
+        if self._arr is None:
+            self._arr = [(L.FsrPackTask * len(chunk))(*chunk) for chunk in (self.tasks[i:i + 48] for i in range(0, len(self.tasks), 48))]
+        for arr in self._arr:
+            L.check(L.load().fsr_pack_multi(arr, len(arr), L.dtype_code(self.dtype), L.stream_ptr(device)), "pack_multi")
+
+
 def conv3x3_c64_raw_stats(x: torch.Tensor, w_packed: torch.Tensor, stats: Optional[torch.Tensor] = None):
     """x NHWC [N,H,W,64] -> (raw NHWC [N,H,W,cout], stats [N,cout,2] fp32 (sum, sumsq))."""
     _cuda(x, w_packed)
@@ -414,6 +447,17 @@ def instnorm_bwd(raw, stats, dy, act=L.ACT_NONE, slope=0.0, alpha=None, dalpha=N
     L.check(L.load().fsr_instnorm_bwd(raw.data_ptr(), stats.data_ptr(), dy.data_ptr(), red.data_ptr(), draw.data_ptr(), L.ptr(alpha),
                                       L.ptr(dalpha), N, H * W, C, act, slope, eps, L.dtype_code(raw.dtype), L.stream_ptr(raw.device)),
             "instnorm bwd")
+    return draw
+
+
+def instnorm_bwd_parity(raw, stats, dy_parity, act=L.ACT_NONE, slope=0.0, alpha=None, dalpha=None, eps=1e-5):
+    """instnorm_bwd with dy in the parity-plane layout [N,4,H/2,W/2,C] (output of a stride-2 data gradient)."""
+    _cuda(raw, stats, dy_parity, alpha, dalpha)
+    N, H, W, C = raw.shape
+    draw = torch.empty_like(raw)
+    L.check(L.load().fsr_instnorm_bwd_parity(raw.data_ptr(), stats.data_ptr(), dy_parity.data_ptr(), draw.data_ptr(), L.ptr(alpha),
+                                             L.ptr(dalpha), N, H, W, C, act, slope, eps, L.dtype_code(raw.dtype), L.stream_ptr(raw.device)),
+            "instnorm bwd (parity dy)")
     return draw
 
 

@@ -48,6 +48,19 @@ const char* fsr_error_string(int code);
 int fsr_pack_conv3x3_weight(const float* w_oihw, const float* bias, void* w_packed, float* bias_packed, int cout,
                             int cin, int cout_pad, int ps_perm, int dtype, void* stream);
 
+/* Up to 48 packs (any mix of fsr_pack_conv3x3_weight and fsr_pack_conv3x3_weight_t) in ONE launch: the training step
+ * re-packs every conv of a network after each AdamW step (trainer.py:181,196).  `tasks` is a HOST array; pad = cout_pad
+ * (forward pack) or row_pad (transposed pack); flags: FSR_PACK_T = transposed (data-gradient) pack, FSR_PACK_PS = ps_perm,
+ * FSR_PACK_FLIP = flipped taps; bias / bias_out / row_scale nullable. */
+#define FSR_PACK_T 1
+#define FSR_PACK_PS 2
+#define FSR_PACK_FLIP 4
+typedef struct {
+  const float* w; void* out; const float* bias; float* bias_out; const float* row_scale;
+  int cout, cin, pad, flags;
+} FsrPackTask;
+int fsr_pack_multi(const FsrPackTask* tasks, int n, int dtype, void* stream);
+
 /* 3x3 / stride 1 / pad 1 convolution, Cin = 64, on tcgen05 tensor cores (implicit GEMM, TMA-fed).
  * Replaces torch.nn.Conv2d at model.py:30-35 (UpSamplingBlock.conv), :47-54/:57-64 (ResidualBlock
  * conv1/conv2), :87-93 (bottleneck), :103-108 (head).
@@ -162,6 +175,10 @@ int fsr_smooth_l1(const void* a, const void* b, size_t n, float* loss_acc, void*
  * statistics and dY, writes dRaw; PReLU slope gradient accumulated into dalpha.  red = [N][C][2] fp32 scratch. */
 int fsr_instnorm_bwd(const void* raw, const int64_t* stats, const void* dy, float* red, void* draw, const float* alpha,
                      float* dalpha, int N, int HW, int C, int act, float slope, float eps, int dtype, void* stream);
+/* same with dy given in the parity-plane layout [N][4][H/2][W/2][C] that a stride-2 data gradient (fsr_conv3x3_gen mode 1)
+ * writes: folds the re-layout pass into the backward (planes <= 64x64, C % 16 == 0). */
+int fsr_instnorm_bwd_parity(const void* raw, const int64_t* stats, const void* dy_parity, void* draw, const float* alpha, float* dalpha,
+                            int N, int H, int W, int C, int act, float slope, float eps, int dtype, void* stream);
 /* activation backward from the stored post-activation tensor (neck PReLU / LeakyReLU). */
 int fsr_act_bwd(const void* y, const void* dy, void* dv, size_t n_elems, const float* alpha, float slope, int act,
                 float* dalpha, int dtype, void* stream);

@@ -171,6 +171,24 @@ def test_instnorm_bwd(dt, mode):
 
 
 @pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("shape", [(3, 128, 24, 24), (2, 64, 48, 48), (5, 512, 12, 12)])
+def test_instnorm_bwd_with_parity_layout_gradient(dt, shape):
+    """fsr_instnorm_bwd_parity (dy read straight from a stride-2 data gradient's parity planes) == re-layout + fsr_instnorm_bwd,
+    and fsr_instnorm_apply_parity == fsr_instnorm_apply + re-layout: same bits."""
+    from fast_srgan_b200 import ops, _lib as L
+    N, C, H, W = shape
+    raw = nhwc(rnd(shape, 31), dt)
+    dy = nhwc(rnd(shape, 32, 0.1), dt)
+    stats = ops.stats_from_float(raw.float().sum(dim=(1, 2)), (raw.float() ** 2).sum(dim=(1, 2)))
+    a = ops.instnorm_bwd(raw, stats, dy, act=L.ACT_LRELU, slope=0.01)
+    b = ops.instnorm_bwd_parity(raw, stats, ops.parity_layout(dy, True), act=L.ACT_LRELU, slope=0.01)
+    assert torch.equal(a, b)
+    y = ops.instnorm_apply(raw, stats, act=L.ACT_LRELU, slope=0.01)
+    yp = ops.instnorm_apply_parity(raw, stats, act=L.ACT_LRELU, slope=0.01)
+    assert torch.equal(ops.parity_layout(y, True), yp)
+
+
+@pytest.mark.parametrize("dt", DT)
 def test_vgg_pool_and_relu_bwd(dt):
     from fast_srgan_b200 import ops
     x = F.relu(rnd((2, 64, 8, 12), 14)).to(dt).float()
