@@ -227,6 +227,9 @@ int small_mma_mode() {
   return g_small_mma;
 }
 
+// fsr_set_pair_rows: the calling thread's 64-channel convs run on pair-expanded weights (pairs.py) until switched off
+thread_local int tl_pair_rows = 0;
+
 template <int NS, int EPI, typename T, bool HALO1, int XF = 0>
 int launch_conv(const void* x, const void* w_packed, int w_rows, ConvParams p, int dtype, cudaStream_t st) {
   using Cfg = ConvCfg<NS, HALO1>;
@@ -240,7 +243,8 @@ int launch_conv(const void* x, const void* w_packed, int w_rows, ConvParams p, i
   p.tiles_x = (p.W + Geo::TW - 1) / Geo::TW;
   p.tiles_y = (p.H + Geo::TH - 1) / Geo::TH;
   p.num_tiles = p.N * p.tiles_x * p.tiles_y;
-  p.ws = ws_mode();
+  p.pair_rows = tl_pair_rows;
+  p.ws = NS >= 64 ? ws_mode() : 0;   // tcgen05.mma.ws needs N >= 64 (the 16-column head variant faults with it)
   {
     static int backoff = -1;
     if (backoff < 0) { const char* e = getenv("FSR_BACKOFF_NS"); backoff = e ? atoi(e) : 0; }
@@ -286,6 +290,7 @@ int launch_up_2cta(const void* x, const void* w_packed, ConvParams p, int dtype,
     FSR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_done = true;
   }
+  p.pair_rows = tl_pair_rows;
   p.tiles_x = (p.W + Geo::TW - 1) / Geo::TW;
   p.tiles_y = (p.H + Geo::TH - 1) / Geo::TH;
   p.num_tiles = p.N * p.tiles_x * p.tiles_y;
@@ -763,6 +768,57 @@ int fsr_conv3x3_c64(const void* x, const void* w_packed, void* out, const float*
   return conv_dispatch<__half>(x, w_packed, out, bias, reinterpret_cast<long long*>(stats), alpha, N, H, W, cout, epilogue, act, slope, out_u8, dtype, st);
 }
 
+// ---- n_filters = 32 networks on "pixel-pair rows" (DESIGN.md 3.7): [N,H,W,32] viewed as [N,H,W/2,64] --------------
+// The 64-channel kernels run unchanged on the pair grid with weights expanded on the host (fast_srgan_b200/pairs.py);
+// the two entries below are what the pair view adds: folding the per-(parity, channel) InstanceNorm sums into
+// per-channel ones, and a head that writes two rgb pixels per row.
+__global__ void in_stats_fold_pair_kernel(long long* __restrict__ stats, int total) {
+  // stats [N][64][2] of the pair grid; channel c of the 32-channel network lives in slots c and 32+c.  The consumers
+  // divide by the PAIR count H*W/2, so both slots receive half the merged sums (exact: fixed-point integers, floor).
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;          // (n, c<32, k<2)
+  if (i >= total) return;
+  const int k = i & 1, c = (i >> 1) & 31, n = i >> 6;
+  long long* a = stats + ((size_t)n * 64 + c) * 2 + k;
+  long long* b = a + 64;
+  const long long m = (*a + *b) >> 1;
+  *a = m; *b = m;
+}
+
+int fsr_set_pair_rows(int on) {
+  tl_pair_rows = on ? 1 : 0;
+  return FSR_OK;
+}
+
+int fsr_in_stats_fold_pair(int64_t* stats, int N, void* stream) {
+  if (!stats) return FSR_ERR_BAD_ARG;
+  if (N <= 0) return FSR_ERR_BAD_SHAPE;
+  const int total = N * 64;
+  in_stats_fold_pair_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<long long*>(stats), total);
+  return cuda_rc(cudaGetLastError());
+}
+
+}  // extern "C"
+template <typename T>
+static int head_pair_dispatch(const void* x, const void* w_packed, void* out, const float* bias, int N, int H, int Wp, int out_u8,
+                              int dtype, cudaStream_t st) {
+  ConvParams p{};
+  p.N = N; p.H = H; p.W = Wp;
+  p.out = out; p.bias = bias; p.act = 2; p.out_u8 = out_u8;
+  p.cout_total = 16; p.num_slices = 1;
+  return launch_conv<16, EPI_HEAD_TANH, T, true>(x, w_packed, 9 * 16, p, dtype, st);
+}
+extern "C" {
+
+int fsr_conv3x3_c64_head_pair(const void* x, const void* w_packed, void* out, const float* bias, int N, int H, int Wp,
+                              int out_u8, int dtype, void* stream) {
+  if (!x || !w_packed || !out) return FSR_ERR_BAD_ARG;
+  if (N <= 0 || H <= 0 || Wp <= 0) return FSR_ERR_BAD_SHAPE;
+  if (out_u8 < 0 || out_u8 > 1) return FSR_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == FSR_BF16) return head_pair_dispatch<__nv_bfloat16>(x, w_packed, out, bias, N, H, Wp, out_u8, dtype, st);
+  return head_pair_dispatch<__half>(x, w_packed, out, bias, N, H, Wp, out_u8, dtype, st);
+}
+
 int fsr_conv3x3_c64_in(const void* x_raw, const int64_t* in_stats, const float* in_alpha, float in_eps, const void* w_packed,
                        void* out, int64_t* stats, int N, int H, int W, int dtype, void* stream) {
   if (!x_raw || !in_stats || !in_alpha || !w_packed || !out || !stats || x_raw == out) return FSR_ERR_BAD_ARG;
@@ -836,11 +892,12 @@ int fsr_conv3x3_head(const void* x, const void* w_packed, void* out, const float
   return launch_head<__half>(x, w_packed, p, dtype, st, cin);
 }
 
-int fsr_neck_conv3x3(const void* x, const float* w, const float* bias, const float* alpha, void* out, int N, int H,
-                     int W, int cout, int act, float slope, int in_u8, int vgg_norm, int dtype, void* stream) {
+static int neck_impl(const void* x, const float* w, const float* bias, const float* alpha, void* out, int N, int H,
+                     int W, int cout, int act, float slope, int in_u8, int vgg_norm, int pitch, int dtype, void* stream) {
   if (!x || !w || !out || cout % 64 || N <= 0 || H <= 0 || W <= 0) return FSR_ERR_BAD_ARG;
   if (act == FSR_ACT_PRELU && !alpha) return FSR_ERR_BAD_ARG;
-  NeckParams p{x, w, bias, alpha, out, N, H, W, cout, act, slope, in_u8, vgg_norm};
+  if (pitch && !small_mma_mode()) return FSR_ERR_BAD_ARG;
+  NeckParams p{x, w, bias, alpha, out, N, H, W, cout, act, slope, in_u8, vgg_norm, pitch};
   const size_t total = (size_t)N * H * W;
   cudaStream_t st = (cudaStream_t)stream;
   LaunchScope scope(FSR_K_NECK, st);
@@ -872,6 +929,16 @@ int fsr_neck_conv3x3(const void* x, const float* w, const float* bias, const flo
     else neck_conv3x3_kernel<__half, 2><<<grid, 256, 0, st>>>(p);
   }
   return cuda_rc(cudaGetLastError());
+}
+
+int fsr_neck_conv3x3(const void* x, const float* w, const float* bias, const float* alpha, void* out, int N, int H,
+                     int W, int cout, int act, float slope, int in_u8, int vgg_norm, int dtype, void* stream) {
+  return neck_impl(x, w, bias, alpha, out, N, H, W, cout, act, slope, in_u8, vgg_norm, 0, dtype, stream);
+}
+
+int fsr_neck_conv3x3_c32(const void* x, const float* w64, const float* bias64, const float* alpha, void* out, int N, int H,
+                         int W, int act, float slope, int in_u8, int dtype, void* stream) {
+  return neck_impl(x, w64, bias64, alpha, out, N, H, W, 64, act, slope, in_u8, 0, 32, dtype, stream);
 }
 
 static int instnorm_apply_impl(const void* raw, const int64_t* stats, const void* residual, void* out, const float* alpha,

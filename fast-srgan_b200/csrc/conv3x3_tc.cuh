@@ -54,6 +54,8 @@ struct ConvParams {
   float slope;              // LeakyReLU slope (ACT_LRELU)
   int act;                  // ActMode (EPI_BIAS_ACT)
   int ws;                   // 1: weight-stationary MMAs (B re-used from the collector across the two interleaved tiles)
+  int pair_rows;            // 1: weights are pair-expanded (pairs.py): tap column 0 only has K in [32,64), column 2 only K in
+                            //    [0,32) -> those 12 of 36 k-steps multiply structural zeros and are not issued
   int out_u8;               // EPI_HEAD_TANH: 0 -> tanh, fp32 NCHW [N,3,H,W]; 1 -> tanh, uint8 NHWC [N,H,W,3];
                             //                2 -> linear (no tanh) fp32 NCHW store; 3 -> linear, accumulate (+=)
   // XF (fused input transform): the conv input is the RAW output of the previous conv; its InstanceNorm + PReLU
@@ -257,12 +259,15 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
               for (int k = 0; k < 4; ++k) {
                 const uint32_t aoff = (uint32_t)(((r * (TW + 2) + s) * 128 + k * 32) >> 4);
                 const uint64_t bdesc = desc_join(b_lo0 + (((r * 3 + s) * (NS * 128) + k * 32) >> 4), kDescHiSw128);
+                if (p.pair_rows && ((s == 0 && k < 2) || (s == 2 && k >= 2))) continue;   // structural zeros
+                // first issued k-step overwrites the accumulator: (r,s,k) = (0,0,0), or (0,0,2) on pair rows
+                const uint32_t accf = (r | s) != 0 ? 1u : (p.pair_rows ? (k > 2 ? 1u : 0u) : (k != 0 ? 1u : 0u));
                 if (two && p.ws) {
-                  umma_f16_ws_fill(d_a, desc_join(a_lo_a + aoff, hi), bdesc, idesc, (s | r | k) != 0 ? 1u : 0u);
-                  umma_f16_ws_lastuse(d_b, desc_join(a_lo_b + aoff, hi), bdesc, idesc, (s | r | k) != 0 ? 1u : 0u);
+                  umma_f16_ws_fill(d_a, desc_join(a_lo_a + aoff, hi), bdesc, idesc, accf);
+                  umma_f16_ws_lastuse(d_b, desc_join(a_lo_b + aoff, hi), bdesc, idesc, accf);
                 } else {
-                  umma_f16(d_a, desc_join(a_lo_a + aoff, hi), bdesc, idesc, (s | r | k) != 0 ? 1u : 0u);
-                  if (two) umma_f16(d_b, desc_join(a_lo_b + aoff, hi), bdesc, idesc, (s | r | k) != 0 ? 1u : 0u);
+                  umma_f16(d_a, desc_join(a_lo_a + aoff, hi), bdesc, idesc, accf);
+                  if (two) umma_f16(d_b, desc_join(a_lo_b + aoff, hi), bdesc, idesc, accf);
                 }
               }
             }
@@ -493,27 +498,37 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty_bar[acc]);
         if (pvalid) {
-          float o[3];
+          // p.act == 2: "pixel-pair rows" (n_filters = 32 networks, engine docs DESIGN.md 3.7): one 128-byte row holds
+          // two horizontally adjacent 32-channel pixels, the GEMM has 6 real columns (pixel parity, rgb) and the image
+          // is 2*p.W wide
+          const int npx = p.act == 2 ? 2 : 1;
+          const int Wt = p.W * npx;
 #pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            const float v = __uint_as_float(r[c]) + smem_bias[c];
-            o[c] = p.out_u8 >= 2 ? v : tanhf(v);
-          }
-          if (p.out_u8 == 1) {
-            // reference inference.py:54-56: ((y+1)/2*255).astype(uint8)  (truncation)
-            uint8_t* o8 = reinterpret_cast<uint8_t*>(p.out) + ((size_t)(n * p.H + y) * p.W + x) * 3;
+          for (int po = 0; po < 2; ++po) {
+            if (po >= npx) break;
+            const int xt = x * npx + po;
+            float o[3];
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-              float f = (o[c] + 1.0f) / 2.0f * 255.0f;
-              o8[c] = (uint8_t)(int)fminf(fmaxf(f, 0.f), 255.f);
+              const float v = __uint_as_float(r[po * 3 + c]) + smem_bias[po * 3 + c];
+              o[c] = p.out_u8 >= 2 ? v : tanhf(v);
             }
-          } else {
-            float* of = reinterpret_cast<float*>(p.out);
-            const size_t plane = (size_t)p.H * p.W;
+            if (p.out_u8 == 1) {
+              // reference inference.py:54-56: ((y+1)/2*255).astype(uint8)  (truncation)
+              uint8_t* o8 = reinterpret_cast<uint8_t*>(p.out) + ((size_t)(n * p.H + y) * Wt + xt) * 3;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-              float* dst = of + ((size_t)n * 3 + c) * plane + (size_t)y * p.W + x;
-              *dst = (p.out_u8 == 3) ? *dst + o[c] : o[c];
+              for (int c = 0; c < 3; ++c) {
+                float f = (o[c] + 1.0f) / 2.0f * 255.0f;
+                o8[c] = (uint8_t)(int)fminf(fmaxf(f, 0.f), 255.f);
+              }
+            } else {
+              float* of = reinterpret_cast<float*>(p.out);
+              const size_t plane = (size_t)p.H * Wt;
+#pragma unroll
+              for (int c = 0; c < 3; ++c) {
+                float* dst = of + ((size_t)n * 3 + c) * plane + (size_t)y * Wt + xt;
+                *dst = (p.out_u8 == 3) ? *dst + o[c] : o[c];
+              }
             }
           }
         }

@@ -208,7 +208,9 @@ conv3x3_up_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
               for (int k = 0; k < 4; ++k) {
                 const uint32_t aoff = (uint32_t)(((r * (TW + 2) + s) * 128 + k * 32) >> 4);
                 const uint64_t bdesc = desc_join(b_lo0 + (((r * 3 + s) * ((Cfg::kN / 2) * 128) + k * 32) >> 4), kDescHiSw128);
-                umma_f16_pair(d_tmem, desc_join(a_lo + aoff, hi), bdesc, idesc, (s | r | k) != 0 ? 1u : 0u);
+                if (p.pair_rows && ((s == 0 && k < 2) || (s == 2 && k >= 2))) continue;   // structural zeros (pairs.py)
+                const uint32_t accf = (r | s) != 0 ? 1u : (p.pair_rows ? (k > 2 ? 1u : 0u) : (k != 0 ? 1u : 0u));
+                umma_f16_pair(d_tmem, desc_join(a_lo + aoff, hi), bdesc, idesc, accf);
               }
             }
           }

@@ -26,6 +26,7 @@ struct NeckParams {
   float slope;
   int in_u8;
   int vgg_norm;
+  int pitch;          // channels per stored pixel (0 = cout); < cout: only the first `pitch` channels are written (pair rows)
 };
 
 template <typename T, int TPP>

@@ -116,6 +116,7 @@ __global__ void __launch_bounds__(kNeckWarps * 32, 3) neck_conv3x3_mma_kernel(co
       }
   const float* bias_l = p.bias ? p.bias + cg * 64 + 16 * t : nullptr;   // lane's 16 channels (views of a flat buffer: 4-B aligned only)
   const float slope = (p.act == ACT_PRELU) ? __ldg(p.alpha) : p.slope;
+  const int pitch = p.pitch ? p.pitch : p.cout;
 
   const int tx = (p.W + 15) >> 4;
   const int rows = p.N * p.H;                    // host guarantees N*H*tx < 2^31
@@ -167,8 +168,8 @@ __global__ void __launch_bounds__(kNeckWarps * 32, 3) neck_conv3x3_mma_kernel(co
 #pragma unroll
     for (int rr = 0; rr < 2; ++rr) {
       const int x = x0 + g + 8 * rr;
-      if (x < p.W) {
-        T* o = reinterpret_cast<T*>(p.out) + ((size_t)(n * p.H + y) * p.W + x) * p.cout + cg * 64 + 16 * t;
+      if (x < p.W && cg * 64 + 16 * t < pitch) {
+        T* o = reinterpret_cast<T*>(p.out) + ((size_t)(n * p.H + y) * p.W + x) * pitch + cg * 64 + 16 * t;
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           uint4 pk;

@@ -176,6 +176,7 @@ class Generator(torch.nn.Module):
         self._packed_key = None
         self._ws = None
         self._precise = None
+        self._pair = None
 
     # -- checkpoints saved from torch.compile'd modules carry `_orig_mod.` (inference.py:30-33)
     def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
@@ -306,6 +307,12 @@ class Generator(torch.nn.Module):
             return self._precise.forward(x, out, in_u8, out_u8)
         if self.padded_filters != 64:
             return self._forward_wide(x, out, in_u8, out_u8)
+        if self.n_filters <= 32 and W % 2 == 0 and os.environ.get("FSR_PAIR32", "1") != "0":
+            # two 32-channel pixels per 128-byte row (pairs.py): half the zero-padding cost of the 64-channel chain
+            if self._pair is None:
+                from .pairs import PairGenerator
+                self._pair = PairGenerator(self)
+            return self._pair.forward(x, out, in_u8, out_u8)
         P = self._params_struct()
         ws, need = self._workspace(N, H, W, x.device)
         rc = L.load().fsr_generator_forward(P, x.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel(), N, H, W,

@@ -361,6 +361,28 @@ int fsr_neck_conv3x3_f32(const float* x, const float* w, const float* bias, cons
                          void* stream);
 /* InstanceNorm statistics (model.py:55,65,94) of an fp32 NHWC tensor [N,HW,64]: stats [N,64,2] int64 fixed point +=, caller zeroes */
 int fsr_in_stats_f32(const float* x, int64_t* stats, int N, int HW, void* stream);
+
+/* ---- n_filters = 32 generators (reference configs/config.yaml allows any n_filters; model.py:72-99) ----------------
+ * A 32-channel NHWC tensor [N,H,W,32] (W even) is byte-identical to a 64-channel one on the "pixel-pair grid"
+ * [N,H,W/2,64]; with the conv weights expanded on the host (fast_srgan_b200/pairs.py) the 64-channel kernels above
+ * compute the 32-channel convolutions on it at half the zero-padding cost.  Two things differ on the pair grid:
+ *  - fsr_in_stats_fold_pair: merge the InstanceNorm sums of slots c and 32+c (same channel, two pixel parities) of a
+ *    stats block [N][64][2] written by FSR_EPI_RAW_STATS / fsr_conv3x3_c64_in, in place, so that the consumers
+ *    (fsr_instnorm_apply, fsr_conv3x3_c64_in) normalise per real channel (model.py:14-24 InstanceNorm2d);
+ *  - fsr_conv3x3_c64_head_pair: the 32->3 head + tanh (model.py:102-110) over pair rows; w_packed = pack of the
+ *    expanded [6 (parity, rgb) -> 16][64][3][3] weight, bias[6]; out = fp32 NCHW [N,3,H,2*Wp] (out_u8 = 0) or uint8
+ *    NHWC [N,H,2*Wp,3] (out_u8 = 1, inference.py:54-56). */
+/* 3->32 neck conv + activation (model.py:75-78) storing 32-channel pixels [N,H,W,32] (= pair rows [N,H,W/2,64]);
+ * w64/bias64 = the [32,3,3,3] weight and [32] bias zero-padded to 64 output channels. */
+int fsr_neck_conv3x3_c32(const void* x, const float* w64, const float* bias64, const float* alpha, void* out, int N, int H,
+                         int W, int act, float slope, int in_u8, int dtype, void* stream);
+/* Performance hint for the CALLING THREAD's following fsr_conv3x3_c64 / _c64_in / _c64_head_pair launches: the packed
+ * weights are pair-expanded, i.e. tap column 0 only has input slots 32..63 and tap column 2 only 0..31 non-zero, so 12 of
+ * the 36 K-steps per tile are not issued.  Results are identical to on = 0 for such weights; switch it off afterwards. */
+int fsr_set_pair_rows(int on);
+int fsr_in_stats_fold_pair(int64_t* stats, int N, void* stream);
+int fsr_conv3x3_c64_head_pair(const void* x, const void* w_packed, void* out, const float* bias, int N, int H, int Wp,
+                              int out_u8, int dtype, void* stream);
 /* out = act((x - mean) * rstd) (+ residual), fp32 NHWC [N,HW,64]; hi/lo (both or neither): fp16 split planes of out */
 int fsr_in_apply_f32(const float* x, const int64_t* stats, const float* residual, float* out, void* hi, void* lo,
                      const float* alpha, int act, int N, int HW, float eps, void* stream);

@@ -19,7 +19,8 @@ if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")):
 B = 32
 print("| n_filters | n_layers | input | GFLOP/frame | ms/batch(32) | frames/s | whole-model TFLOP/s (algorithmic) | frac of %.0f |" % peak)
 print("|---|---|---|---|---|---|---|---|")
-for F, L in [(f, l) for f in (32, 64, 128) for l in (4, 8, 12, 16)]:
+FS = tuple(int(a) for a in sys.argv[1:]) or (32, 64, 128)
+for F, L in [(f, l) for f in FS for l in (4, 8, 12, 16)]:
     g = Generator(types.SimpleNamespace(n_filters=F, n_layers=L), compute_dtype=torch.float16)
     g = g.cuda().eval()
     for (h, w) in ((90, 160), (180, 320)):
