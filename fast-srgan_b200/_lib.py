@@ -107,6 +107,7 @@ _SIGS = {
     "fsr_in_stats_f32": (_i, [_fp, _vp, _i, _i, _vp]),
     "fsr_in_stats_fold_pair": (_i, [_vp, _i, _vp]),
     "fsr_set_pair_rows": (_i, [_i]),
+    "fsr_set_pdl": (_i, [_i]),
     "fsr_conv3x3_c64_head_pair": (_i, [_vp, _vp, _vp, _fp, _i, _i, _i, _i, _i, _vp]),
     "fsr_neck_conv3x3_c32": (_i, [_vp, _fp, _fp, _fp, _vp, _i, _i, _i, _i, _f, _i, _i, _vp]),
     "fsr_in_apply_f32": (_i, [_fp, _vp, _fp, _fp, _vp, _vp, _fp, _i, _i, _i, _f, _vp]),

@@ -40,6 +40,7 @@ struct MetricParams {
 };
 
 __global__ void __launch_bounds__(256) psnr_ssim_kernel(const MetricParams p) {
+  pdl_grid_sync();
   __shared__ float sp[26][27], st[26][27];
   __shared__ float rw[5][26][17];
   __shared__ double s_tmp[8];
@@ -123,6 +124,7 @@ struct CropResizeParams {
 };
 
 __global__ void __launch_bounds__(256) crop_resize_aa_kernel(const CropResizeParams p) {
+  pdl_grid_sync();
   extern __shared__ __align__(16) uint8_t s_raw[];
   const int hr = p.lr_size * p.scale, lr = p.lr_size;
   uint8_t* crop = s_raw;

@@ -40,6 +40,37 @@ struct FsrCtxImpl {
 thread_local FsrCtxImpl* tl_ctx = nullptr;
 inline int ctx_opt(int key) { return tl_ctx ? tl_ctx->opt[key] : -1; }
 
+// Every kernel launch of the library goes through here.  With programmatic dependent launch on (FSR_PDL=1 or
+// fsr_set_pdl(1); default OFF) the launch carries the programmatic-stream-serialization attribute: the grid may become
+// resident while its predecessor drains and blocks in pdl_grid_sync() (fsr_common.cuh) until that grid has completed.
+// Measured (same box, profiles/r02/pdl_ab.md): results identical, but every launch got ~1.7 us SLOWER - GAN step b64
+// 6.57 -> 7.04 ms in one CUDA graph (284 programmatic edges), generator 7.90 -> 8.01 ms - so it stays an opt-in switch.
+int g_pdl = -1;
+inline int pdl_mode() {
+  if (g_pdl < 0) {
+    const char* e = getenv("FSR_PDL");
+    g_pdl = (e && e[0] == '1') ? 1 : 0;
+  }
+  return g_pdl;
+}
+struct PdlLaunch {
+  dim3 grid, block;
+  size_t smem;
+  cudaStream_t st;
+  PdlLaunch(dim3 g, dim3 b, size_t s, cudaStream_t stream) : grid(g), block(b), smem(s), st(stream) {}
+  template <typename... KArgs, typename... Args>
+  void operator()(void (*kern)(KArgs...), Args&&... args) const {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_mode() ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);   // errors surface through cudaGetLastError()
+  }
+};
+
 std::atomic<unsigned long long> g_launches{0};
 unsigned g_prof_mask = 0;            // bit k set: launches of kernel id k are bracketed with an event pair
 struct ProfRec { int id; cudaEvent_t a, b; double flops; };
@@ -268,7 +299,7 @@ int launch_conv(const void* x, const void* w_packed, int w_rows, ConvParams p, i
                     : EPI == EPI_HEAD_TANH ? FSR_K_CONV_HEAD : FSR_K_CONV_BIAS_ACT;
   {
     LaunchScope scope(kid, st, 2.0 * p.N * p.H * p.W * (double)(EPI == EPI_HEAD_TANH ? 3 : p.cout_total) * 64 * 9);
-    kern<<<grid, XF ? Cfg::kThreadsXf : Cfg::kThreads, Cfg::kSmemBytes, st>>>(tmx, tmw, tmo, p);
+    PdlLaunch(grid, XF ? Cfg::kThreadsXf : Cfg::kThreads, Cfg::kSmemBytes, st)(kern, tmx, tmw, tmo, p);
   }
   return cuda_rc(cudaGetLastError());
 }
@@ -306,7 +337,7 @@ int launch_up_2cta(const void* x, const void* w_packed, ConvParams p, int dtype,
   if (clusters < 1) clusters = 1;
   {
     LaunchScope scope(FSR_K_CONV_UP, st, 2.0 * p.N * p.H * p.W * 256.0 * 64 * 9);
-    kern<<<2 * clusters, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tmx, tmw, tmo, p);   // __cluster_dims__(2,1,1)
+    PdlLaunch(2 * clusters, Cfg::kThreads, Cfg::kSmemBytes, st)(kern, tmx, tmw, tmo, p);   // __cluster_dims__(2,1,1)
   }
   return cuda_rc(cudaGetLastError());
 }
@@ -331,7 +362,7 @@ int launch_head(const void* x, const void* w_packed, ConvParams p, int dtype, cu
   if (grid > p.num_tiles) grid = p.num_tiles;
   {
     LaunchScope scope(FSR_K_CONV_HEAD, st, 2.0 * p.N * p.H * p.W * 3.0 * cin * 9);
-    kern<<<grid, HeadCfg::kThreads, HeadCfg::kSmemBytes, st>>>(tmx, reinterpret_cast<const T*>(w_packed), p, cin);
+    PdlLaunch(grid, HeadCfg::kThreads, HeadCfg::kSmemBytes, st)(kern, tmx, reinterpret_cast<const T*>(w_packed), p, cin);
   }
   return cuda_rc(cudaGetLastError());
 }
@@ -424,7 +455,7 @@ int launch_gen(const CUtensorMap* maps, const CUtensorMap& tmw, GenParams& p, cu
     int ntaps2 = 0;
     for (int k = 0; k < p.nkinds; ++k) ntaps2 += p.kinds[k].ntaps;
     LaunchScope scope(FSR_K_CONV_GEN, st, 2.0 * p.N * p.Ho * p.Wo * (double)p.cout_total * p.cin * ntaps2);
-    k2<<<2 * cps * p2.num_slices, C2::kThreads, C2::kSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], tmw, tmo, p2);
+    PdlLaunch(2 * cps * p2.num_slices, C2::kThreads, C2::kSmemBytes, st)(k2, maps[0], maps[1], maps[2], maps[3], tmw, tmo, p2);
     return cuda_rc(cudaGetLastError());
   }
   int ctas_per_slice = num_sms() / p.num_slices;
@@ -443,7 +474,7 @@ int launch_gen(const CUtensorMap* maps, const CUtensorMap& tmw, GenParams& p, cu
       wattr_done = true;
     }
     LaunchScope scope(FSR_K_CONV_GEN, st, flops);
-    wkern<<<grid, WCfg::kThreads, WCfg::kSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], tmw, p);
+    PdlLaunch(grid, WCfg::kThreads, WCfg::kSmemBytes, st)(wkern, maps[0], maps[1], maps[2], maps[3], tmw, p);
     return cuda_rc(cudaGetLastError());
   }
   auto kern = conv3x3_gen_kernel<EPI, T, MAXTAPS>;
@@ -454,7 +485,7 @@ int launch_gen(const CUtensorMap* maps, const CUtensorMap& tmw, GenParams& p, cu
   }
   {
     LaunchScope scope(FSR_K_CONV_GEN, st, flops);
-    kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], tmw, p);
+    PdlLaunch(grid, Cfg::kThreads, Cfg::kSmemBytes, st)(kern, maps[0], maps[1], maps[2], maps[3], tmw, p);
   }
   return cuda_rc(cudaGetLastError());
 }
@@ -599,7 +630,7 @@ int gen_flat_dispatch(const void* x, const void* w_packed, void* out, const floa
   if (cps < 1) cps = 1;
   if (cps > pairs) cps = pairs;
   LaunchScope scope(FSR_K_CONV_GEN, st, 2.0 * N * H * W * (double)cout * cin * 9);
-  k2<<<2 * cps * p.num_slices, C2::kThreads, C2::kSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], tmw, tmo, p);
+  PdlLaunch(2 * cps * p.num_slices, C2::kThreads, C2::kSmemBytes, st)(k2, maps[0], maps[1], maps[2], maps[3], tmw, tmo, p);
   return cuda_rc(cudaGetLastError());
 }
 
@@ -681,12 +712,12 @@ int wgrad_dispatch(const void* x, const void* dy, float* const* dw, int groups, 
   rp.npairs_all = npairs_all; rp.ctas_per_pair = cpp;
   {
     LaunchScope scope(FSR_K_CONV_WGRAD, st, 2.0 * groups * N * Ho * Wo * (double)cin * cout * 9);
-    kern<<<npairs_all * cpp, WgradCfg::kThreads, WgradCfg::kSmemBytes, st>>>(mx[0], mx[1], mx[2], mx[3], mdy, p);
+    PdlLaunch(npairs_all * cpp, WgradCfg::kThreads, WgradCfg::kSmemBytes, st)(kern, mx[0], mx[1], mx[2], mx[3], mdy, p);
   }
   FSR_CUDA(cudaGetLastError());
   {
     LaunchScope scope(FSR_K_NONE - 1, st);
-    wgrad_reduce_kernel<<<dim3(npairs_all, 8, 9), 256, 0, st>>>(rp);
+    PdlLaunch(dim3(npairs_all, 8, 9), 256, 0, st)(wgrad_reduce_kernel, rp);
   }
   return cuda_rc(cudaGetLastError());
 }
@@ -727,10 +758,10 @@ int fsr_pack_conv3x3_weight(const float* w_oihw, const float* bias, void* w_pack
   const int blocks = (int)((total + 255) / 256 > 4096 ? 4096 : (total + 255) / 256);
   LaunchScope scope(FSR_K_NONE - 1, st);
   if (dtype == FSR_BF16)
-    pack_conv3x3_weight_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(w_oihw, (__nv_bfloat16*)w_packed, cout, cin, cout_pad, ps_perm);
+    PdlLaunch(blocks, 256, 0, st)(pack_conv3x3_weight_kernel<__nv_bfloat16>, w_oihw, (__nv_bfloat16*)w_packed, cout, cin, cout_pad, ps_perm);
   else
-    pack_conv3x3_weight_kernel<__half><<<blocks, 256, 0, st>>>(w_oihw, (__half*)w_packed, cout, cin, cout_pad, ps_perm);
-  if (bias && bias_packed) permute_bias_ps_kernel<<<(cout_pad + 127) / 128, 128, 0, st>>>(bias, bias_packed, cout, cout_pad, ps_perm);
+    PdlLaunch(blocks, 256, 0, st)(pack_conv3x3_weight_kernel<__half>, w_oihw, (__half*)w_packed, cout, cin, cout_pad, ps_perm);
+  if (bias && bias_packed) PdlLaunch((cout_pad + 127) / 128, 128, 0, st)(permute_bias_ps_kernel, bias, bias_packed, cout, cout_pad, ps_perm);
   return cuda_rc(cudaGetLastError());
 }
 
@@ -753,8 +784,8 @@ int fsr_pack_multi(const FsrPackTask* tasks, int n, int dtype, void* stream) {
   p.block_begin[n] = blocks;
   cudaStream_t st = (cudaStream_t)stream;
   LaunchScope scope(FSR_K_NONE - 1, st);
-  if (dtype == FSR_BF16) pack_multi_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(p);
-  else pack_multi_kernel<__half><<<blocks, 256, 0, st>>>(p);
+  if (dtype == FSR_BF16) PdlLaunch(blocks, 256, 0, st)(pack_multi_kernel<__nv_bfloat16>, p);
+  else PdlLaunch(blocks, 256, 0, st)(pack_multi_kernel<__half>, p);
   return cuda_rc(cudaGetLastError());
 }
 
@@ -773,6 +804,7 @@ int fsr_conv3x3_c64(const void* x, const void* w_packed, void* out, const float*
 // the two entries below are what the pair view adds: folding the per-(parity, channel) InstanceNorm sums into
 // per-channel ones, and a head that writes two rgb pixels per row.
 __global__ void in_stats_fold_pair_kernel(long long* __restrict__ stats, int total) {
+  pdl_grid_sync();
   // stats [N][64][2] of the pair grid; channel c of the 32-channel network lives in slots c and 32+c.  The consumers
   // divide by the PAIR count H*W/2, so both slots receive half the merged sums (exact: fixed-point integers, floor).
   const int i = blockIdx.x * blockDim.x + threadIdx.x;          // (n, c<32, k<2)
@@ -784,6 +816,11 @@ __global__ void in_stats_fold_pair_kernel(long long* __restrict__ stats, int tot
   *a = m; *b = m;
 }
 
+int fsr_set_pdl(int on) {
+  g_pdl = on ? 1 : 0;
+  return FSR_OK;
+}
+
 int fsr_set_pair_rows(int on) {
   tl_pair_rows = on ? 1 : 0;
   return FSR_OK;
@@ -793,7 +830,7 @@ int fsr_in_stats_fold_pair(int64_t* stats, int N, void* stream) {
   if (!stats) return FSR_ERR_BAD_ARG;
   if (N <= 0) return FSR_ERR_BAD_SHAPE;
   const int total = N * 64;
-  in_stats_fold_pair_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<long long*>(stats), total);
+  PdlLaunch((total + 127) / 128, 128, 0, (cudaStream_t)stream)(in_stats_fold_pair_kernel, reinterpret_cast<long long*>(stats), total);
   return cuda_rc(cudaGetLastError());
 }
 
@@ -909,9 +946,9 @@ static int neck_impl(const void* x, const float* w, const float* bias, const flo
     dim3 grid((unsigned)bx, cout / 64);
 #define FSR_NECK_MMA(T)                                                                                       \
   do {                                                                                                        \
-    if (in_u8) neck_conv3x3_mma_kernel<T, true, false><<<grid, kNeckWarps * 32, 0, st>>>(p);                  \
-    else if (vgg_norm) neck_conv3x3_mma_kernel<T, false, true><<<grid, kNeckWarps * 32, 0, st>>>(p);          \
-    else neck_conv3x3_mma_kernel<T, false, false><<<grid, kNeckWarps * 32, 0, st>>>(p);                       \
+    if (in_u8) PdlLaunch(grid, kNeckWarps * 32, 0, st)(neck_conv3x3_mma_kernel<T, true, false>, p);                  \
+    else if (vgg_norm) PdlLaunch(grid, kNeckWarps * 32, 0, st)(neck_conv3x3_mma_kernel<T, false, true>, p);          \
+    else PdlLaunch(grid, kNeckWarps * 32, 0, st)(neck_conv3x3_mma_kernel<T, false, false>, p);                       \
   } while (0)
     if (in_u8 && vgg_norm) return FSR_ERR_BAD_ARG;
     if (dtype == FSR_BF16) FSR_NECK_MMA(__nv_bfloat16);
@@ -921,12 +958,12 @@ static int neck_impl(const void* x, const float* w, const float* bias, const flo
   }
   if (total > (size_t)1 << 20) {     // large frames/batches: one thread per pixel
     dim3 grid((unsigned)((total + 127) / 128), cout / 64);
-    if (dtype == FSR_BF16) neck_conv3x3_kernel<__nv_bfloat16, 1><<<grid, 128, 0, st>>>(p);
-    else neck_conv3x3_kernel<__half, 1><<<grid, 128, 0, st>>>(p);
+    if (dtype == FSR_BF16) PdlLaunch(grid, 128, 0, st)(neck_conv3x3_kernel<__nv_bfloat16, 1>, p);
+    else PdlLaunch(grid, 128, 0, st)(neck_conv3x3_kernel<__half, 1>, p);
   } else {
     dim3 grid((unsigned)((2 * total + 255) / 256), cout / 64);
-    if (dtype == FSR_BF16) neck_conv3x3_kernel<__nv_bfloat16, 2><<<grid, 256, 0, st>>>(p);
-    else neck_conv3x3_kernel<__half, 2><<<grid, 256, 0, st>>>(p);
+    if (dtype == FSR_BF16) PdlLaunch(grid, 256, 0, st)(neck_conv3x3_kernel<__nv_bfloat16, 2>, p);
+    else PdlLaunch(grid, 256, 0, st)(neck_conv3x3_kernel<__half, 2>, p);
   }
   return cuda_rc(cudaGetLastError());
 }
@@ -956,8 +993,8 @@ static int instnorm_apply_impl(const void* raw, const int64_t* stats, const void
   cudaStream_t st = (cudaStream_t)stream;
   const size_t sm = (size_t)2 * C * sizeof(float);
   LaunchScope scope(FSR_K_IN_APPLY, st);
-  if (dtype == FSR_BF16) instnorm_apply_kernel<__nv_bfloat16><<<grid, 256, sm, st>>>(p);
-  else instnorm_apply_kernel<__half><<<grid, 256, sm, st>>>(p);
+  if (dtype == FSR_BF16) PdlLaunch(grid, 256, sm, st)(instnorm_apply_kernel<__nv_bfloat16>, p);
+  else PdlLaunch(grid, 256, sm, st)(instnorm_apply_kernel<__half>, p);
   return cuda_rc(cudaGetLastError());
 }
 
@@ -979,9 +1016,9 @@ int fsr_pixel_shuffle2(const void* in, void* out, int N, int H, int W, int C, in
   cudaStream_t st = (cudaStream_t)stream;
   LaunchScope scope(FSR_K_NONE - 1, st);
   if (dtype == FSR_BF16)
-    pixel_shuffle2_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, N, H, W, C);
+    PdlLaunch(blocks, 256, 0, st)(pixel_shuffle2_kernel<__nv_bfloat16>, (const __nv_bfloat16*)in, (__nv_bfloat16*)out, N, H, W, C);
   else
-    pixel_shuffle2_kernel<__half><<<blocks, 256, 0, st>>>((const __half*)in, (__half*)out, N, H, W, C);
+    PdlLaunch(blocks, 256, 0, st)(pixel_shuffle2_kernel<__half>, (const __half*)in, (__half*)out, N, H, W, C);
   return cuda_rc(cudaGetLastError());
 }
 
@@ -990,8 +1027,8 @@ int fsr_nchw_f32_to_nhwc(const float* in, void* out, int N, int C, int HW, int d
   dim3 grid((HW + 31) / 32, (C + 31) / 32, N);
   cudaStream_t st = (cudaStream_t)stream;
   LaunchScope scope(FSR_K_NONE - 1, st);
-  if (dtype == FSR_BF16) nchw_f32_to_nhwc_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(in, (__nv_bfloat16*)out, N, C, HW);
-  else nchw_f32_to_nhwc_kernel<__half><<<grid, 256, 0, st>>>(in, (__half*)out, N, C, HW);
+  if (dtype == FSR_BF16) PdlLaunch(grid, 256, 0, st)(nchw_f32_to_nhwc_kernel<__nv_bfloat16>, in, (__nv_bfloat16*)out, N, C, HW);
+  else PdlLaunch(grid, 256, 0, st)(nchw_f32_to_nhwc_kernel<__half>, in, (__half*)out, N, C, HW);
   return cuda_rc(cudaGetLastError());
 }
 
@@ -1000,8 +1037,8 @@ int fsr_nhwc_to_nchw_f32(const void* in, float* out, int N, int C, int HW, int d
   dim3 grid((HW + 31) / 32, (C + 31) / 32, N);
   cudaStream_t st = (cudaStream_t)stream;
   LaunchScope scope(FSR_K_NONE - 1, st);
-  if (dtype == FSR_BF16) nhwc_to_nchw_f32_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)in, out, N, C, HW);
-  else nhwc_to_nchw_f32_kernel<__half><<<grid, 256, 0, st>>>((const __half*)in, out, N, C, HW);
+  if (dtype == FSR_BF16) PdlLaunch(grid, 256, 0, st)(nhwc_to_nchw_f32_kernel<__nv_bfloat16>, (const __nv_bfloat16*)in, out, N, C, HW);
+  else PdlLaunch(grid, 256, 0, st)(nhwc_to_nchw_f32_kernel<__half>, (const __half*)in, out, N, C, HW);
   return cuda_rc(cudaGetLastError());
 }
 
@@ -1239,8 +1276,8 @@ int fsr_pack_conv3x3_weight_t(const float* w_oihw, void* w_packed, int cout, int
   cudaStream_t st = (cudaStream_t)stream;
   const size_t total = (size_t)9 * cout * row_pad;
   LaunchScope scope(FSR_K_NONE - 1, st);
-  FSR_T((pack_conv3x3_weight_t_kernel<__half><<<ew_blocks(total), 256, 0, st>>>(w_oihw, (__half*)w_packed, cout, cin, ps_perm, flip, row_pad, row_scale)),
-        (pack_conv3x3_weight_t_kernel<__nv_bfloat16><<<ew_blocks(total), 256, 0, st>>>(w_oihw, (__nv_bfloat16*)w_packed, cout, cin, ps_perm, flip, row_pad, row_scale)));
+  FSR_T((PdlLaunch(ew_blocks(total), 256, 0, st)(pack_conv3x3_weight_t_kernel<__half>, w_oihw, (__half*)w_packed, cout, cin, ps_perm, flip, row_pad, row_scale)),
+        (PdlLaunch(ew_blocks(total), 256, 0, st)(pack_conv3x3_weight_t_kernel<__nv_bfloat16>, w_oihw, (__nv_bfloat16*)w_packed, cout, cin, ps_perm, flip, row_pad, row_scale)));
   return cuda_rc(cudaGetLastError());
 }
 
@@ -1273,8 +1310,8 @@ int fsr_parity_layout(const void* in, void* out, int N, int H, int W, int C, int
   cudaStream_t st = (cudaStream_t)stream;
   const size_t total = (size_t)N * H * W * (C / 8);
   LaunchScope scope(FSR_K_NONE - 1, st);
-  if (to_parity) parity_layout_kernel<true><<<ew_blocks(total), 256, 0, st>>>((const uint4*)in, (uint4*)out, N, H, W, C / 8);
-  else parity_layout_kernel<false><<<ew_blocks(total), 256, 0, st>>>((const uint4*)in, (uint4*)out, N, H, W, C / 8);
+  if (to_parity) PdlLaunch(ew_blocks(total), 256, 0, st)(parity_layout_kernel<true>, (const uint4*)in, (uint4*)out, N, H, W, C / 8);
+  else PdlLaunch(ew_blocks(total), 256, 0, st)(parity_layout_kernel<false>, (const uint4*)in, (uint4*)out, N, H, W, C / 8);
   return cuda_rc(cudaGetLastError());
 }
 
@@ -1283,8 +1320,8 @@ static int maxpool2_impl(const void* in, void* out, int N, int H, int W, int C, 
   cudaStream_t st = (cudaStream_t)stream;
   const size_t total = (size_t)N * (H / 2) * (W / 2) * (C / 8);
   LaunchScope scope(FSR_K_NONE - 1, st);
-  FSR_T((maxpool2_fwd_kernel<__half><<<ew_blocks(total), 256, 0, st>>>((const __half*)in, (__half*)out, N, H, W, C, in_pad, out_pad)),
-        (maxpool2_fwd_kernel<__nv_bfloat16><<<ew_blocks(total), 256, 0, st>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, N, H, W, C, in_pad, out_pad)));
+  FSR_T((PdlLaunch(ew_blocks(total), 256, 0, st)(maxpool2_fwd_kernel<__half>, (const __half*)in, (__half*)out, N, H, W, C, in_pad, out_pad)),
+        (PdlLaunch(ew_blocks(total), 256, 0, st)(maxpool2_fwd_kernel<__nv_bfloat16>, (const __nv_bfloat16*)in, (__nv_bfloat16*)out, N, H, W, C, in_pad, out_pad)));
   return cuda_rc(cudaGetLastError());
 }
 
@@ -1294,8 +1331,8 @@ static int maxpool2_relu_bwd_impl(const void* in, const void* dout, void* din, i
   cudaStream_t st = (cudaStream_t)stream;
   const size_t total = (size_t)N * (H / 2) * (W / 2) * C;
   LaunchScope scope(FSR_K_NONE - 1, st);
-  FSR_T((maxpool2_relu_bwd_kernel<__half><<<ew_blocks(total), 256, 0, st>>>((const __half*)in, (const __half*)dout, (__half*)din, N, H, W, C, in_pad, out_pad)),
-        (maxpool2_relu_bwd_kernel<__nv_bfloat16><<<ew_blocks(total), 256, 0, st>>>((const __nv_bfloat16*)in, (const __nv_bfloat16*)dout, (__nv_bfloat16*)din, N, H, W, C, in_pad, out_pad)));
+  FSR_T((PdlLaunch(ew_blocks(total), 256, 0, st)(maxpool2_relu_bwd_kernel<__half>, (const __half*)in, (const __half*)dout, (__half*)din, N, H, W, C, in_pad, out_pad)),
+        (PdlLaunch(ew_blocks(total), 256, 0, st)(maxpool2_relu_bwd_kernel<__nv_bfloat16>, (const __nv_bfloat16*)in, (const __nv_bfloat16*)dout, (__nv_bfloat16*)din, N, H, W, C, in_pad, out_pad)));
   return cuda_rc(cudaGetLastError());
 }
 
@@ -1317,8 +1354,8 @@ int fsr_relu_bwd(const void* y, const void* dy, void* dx, size_t n_elems, int dt
   if (!y || !dy || !dx || n_elems % 8) return FSR_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   LaunchScope scope(FSR_K_NONE - 1, st);
-  FSR_T((relu_bwd_kernel<__half><<<ew_blocks(n_elems / 8), 256, 0, st>>>((const uint4*)y, (const uint4*)dy, (uint4*)dx, n_elems / 8)),
-        (relu_bwd_kernel<__nv_bfloat16><<<ew_blocks(n_elems / 8), 256, 0, st>>>((const uint4*)y, (const uint4*)dy, (uint4*)dx, n_elems / 8)));
+  FSR_T((PdlLaunch(ew_blocks(n_elems / 8), 256, 0, st)(relu_bwd_kernel<__half>, (const uint4*)y, (const uint4*)dy, (uint4*)dx, n_elems / 8)),
+        (PdlLaunch(ew_blocks(n_elems / 8), 256, 0, st)(relu_bwd_kernel<__nv_bfloat16>, (const uint4*)y, (const uint4*)dy, (uint4*)dx, n_elems / 8)));
   return cuda_rc(cudaGetLastError());
 }
 
@@ -1326,8 +1363,8 @@ int fsr_add(const void* a, const void* b, void* out, size_t n_elems, int dtype, 
   if (!a || !b || !out || n_elems % 8) return FSR_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   LaunchScope scope(FSR_K_NONE - 1, st);
-  FSR_T((add_kernel<__half><<<ew_blocks(n_elems / 8), 256, 0, st>>>((const uint4*)a, (const uint4*)b, (uint4*)out, n_elems / 8)),
-        (add_kernel<__nv_bfloat16><<<ew_blocks(n_elems / 8), 256, 0, st>>>((const uint4*)a, (const uint4*)b, (uint4*)out, n_elems / 8)));
+  FSR_T((PdlLaunch(ew_blocks(n_elems / 8), 256, 0, st)(add_kernel<__half>, (const uint4*)a, (const uint4*)b, (uint4*)out, n_elems / 8)),
+        (PdlLaunch(ew_blocks(n_elems / 8), 256, 0, st)(add_kernel<__nv_bfloat16>, (const uint4*)a, (const uint4*)b, (uint4*)out, n_elems / 8)));
   return cuda_rc(cudaGetLastError());
 }
 
@@ -1336,8 +1373,8 @@ int fsr_conv1x1_to1_fwd(const void* x, const float* w, const float* b, float* z,
   cudaStream_t st = (cudaStream_t)stream;
   const int blocks = (npix * 32 + 255) / 256;
   LaunchScope scope(FSR_K_NONE - 1, st);
-  FSR_T((conv1x1_to1_fwd_kernel<__half><<<blocks, 256, 0, st>>>((const __half*)x, w, b, z, npix, C)),
-        (conv1x1_to1_fwd_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, w, b, z, npix, C)));
+  FSR_T((PdlLaunch(blocks, 256, 0, st)(conv1x1_to1_fwd_kernel<__half>, (const __half*)x, w, b, z, npix, C)),
+        (PdlLaunch(blocks, 256, 0, st)(conv1x1_to1_fwd_kernel<__nv_bfloat16>, (const __nv_bfloat16*)x, w, b, z, npix, C)));
   return cuda_rc(cudaGetLastError());
 }
 
@@ -1348,8 +1385,8 @@ int fsr_conv1x1_to1_bwd(const void* x, const float* w, const float* dz, void* dx
   int blocks = (npix + 15) / 16;
   if (blocks > num_sms() * 4) blocks = num_sms() * 4;
   LaunchScope scope(FSR_K_NONE - 1, st);
-  FSR_T((conv1x1_to1_bwd_kernel<__half><<<blocks, 256, 0, st>>>((const __half*)x, w, dz, (__half*)dx, dw, db, npix, C)),
-        (conv1x1_to1_bwd_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, w, dz, (__nv_bfloat16*)dx, dw, db, npix, C)));
+  FSR_T((PdlLaunch(blocks, 256, 0, st)(conv1x1_to1_bwd_kernel<__half>, (const __half*)x, w, dz, (__half*)dx, dw, db, npix, C)),
+        (PdlLaunch(blocks, 256, 0, st)(conv1x1_to1_bwd_kernel<__nv_bfloat16>, (const __nv_bfloat16*)x, w, dz, (__nv_bfloat16*)dx, dw, db, npix, C)));
   return cuda_rc(cudaGetLastError());
 }
 
@@ -1358,7 +1395,7 @@ int fsr_bce_logits(const float* z, const float* noise, float lab_scale, float la
   if (!z || !noise || !loss_out || n <= 0) return FSR_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   LaunchScope scope(FSR_K_NONE - 1, st);
-  bce_logits_kernel<<<1, 256, 0, st>>>(z, noise, lab_scale, lab_shift, n, loss_out, dz, grad_scale);
+  PdlLaunch(1, 256, 0, st)(bce_logits_kernel, z, noise, lab_scale, lab_shift, n, loss_out, dz, grad_scale);
   return cuda_rc(cudaGetLastError());
 }
 
@@ -1366,9 +1403,9 @@ int fsr_smooth_l1(const void* a, const void* b, size_t n, float* loss_acc, void*
   if (!a || !b || !loss_acc) return FSR_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   LaunchScope scope(FSR_K_NONE - 1, st);
-  if (dtype == 2) smooth_l1_f32_kernel<<<ew_blocks(n), 256, 0, st>>>((const float*)a, (const float*)b, n, loss_acc, (float*)da, grad_scale);
-  else FSR_T((smooth_l1_kernel<__half><<<ew_blocks(n), 256, 0, st>>>((const __half*)a, (const __half*)b, n, loss_acc, (__half*)da, grad_scale)),
-             (smooth_l1_kernel<__nv_bfloat16><<<ew_blocks(n), 256, 0, st>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, n, loss_acc, (__nv_bfloat16*)da, grad_scale)));
+  if (dtype == 2) PdlLaunch(ew_blocks(n), 256, 0, st)(smooth_l1_f32_kernel, (const float*)a, (const float*)b, n, loss_acc, (float*)da, grad_scale);
+  else FSR_T((PdlLaunch(ew_blocks(n), 256, 0, st)(smooth_l1_kernel<__half>, (const __half*)a, (const __half*)b, n, loss_acc, (__half*)da, grad_scale)),
+             (PdlLaunch(ew_blocks(n), 256, 0, st)(smooth_l1_kernel<__nv_bfloat16>, (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, n, loss_acc, (__nv_bfloat16*)da, grad_scale)));
   return cuda_rc(cudaGetLastError());
 }
 
@@ -1383,8 +1420,8 @@ static int instnorm_bwd_impl(const void* raw, const int64_t* stats, const void* 
   if (fused) {
     // training shapes: one launch, the per-(n,c) sums stay inside the block (no `red` scratch, no memset, no atomics)
     LaunchScope scope(FSR_K_NONE - 1, st);
-    FSR_T((instnorm_bwd_fused_kernel<__half><<<dim3(C / 16, N), 256, 0, st>>>(p)),
-          (instnorm_bwd_fused_kernel<__nv_bfloat16><<<dim3(C / 16, N), 256, 0, st>>>(p)));
+    FSR_T((PdlLaunch(dim3(C / 16, N), 256, 0, st)(instnorm_bwd_fused_kernel<__half>, p)),
+          (PdlLaunch(dim3(C / 16, N), 256, 0, st)(instnorm_bwd_fused_kernel<__nv_bfloat16>, p)));
     return cuda_rc(cudaGetLastError());
   }
   if (!red) return FSR_ERR_BAD_ARG;
@@ -1398,11 +1435,11 @@ static int instnorm_bwd_impl(const void* raw, const int64_t* stats, const void* 
   FSR_CUDA(cudaMemsetAsync(red, 0, (size_t)N * C * 2 * sizeof(float), st));
   {
     LaunchScope scope(FSR_K_NONE - 1, st);
-    FSR_T((instnorm_bwd_kernel<__half, 1><<<grid, 256, sm, st>>>(p)), (instnorm_bwd_kernel<__nv_bfloat16, 1><<<grid, 256, sm, st>>>(p)));
+    FSR_T((PdlLaunch(grid, 256, sm, st)(instnorm_bwd_kernel<__half, 1>, p)), (PdlLaunch(grid, 256, sm, st)(instnorm_bwd_kernel<__nv_bfloat16, 1>, p)));
   }
   {
     LaunchScope scope(FSR_K_NONE - 1, st);
-    FSR_T((instnorm_bwd_kernel<__half, 2><<<grid, 256, sm, st>>>(p)), (instnorm_bwd_kernel<__nv_bfloat16, 2><<<grid, 256, sm, st>>>(p)));
+    FSR_T((PdlLaunch(grid, 256, sm, st)(instnorm_bwd_kernel<__half, 2>, p)), (PdlLaunch(grid, 256, sm, st)(instnorm_bwd_kernel<__nv_bfloat16, 2>, p)));
   }
   return cuda_rc(cudaGetLastError());
 }
@@ -1423,8 +1460,8 @@ int fsr_act_bwd(const void* y, const void* dy, void* dv, size_t n_elems, const f
   if (act == FSR_ACT_PRELU && !alpha) return FSR_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   LaunchScope scope(FSR_K_NONE - 1, st);
-  FSR_T((act_bwd_kernel<__half><<<ew_blocks(n_elems / 8), 256, 0, st>>>((const uint4*)y, (const uint4*)dy, (uint4*)dv, n_elems / 8, alpha, slope, act, dalpha)),
-        (act_bwd_kernel<__nv_bfloat16><<<ew_blocks(n_elems / 8), 256, 0, st>>>((const uint4*)y, (const uint4*)dy, (uint4*)dv, n_elems / 8, alpha, slope, act, dalpha)));
+  FSR_T((PdlLaunch(ew_blocks(n_elems / 8), 256, 0, st)(act_bwd_kernel<__half>, (const uint4*)y, (const uint4*)dy, (uint4*)dv, n_elems / 8, alpha, slope, act, dalpha)),
+        (PdlLaunch(ew_blocks(n_elems / 8), 256, 0, st)(act_bwd_kernel<__nv_bfloat16>, (const uint4*)y, (const uint4*)dy, (uint4*)dv, n_elems / 8, alpha, slope, act, dalpha)));
   return cuda_rc(cudaGetLastError());
 }
 
@@ -1434,8 +1471,8 @@ int fsr_ps_prelu_bwd(const void* U, const void* dU, void* dconv, int N, int H, i
   cudaStream_t st = (cudaStream_t)stream;
   const size_t total = (size_t)N * H * W * 4 * (F / 8);
   LaunchScope scope(FSR_K_NONE - 1, st);
-  FSR_T((ps_prelu_bwd_kernel<__half><<<ew_blocks(total), 256, 0, st>>>((const __half*)U, (const __half*)dU, (__half*)dconv, N, H, W, F, alpha, dalpha)),
-        (ps_prelu_bwd_kernel<__nv_bfloat16><<<ew_blocks(total), 256, 0, st>>>((const __nv_bfloat16*)U, (const __nv_bfloat16*)dU, (__nv_bfloat16*)dconv, N, H, W, F, alpha, dalpha)));
+  FSR_T((PdlLaunch(ew_blocks(total), 256, 0, st)(ps_prelu_bwd_kernel<__half>, (const __half*)U, (const __half*)dU, (__half*)dconv, N, H, W, F, alpha, dalpha)),
+        (PdlLaunch(ew_blocks(total), 256, 0, st)(ps_prelu_bwd_kernel<__nv_bfloat16>, (const __nv_bfloat16*)U, (const __nv_bfloat16*)dU, (__nv_bfloat16*)dconv, N, H, W, F, alpha, dalpha)));
   return cuda_rc(cudaGetLastError());
 }
 
@@ -1443,7 +1480,7 @@ int fsr_tanh_bwd(const float* y, const float* dy, float* dpre, size_t n, void* s
   if (!y || !dy || !dpre) return FSR_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   LaunchScope scope(FSR_K_NONE - 1, st);
-  tanh_bwd_kernel<<<ew_blocks(n), 256, 0, st>>>(y, dy, dpre, n);
+  PdlLaunch(ew_blocks(n), 256, 0, st)(tanh_bwd_kernel, y, dy, dpre, n);
   return cuda_rc(cudaGetLastError());
 }
 
@@ -1463,12 +1500,12 @@ int fsr_wgrad_c3(const float* img, const void* act, float* out, int N, int H, in
     long long mb = (steps + 8 * kWgc3Warps - 1) / (8 * kWgc3Warps);      // >= 8 steps per warp
     if (mb > (long long)num_sms() * 3) mb = (long long)num_sms() * 3;
     dim3 mgrid((unsigned)mb, C64 / 64);
-    FSR_T((wgrad_c3_mma_kernel<__half><<<mgrid, kWgc3Warps * 32, 0, st>>>(img, (const __half*)act, out, N, H, W, C64, flip, layout)),
-          (wgrad_c3_mma_kernel<__nv_bfloat16><<<mgrid, kWgc3Warps * 32, 0, st>>>(img, (const __nv_bfloat16*)act, out, N, H, W, C64, flip, layout)));
+    FSR_T((PdlLaunch(mgrid, kWgc3Warps * 32, 0, st)(wgrad_c3_mma_kernel<__half>, img, (const __half*)act, out, N, H, W, C64, flip, layout)),
+          (PdlLaunch(mgrid, kWgc3Warps * 32, 0, st)(wgrad_c3_mma_kernel<__nv_bfloat16>, img, (const __nv_bfloat16*)act, out, N, H, W, C64, flip, layout)));
     return cuda_rc(cudaGetLastError());
   }
-  FSR_T((wgrad_c3_kernel<__half><<<grid, 224, 0, st>>>(img, (const __half*)act, out, N, H, W, C64, flip, layout)),
-        (wgrad_c3_kernel<__nv_bfloat16><<<grid, 224, 0, st>>>(img, (const __nv_bfloat16*)act, out, N, H, W, C64, flip, layout)));
+  FSR_T((PdlLaunch(grid, 224, 0, st)(wgrad_c3_kernel<__half>, img, (const __half*)act, out, N, H, W, C64, flip, layout)),
+        (PdlLaunch(grid, 224, 0, st)(wgrad_c3_kernel<__nv_bfloat16>, img, (const __nv_bfloat16*)act, out, N, H, W, C64, flip, layout)));
   return cuda_rc(cudaGetLastError());
 }
 
@@ -1480,8 +1517,8 @@ int fsr_bias_grad(const void* g, float* db, size_t npix, int C, int ps_perm, int
   if (blocks < 1) blocks = 1;
   const size_t sm = (size_t)C * sizeof(float);
   LaunchScope scope(FSR_K_NONE - 1, st);
-  FSR_T((bias_grad_kernel<__half><<<blocks, 256, sm, st>>>((const __half*)g, db, npix, C, ps_perm)),
-        (bias_grad_kernel<__nv_bfloat16><<<blocks, 256, sm, st>>>((const __nv_bfloat16*)g, db, npix, C, ps_perm)));
+  FSR_T((PdlLaunch(blocks, 256, sm, st)(bias_grad_kernel<__half>, (const __half*)g, db, npix, C, ps_perm)),
+        (PdlLaunch(blocks, 256, sm, st)(bias_grad_kernel<__nv_bfloat16>, (const __nv_bfloat16*)g, db, npix, C, ps_perm)));
   return cuda_rc(cudaGetLastError());
 }
 
@@ -1491,7 +1528,7 @@ int fsr_bias_grad_nchw(const float* g, float* db, int N, int C, size_t HW, void*
   int bx = (int)((HW + 255) / 256);
   if (bx > 64) bx = 64;
   LaunchScope scope(FSR_K_NONE - 1, st);
-  bias_grad_nchw_kernel<<<dim3(bx, C), 256, 0, st>>>(g, db, N, C, HW);
+  PdlLaunch(dim3(bx, C), 256, 0, st)(bias_grad_nchw_kernel, g, db, N, C, HW);
   return cuda_rc(cudaGetLastError());
 }
 
@@ -1502,7 +1539,7 @@ int fsr_adamw(float* p, const float* g, float* m, float* v, size_t n, float lr, 
   const float bc1 = 1.0f - powf(b1, (float)step);
   const float bc2s = sqrtf(1.0f - powf(b2, (float)step));
   LaunchScope scope(FSR_K_NONE - 1, st);
-  adamw_kernel<<<ew_blocks(n), 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, wd, bc1, bc2s, grad_scale);
+  PdlLaunch(ew_blocks(n), 256, 0, st)(adamw_kernel, p, g, m, v, n, lr, b1, b2, eps, wd, bc1, bc2s, grad_scale);
   return cuda_rc(cudaGetLastError());
 }
 
@@ -1512,10 +1549,10 @@ int fsr_adamw_dev(float* p, const float* g, float* m, float* v, size_t n, float 
   cudaStream_t st = (cudaStream_t)stream;
   {
     LaunchScope scope(FSR_K_NONE - 1, st);
-    step_inc_kernel<<<1, 32, 0, st>>>(step_dev);
+    PdlLaunch(1, 32, 0, st)(step_inc_kernel, step_dev);
   }
   LaunchScope scope(FSR_K_NONE - 1, st);
-  adamw_dev_kernel<<<ew_blocks(n), 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, wd, step_dev, grad_scale);
+  PdlLaunch(ew_blocks(n), 256, 0, st)(adamw_dev_kernel, p, g, m, v, n, lr, b1, b2, eps, wd, step_dev, grad_scale);
   return cuda_rc(cudaGetLastError());
 }
 
@@ -1533,7 +1570,7 @@ int fsr_psnr_ssim(const float* pred, const float* target, int N, int C, int H, i
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid((unsigned)((W - 10 + 15) / 16), (unsigned)((H - 10 + 15) / 16), (unsigned)(N * C));
   LaunchScope scope(FSR_K_NONE - 1, st);
-  psnr_ssim_kernel<<<grid, 256, 0, st>>>(p);
+  PdlLaunch(grid, 256, 0, st)(psnr_ssim_kernel, p);
   return cuda_rc(cudaGetLastError());
 }
 
@@ -1553,7 +1590,7 @@ int fsr_crop_resize_aa(const uint8_t* cache, const int64_t* img_off, const int32
   CropResizeParams p{cache, (const long long*)img_off, img_h, img_w, samples, tap_min, tap_size, tap_w, lr, hr, B, lr_size, scale, K};
   cudaStream_t st = (cudaStream_t)stream;
   LaunchScope scope(FSR_K_NONE - 1, st);
-  crop_resize_aa_kernel<<<dim3((unsigned)B, 3), 256, smem, st>>>(p);
+  PdlLaunch(dim3((unsigned)B, 3), 256, smem, st)(crop_resize_aa_kernel, p);
   return cuda_rc(cudaGetLastError());
 }
 
@@ -1594,7 +1631,7 @@ int fsr_split_f32(const float* x, void* hi, void* lo, size_t n_elems, void* stre
   if (!x || !hi || !lo || n_elems % 8) return FSR_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   LaunchScope scope(FSR_K_NONE - 1, st);
-  split_f32_kernel<<<ew_blocks(n_elems / 8), 256, 0, st>>>(x, (__half*)hi, (__half*)lo, n_elems / 8);
+  PdlLaunch(ew_blocks(n_elems / 8), 256, 0, st)(split_f32_kernel, x, (__half*)hi, (__half*)lo, n_elems / 8);
   return cuda_rc(cudaGetLastError());
 }
 
@@ -1604,7 +1641,7 @@ int fsr_neck_conv3x3_f32(const float* x, const float* w, const float* bias, cons
   cudaStream_t st = (cudaStream_t)stream;
   const size_t threads = (size_t)N * H * W * 2;
   LaunchScope scope(FSR_K_NECK, st);
-  neck_conv3x3_f32_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(x, w, bias, alpha, out, N, H, W);
+  PdlLaunch((unsigned)((threads + 255) / 256), 256, 0, st)(neck_conv3x3_f32_kernel, x, w, bias, alpha, out, N, H, W);
   return cuda_rc(cudaGetLastError());
 }
 
@@ -1616,7 +1653,7 @@ int fsr_in_stats_f32(const float* x, int64_t* stats, int N, int HW, void* stream
   if (bpi > cap) bpi = cap;
   if (bpi < 1) bpi = 1;
   LaunchScope scope(FSR_K_NONE - 1, st);
-  in_stats_f32_kernel<<<dim3(bpi, N), 256, 0, st>>>(x, reinterpret_cast<long long*>(stats), HW);
+  PdlLaunch(dim3(bpi, N), 256, 0, st)(in_stats_f32_kernel, x, reinterpret_cast<long long*>(stats), HW);
   return cuda_rc(cudaGetLastError());
 }
 
@@ -1630,7 +1667,7 @@ int fsr_in_apply_f32(const float* x, const int64_t* stats, const float* residual
   if (bpi > cap) bpi = cap;
   if (bpi < 1) bpi = 1;
   LaunchScope scope(FSR_K_IN_APPLY, st);
-  in_apply_f32_kernel<<<dim3(bpi, N), 256, 0, st>>>(x, reinterpret_cast<const long long*>(stats), residual, out, (__half*)hi, (__half*)lo,
+  PdlLaunch(dim3(bpi, N), 256, 0, st)(in_apply_f32_kernel, x, reinterpret_cast<const long long*>(stats), residual, out, (__half*)hi, (__half*)lo,
                                                      alpha, act, HW, eps);
   return cuda_rc(cudaGetLastError());
 }
@@ -1640,7 +1677,7 @@ int fsr_ps_prelu_f32(const float* conv, const float* bias_packed, const float* a
   if (!conv || !bias_packed || !alpha || !out || N <= 0 || (hi == nullptr) != (lo == nullptr)) return FSR_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   LaunchScope scope(FSR_K_NONE - 1, st);
-  ps_prelu_f32_kernel<<<ew_blocks((size_t)N * H * W * 32), 256, 0, st>>>(conv, bias_packed, alpha, out, (__half*)hi, (__half*)lo, N, H, W);
+  PdlLaunch(ew_blocks((size_t)N * H * W * 32), 256, 0, st)(ps_prelu_f32_kernel, conv, bias_packed, alpha, out, (__half*)hi, (__half*)lo, N, H, W);
   return cuda_rc(cudaGetLastError());
 }
 
@@ -1649,8 +1686,8 @@ int fsr_tanh_f32(float* pre, uint8_t* out_u8, int N, int HW, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const size_t n = (size_t)N * 3 * HW;
   LaunchScope scope(FSR_K_NONE - 1, st);
-  if (out_u8) tanh_u8_kernel<<<ew_blocks(n), 256, 0, st>>>(pre, out_u8, N, HW);
-  else tanh_f32_kernel<<<ew_blocks(n), 256, 0, st>>>(pre, n);
+  if (out_u8) PdlLaunch(ew_blocks(n), 256, 0, st)(tanh_u8_kernel, pre, out_u8, N, HW);
+  else PdlLaunch(ew_blocks(n), 256, 0, st)(tanh_f32_kernel, pre, n);
   return cuda_rc(cudaGetLastError());
 }
 

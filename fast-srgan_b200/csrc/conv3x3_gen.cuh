@@ -81,6 +81,7 @@ __global__ void __launch_bounds__(GenCfg<MAXTAPS>::kThreads, 1)
 conv3x3_gen_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUtensorMap tm_a1,
                    const __grid_constant__ CUtensorMap tm_a2, const __grid_constant__ CUtensorMap tm_a3,
                    const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ GenParams p) {
+  pdl_grid_sync();
   using Cfg = GenCfg<MAXTAPS>;
   constexpr int NS = 64, TH = 16, TW = 8;
   extern __shared__ uint8_t smem_raw[];

@@ -43,6 +43,7 @@ conv3x3_gen_2cta_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_
                         const __grid_constant__ CUtensorMap tm_a2, const __grid_constant__ CUtensorMap tm_a3,
                         const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_out,
                         const __grid_constant__ GenParams p) {
+  pdl_grid_sync();
   using Cfg = Gen2Cfg<MAXTAPS>;
   using T = T_;
   constexpr int TH = 16, TW = 8, TG = Cfg::TG;

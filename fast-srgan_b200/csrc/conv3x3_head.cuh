@@ -43,6 +43,7 @@ template <typename T>
 __global__ void __launch_bounds__(HeadCfg::kThreads, 1)
 conv3x3_head_kernel(const __grid_constant__ CUtensorMap tm_x, const T* __restrict__ w_packed /*[9][16][cin]*/,
                     const ConvParams p, const int cin) {
+  pdl_grid_sync();
   const int KC = cin >> 6;
   using Cfg = HeadCfg;
   constexpr int TH = Cfg::TH, TW = Cfg::TW;

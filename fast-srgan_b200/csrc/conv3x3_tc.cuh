@@ -127,6 +127,7 @@ template <int NS, int EPI, typename T, bool HALO1, int XF = 0>
 __global__ void __launch_bounds__(XF ? ConvCfg<NS, HALO1>::kThreadsXf : ConvCfg<NS, HALO1>::kThreads, 1)
 conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                    const __grid_constant__ CUtensorMap tm_out, const ConvParams p) {
+  pdl_grid_sync();
   // NHWC outputs leave through a TMA store of the staged (swizzled) tile: no smem read-back, hardware edge clipping
   constexpr bool kTmaStore = (EPI == EPI_RAW_STATS || EPI == EPI_BIAS_ACT);
   using Cfg = ConvCfg<NS, HALO1>;

@@ -102,6 +102,7 @@ template <typename T>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Up2Cfg::kThreads, 1)
 conv3x3_up_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                        const __grid_constant__ CUtensorMap tm_out, const ConvParams p) {
+  pdl_grid_sync();
   using Cfg = Up2Cfg;
   using Geo = Cfg::Geo;
   constexpr int TH = Geo::TH, TW = Geo::TW;

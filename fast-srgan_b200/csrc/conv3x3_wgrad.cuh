@@ -69,6 +69,7 @@ __global__ void __launch_bounds__(WgradCfg::kThreads, 1)
 conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_constant__ CUtensorMap tm_x1,
                      const __grid_constant__ CUtensorMap tm_x2, const __grid_constant__ CUtensorMap tm_x3,
                      const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ WgradParams p) {
+  pdl_grid_sync();
   using Cfg = WgradCfg;
   constexpr int TH = 16, TW = 8;
   extern __shared__ uint8_t smem_raw[];
@@ -203,6 +204,7 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_con
 // 64 input channels x 4 split slices: slice s sums partials s, s+4, s+8, ... four at a time (independent loads in
 // flight: a 1-pair layer has up to 148 partials), the four slice sums are then added in fixed order through smem.
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const __grid_constant__ WgradReduceParams p) {
+  pdl_grid_sync();
   __shared__ float part[4][64][9];
   const int pair_all = blockIdx.x, co0 = blockIdx.y * 8, tap = blockIdx.z;
   const int KC = p.cin >> 6, NSL = p.cout >> 6;

@@ -31,6 +31,7 @@ struct NeckParams {
 
 template <typename T, int TPP>
 __global__ void __launch_bounds__(TPP == 2 ? 256 : 128, TPP == 2 ? 3 : 1) neck_conv3x3_kernel(const NeckParams p) {
+  pdl_grid_sync();
   // TPP threads per output pixel, 64/TPP output channels each.  TPP = 2 (fewer registers, more resident warps) wins on
   // the small training images, TPP = 1 (one input gather per pixel) on large inference batches (measured).
   // weights [27][64] fp32 in smem, read as broadcast float4
@@ -121,6 +122,7 @@ struct InApplyParams {
 
 template <typename T>
 __global__ void __launch_bounds__(256) instnorm_apply_kernel(const InApplyParams p) {
+  pdl_grid_sync();
   extern __shared__ float s_ms[];  // mean[C], rstd[C]
   float* s_mean = s_ms;
   float* s_rstd = s_ms + p.C;
@@ -175,6 +177,7 @@ __global__ void __launch_bounds__(256) instnorm_apply_kernel(const InApplyParams
 template <typename T>
 __global__ void __launch_bounds__(256) pixel_shuffle2_kernel(const T* __restrict__ in, T* __restrict__ out, int N,
                                                              int H, int W, int C /*output channels*/) {
+  pdl_grid_sync();
   const int groups = C / 8;
   const size_t total = (size_t)N * H * W * groups;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
@@ -209,6 +212,7 @@ __global__ void __launch_bounds__(256) pixel_shuffle2_kernel(const T* __restrict
 template <typename T>
 __global__ void __launch_bounds__(256) nchw_f32_to_nhwc_kernel(const float* __restrict__ in, T* __restrict__ out, int N,
                                                                int C, int HW) {
+  pdl_grid_sync();
   // tile transpose through smem: 32 pixels x 32 channels
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
@@ -228,6 +232,7 @@ __global__ void __launch_bounds__(256) nchw_f32_to_nhwc_kernel(const float* __re
 template <typename T>
 __global__ void __launch_bounds__(256) nhwc_to_nchw_f32_kernel(const T* __restrict__ in, float* __restrict__ out, int N,
                                                                int C, int HW) {
+  pdl_grid_sync();
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -250,6 +255,7 @@ __global__ void __launch_bounds__(256) nhwc_to_nchw_f32_kernel(const T* __restri
 template <typename T>
 __global__ void pack_conv3x3_weight_kernel(const float* __restrict__ w, T* __restrict__ out, int cout, int cin,
                                            int cout_pad, int ps_perm) {
+  pdl_grid_sync();
   const size_t total = (size_t)9 * cout_pad * cin;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
     const int ci = (int)(idx % cin);
@@ -276,6 +282,7 @@ __global__ void pack_conv3x3_weight_kernel(const float* __restrict__ w, T* __res
 template <typename T>
 __global__ void pack_conv3x3_weight_t_kernel(const float* __restrict__ w, T* __restrict__ out, int cout, int cin, int ps_perm,
                                              int flip, int row_pad, const float* __restrict__ row_scale) {
+  pdl_grid_sync();
   const size_t total = (size_t)9 * row_pad * cout;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
     const int col = (int)(idx % cout);
@@ -294,6 +301,7 @@ __global__ void pack_conv3x3_weight_t_kernel(const float* __restrict__ w, T* __r
 
 __global__ void permute_bias_ps_kernel(const float* __restrict__ b, float* __restrict__ out, int cout, int cout_pad,
                                        int ps_perm) {
+  pdl_grid_sync();
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= cout_pad) return;
   float v = 0.f;
@@ -323,6 +331,7 @@ struct PackMultiParams {
 
 template <typename T>
 __global__ void __launch_bounds__(256) pack_multi_kernel(const __grid_constant__ PackMultiParams p) {
+  pdl_grid_sync();
   int ti = 0;
   while (ti + 1 < p.n && (int)blockIdx.x >= p.block_begin[ti + 1]) ++ti;
   const PackTaskDev& k = p.t[ti];

@@ -28,6 +28,16 @@ enum : int {
 FSR_DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // ---------------------------------------------------------------- mbarrier
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-serialization attribute may become
+// resident while its predecessor in the stream drains.  griddepcontrol.wait blocks until every prerequisite grid has
+// COMPLETED and its memory is visible (a no-op for a normally launched kernel), so everything after it sees exactly
+// what plain stream order would show; launch_dependents lets the following grid start launching.  Every kernel of this
+// library calls this before its first global-memory access.
+FSR_DEVINL void pdl_grid_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 FSR_DEVINL void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }

@@ -32,6 +32,7 @@ FSR_DEVINL void split_store8(const float (&v)[8], __half* hi, __half* lo) {
 
 // fp32 [n8 * 8] -> fp16 hi / lo planes (same layout)
 __global__ void split_f32_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo, size_t n8) {
+  pdl_grid_sync();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
     const float4 a = reinterpret_cast<const float4*>(x)[2 * i], b = reinterpret_cast<const float4*>(x)[2 * i + 1];
     const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
@@ -44,6 +45,7 @@ __global__ void split_f32_kernel(const float* __restrict__ x, __half* __restrict
 __global__ void __launch_bounds__(256) neck_conv3x3_f32_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                                 const float* __restrict__ bias, const float* __restrict__ alpha,
                                                                 float* __restrict__ out, int N, int H, int W) {
+  pdl_grid_sync();
   __shared__ __align__(16) float sw[27 * 64];
   __shared__ float sb[64];
   for (int i = threadIdx.x; i < 27 * 64; i += blockDim.x) sw[i] = w[(size_t)(i % 64) * 27 + i / 64];   // OIHW -> [tap_ci][co]
@@ -94,6 +96,7 @@ __global__ void __launch_bounds__(256) neck_conv3x3_f32_kernel(const float* __re
 // InstanceNorm statistics of an fp32 NHWC tensor [N][HW][64]: stats [N][64][2] += fixed point (sum * 2^24, sumsq * 2^20).
 // grid (blocks_per_image, N), 256 threads: thread = (pixel lane 0..15, 4-channel group 0..15).
 __global__ void __launch_bounds__(256) in_stats_f32_kernel(const float* __restrict__ x, long long* __restrict__ stats, int HW) {
+  pdl_grid_sync();
   const int n = blockIdx.y;
   const int cg = threadIdx.x & 15, pl = threadIdx.x >> 4;
   const float4* base = reinterpret_cast<const float4*>(x + (size_t)n * HW * 64) + cg;
@@ -126,6 +129,7 @@ __global__ void __launch_bounds__(256) in_apply_f32_kernel(const float* __restri
                                                             const float* __restrict__ residual, float* __restrict__ out,
                                                             __half* __restrict__ hi, __half* __restrict__ lo,
                                                             const float* __restrict__ alpha, int act, int HW, float eps) {
+  pdl_grid_sync();
   const int n = blockIdx.y;
   __shared__ float smean[64], srstd[64];
   if (threadIdx.x < 64) stat_mean_rstd(stats + ((size_t)n * 64 + threadIdx.x) * 2, 1.0 / (double)HW, eps, smean[threadIdx.x], srstd[threadIdx.x]);
@@ -155,6 +159,7 @@ __global__ void __launch_bounds__(256) in_apply_f32_kernel(const float* __restri
 __global__ void __launch_bounds__(256) ps_prelu_f32_kernel(const float* __restrict__ conv, const float* __restrict__ bias_packed,
                                                             const float* __restrict__ alpha, float* __restrict__ out,
                                                             __half* __restrict__ hi, __half* __restrict__ lo, int N, int H, int W) {
+  pdl_grid_sync();
   const float slope = __ldg(alpha);
   const size_t nvec = (size_t)N * H * W * 32;               // 8-column vectors of the conv output
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
@@ -175,9 +180,11 @@ __global__ void __launch_bounds__(256) ps_prelu_f32_kernel(const float* __restri
 
 // head tail (model.py:109 / inference.py:54-56): y = tanh(pre) in place (fp32 NCHW), or -> uint8 NHWC (truncating cast)
 __global__ void tanh_f32_kernel(float* __restrict__ y, size_t n) {
+  pdl_grid_sync();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) y[i] = tanhf(y[i]);
 }
 __global__ void tanh_u8_kernel(const float* __restrict__ pre, uint8_t* __restrict__ out, int N, int HW) {
+  pdl_grid_sync();
   const size_t total = (size_t)N * HW * 3;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % 3);

@@ -81,6 +81,7 @@ FSR_DEVINL void neck_load_strip(const NeckParams& p, int n, int y, int x0, int l
 
 template <typename T, bool IN_U8, bool VGG>
 __global__ void __launch_bounds__(kNeckWarps * 32, 3) neck_conv3x3_mma_kernel(const NeckParams p) {
+  pdl_grid_sync();
   __shared__ float s_strip[kNeckWarps][3 * 3 * 18 + 30];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
@@ -197,6 +198,7 @@ template <typename T>
 __global__ void __launch_bounds__(kWgc3Warps * 32, 3) wgrad_c3_mma_kernel(const float* __restrict__ img, const T* __restrict__ act,
                                                                           float* __restrict__ out, int N, int H, int W, int C64,
                                                                           int flip, int layout) {
+  pdl_grid_sync();
   __shared__ float s_red[32 * 65];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;

@@ -25,6 +25,7 @@ FSR_DEVINL float block_sum(float v, float* smem /* >= 32 floats */) {
 template <bool TO_PARITY>
 __global__ void __launch_bounds__(256) parity_layout_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int N,
                                                             int H, int W, int CV /*C/8*/) {
+  pdl_grid_sync();
   const size_t total = (size_t)N * H * W * CV;
   const int H2 = H >> 1, W2 = W >> 1;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -42,6 +43,7 @@ __global__ void __launch_bounds__(256) parity_layout_kernel(const uint4* __restr
 template <typename T>
 __global__ void __launch_bounds__(256) maxpool2_fwd_kernel(const T* __restrict__ in, T* __restrict__ out, int N, int H,
                                                            int W, int C, int ip = 0, int op = 0) {
+  pdl_grid_sync();
   // ip / op = 1: `in` / `out` are in the zero-bordered PADDED layout [N][H+2][W+2][C] of the flat conv kernels
   // (conv3x3_gen_2cta.cuh, flat mode); only interior pixels are read / written (the caller zero-fills a padded `out`)
   const int Ho = H >> 1, Wo = W >> 1, CV = C / 8;
@@ -82,6 +84,7 @@ __global__ void __launch_bounds__(256) maxpool2_fwd_kernel(const T* __restrict__
 template <typename T>
 __global__ void __launch_bounds__(256) maxpool2_relu_bwd_kernel(const T* __restrict__ in, const T* __restrict__ dout,
                                                                 T* __restrict__ din, int N, int H, int W, int C, int ip = 0, int op = 0) {
+  pdl_grid_sync();
   // ip = 1: `in` and `din` are in the padded layout [N][H+2][W+2][C]; op = 1: `dout` is [N][H/2+2][W/2+2][C]
   const int Ho = H >> 1, Wo = W >> 1;
   const int Wi = W + 2 * ip, Hi = H + 2 * ip, Wq = Wo + 2 * op, Hq = Ho + 2 * op;
@@ -111,6 +114,7 @@ __global__ void __launch_bounds__(256) maxpool2_relu_bwd_kernel(const T* __restr
 template <typename T>
 __global__ void __launch_bounds__(256) relu_bwd_kernel(const uint4* __restrict__ y, const uint4* __restrict__ dy,
                                                        uint4* __restrict__ dx, size_t nvec) {
+  pdl_grid_sync();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
     const uint4 a = y[i], g = dy[i];
     const uint32_t au[4] = {a.x, a.y, a.z, a.w}, gu[4] = {g.x, g.y, g.z, g.w};
@@ -128,6 +132,7 @@ __global__ void __launch_bounds__(256) relu_bwd_kernel(const uint4* __restrict__
 template <typename T>
 __global__ void __launch_bounds__(256) add_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b,
                                                   uint4* __restrict__ out, size_t nvec) {
+  pdl_grid_sync();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
     const uint4 x = a[i], y = b[i];
     const uint32_t xu[4] = {x.x, x.y, x.z, x.w}, yu[4] = {y.x, y.y, y.z, y.w};
@@ -147,6 +152,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) conv1x1_to1_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w,
                                                               const float* __restrict__ b, float* __restrict__ z,
                                                               int npix, int C) {
+  pdl_grid_sync();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= npix) return;
   float acc = 0.f;
@@ -164,6 +170,7 @@ __global__ void __launch_bounds__(256) conv1x1_to1_bwd_kernel(const T* __restric
                                                               const float* __restrict__ dz, T* __restrict__ dx,
                                                               float* __restrict__ dw, float* __restrict__ db,
                                                               int npix, int C) {
+  pdl_grid_sync();
   // thread = channel (C <= 1024 handled by stride), block handles a pixel range
   const int per = (npix + gridDim.x - 1) / gridDim.x;
   const int p0 = blockIdx.x * per, p1 = min(npix, p0 + per);
@@ -190,6 +197,7 @@ __global__ void __launch_bounds__(256) conv1x1_to1_bwd_kernel(const T* __restric
 __global__ void __launch_bounds__(256) bce_logits_kernel(const float* __restrict__ z, const float* __restrict__ noise,
                                                          float lab_scale, float lab_shift, int n, float* __restrict__ loss_out,
                                                          float* __restrict__ dz, float grad_scale) {
+  pdl_grid_sync();
   __shared__ float sm[32];
   float acc = 0.f;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -206,6 +214,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) smooth_l1_kernel(const T* __restrict__ a, const T* __restrict__ b, size_t n,
                                                         float* __restrict__ loss_acc /* += sum */, T* __restrict__ da,
                                                         float grad_scale /* = weight / n */) {
+  pdl_grid_sync();
   __shared__ float sm[32];
   float acc = 0.f;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -220,6 +229,7 @@ __global__ void __launch_bounds__(256) smooth_l1_kernel(const T* __restrict__ a,
 // same with fp32 NCHW operands (pretrain step, trainer.py:109): a = generator output, b = hr images
 __global__ void __launch_bounds__(256) smooth_l1_f32_kernel(const float* __restrict__ a, const float* __restrict__ b, size_t n,
                                                             float* __restrict__ loss_acc, float* __restrict__ da, float grad_scale) {
+  pdl_grid_sync();
   __shared__ float sm[32];
   float acc = 0.f;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -253,6 +263,7 @@ struct InBwdParams {
 
 template <typename T, int PASS>
 __global__ void __launch_bounds__(256) instnorm_bwd_kernel(const InBwdParams p) {
+  pdl_grid_sync();
   extern __shared__ float s_all[];   // mean[C], rstd[C], (pass 1: acc1[C], acc2[C]) (pass 2: m1[C], m2[C])
   float* s_mean = s_all;
   float* s_rstd = s_all + p.C;
@@ -345,6 +356,7 @@ __global__ void __launch_bounds__(256) instnorm_bwd_kernel(const InBwdParams p) 
 // reduction, no atomics): the InstanceNorm backward is bitwise reproducible.
 template <typename T>
 __global__ void __launch_bounds__(256) instnorm_bwd_fused_kernel(const InBwdParams p) {
+  pdl_grid_sync();
   __shared__ float s_red[8][2][16];                  // [warp][vector of the pixel][a1 0..7, a2 0..7]
   __shared__ float s_m[2][16];                       // mean(g), mean(g*xhat) per (vector, channel)
   __shared__ float s_da[8];
@@ -447,6 +459,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) act_bwd_kernel(const uint4* __restrict__ y, const uint4* __restrict__ dy,
                                                       uint4* __restrict__ dv, size_t nvec, const float* alpha, float slope_in,
                                                       int act, float* dalpha) {
+  pdl_grid_sync();
   const float slope = (act == ACT_PRELU) ? __ldg(alpha) : slope_in;
   const float inv = slope != 0.f ? 1.0f / slope : 0.f;
   float da = 0.f;
@@ -479,6 +492,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) ps_prelu_bwd_kernel(const T* __restrict__ U, const T* __restrict__ dU,
                                                            T* __restrict__ dconv, int N, int H, int W, int F,
                                                            const float* __restrict__ alpha, float* dalpha) {
+  pdl_grid_sync();
   const float slope = __ldg(alpha);
   const float inv = slope != 0.f ? 1.0f / slope : 0.f;
   const int vpc = F >> 3;                           // 8-channel vectors per output pixel
@@ -515,6 +529,7 @@ __global__ void __launch_bounds__(256) ps_prelu_bwd_kernel(const T* __restrict__
 // y = tanh(conv + b) fp32 NCHW [N,3,H,W];  dpre = dy * (1 - y^2)  (fp32 NCHW, feeds the 3->64 direct dgrad)
 __global__ void __launch_bounds__(256) tanh_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dy,
                                                        float* __restrict__ dpre, size_t n) {
+  pdl_grid_sync();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     dpre[i] = dy[i] * (1.0f - y[i] * y[i]);
 }
@@ -529,6 +544,7 @@ template <typename T>
 __global__ void __launch_bounds__(224) wgrad_c3_kernel(const float* __restrict__ img, const T* __restrict__ act,
                                                        float* __restrict__ out, int N, int H, int W, int C64, int flip,
                                                        int layout /*0: [27][C64]; 1: OIHW [3][C64][9] (head); 2: OIHW [C64][3][9] (neck)*/) {
+  pdl_grid_sync();
   // thread = (k = c3*9 + tap, 8-channel group): one image value + one 16-B activation vector -> 8 FMAs per pixel;
   // a block walks a contiguous pixel range and issues 8 atomics per thread at the end.
   const int k = threadIdx.x >> 3, cg = threadIdx.x & 7;
@@ -586,6 +602,7 @@ __global__ void __launch_bounds__(224) wgrad_c3_kernel(const float* __restrict__
 template <typename T>
 __global__ void __launch_bounds__(256) bias_grad_kernel(const T* __restrict__ g, float* __restrict__ db, size_t npix, int C,
                                                         int ps_perm /* g columns pixel-shuffle-permuted: col q*C/4+c <-> channel 4c+q */) {
+  pdl_grid_sync();
   // thread = (8-channel vector, pixel lane): 16-B loads, register accumulation, one smem + one global atomic per channel
   extern __shared__ float s_acc[];           // [C]
   for (int c = threadIdx.x; c < C; c += blockDim.x) s_acc[c] = 0.f;
@@ -619,6 +636,7 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(const T* __restrict__ g,
 // fp32 NCHW variant (head bias: g = dpre [N,3,H,W])
 __global__ void __launch_bounds__(256) bias_grad_nchw_kernel(const float* __restrict__ g, float* __restrict__ db, int N, int C,
                                                              size_t HW) {
+  pdl_grid_sync();
   __shared__ float sm[32];
   const int c = blockIdx.y;
   float acc = 0.f;
@@ -635,6 +653,7 @@ __global__ void __launch_bounds__(256) bias_grad_nchw_kernel(const float* __rest
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                     float* __restrict__ v, size_t n, float lr, float b1, float b2, float eps,
                                                     float wd, float bc1, float bc2_sqrt, float grad_scale) {
+  pdl_grid_sync();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const float gi = g[i] * grad_scale;
     float pi = p[i] * (1.0f - lr * wd);
@@ -648,10 +667,12 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
 }
 
 // Device-side step counter variant (CUDA-graph friendly: nothing step-dependent is baked into launch parameters)
-__global__ void step_inc_kernel(int* step) { if (threadIdx.x == 0 && blockIdx.x == 0) *step += 1; }
+__global__ void step_inc_kernel(int* step) {
+  pdl_grid_sync(); if (threadIdx.x == 0 && blockIdx.x == 0) *step += 1; }
 __global__ void __launch_bounds__(256) adamw_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                         float* __restrict__ v, size_t n, float lr, float b1, float b2, float eps,
                                                         float wd, const int* __restrict__ step, float grad_scale) {
+  pdl_grid_sync();
   const float t = (float)(*step);
   const float bc1 = 1.0f - powf(b1, t);
   const float bc2_sqrt = sqrtf(1.0f - powf(b2, t));

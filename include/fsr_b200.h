@@ -380,6 +380,12 @@ int fsr_neck_conv3x3_c32(const void* x, const float* w64, const float* bias64, c
  * weights are pair-expanded, i.e. tap column 0 only has input slots 32..63 and tap column 2 only 0..31 non-zero, so 12 of
  * the 36 K-steps per tile are not issued.  Results are identical to on = 0 for such weights; switch it off afterwards. */
 int fsr_set_pair_rows(int on);
+
+/* Programmatic dependent launch for every kernel of the library (default OFF; env FSR_PDL=1): launches carry the
+ * programmatic-stream-serialization attribute and every kernel waits for its predecessor's completion on the device
+ * (griddepcontrol.wait) before its first global access - same results as plain stream order.  Measured slower on B200
+ * for this workload, kept as a switch. */
+int fsr_set_pdl(int on);
 int fsr_in_stats_fold_pair(int64_t* stats, int N, void* stream);
 int fsr_conv3x3_c64_head_pair(const void* x, const void* w_packed, void* out, const float* bias, int N, int H, int Wp,
                               int out_u8, int dtype, void* stream);
