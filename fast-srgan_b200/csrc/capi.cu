@@ -188,6 +188,48 @@ int num_sms() {
   return sms;
 }
 
+// Pool of zeroed reduction slots for the deterministic cross-block sums (fsr_common.cuh DetRed).  Every launch that
+// reduces takes the next slot round-robin; a slot is left zeroed by the launch that used it.  512 slots: a slot is only
+// handed out again 512 reducing launches later (a training step has ~25), long after its previous user has finished -
+// also when a step is a captured graph (the slot index is baked in; replays of one graph serialise).  Allocated per
+// device on first use; the weight-pack entry points touch it too, so that it exists before any stream capture.
+constexpr int kDetSlots = 512;
+struct DetPool { unsigned long long* acc = nullptr; unsigned int* tickets = nullptr; };
+DetPool g_det_pool[16];
+std::atomic<unsigned> g_det_next{0};
+std::mutex g_det_mutex;
+int det_pool_ensure(DetPool** out = nullptr) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 16) return FSR_ERR_BAD_ARG;
+  DetPool& P = g_det_pool[dev];
+  if (!P.acc) {
+    std::lock_guard<std::mutex> lock(g_det_mutex);
+    if (!P.acc) {
+      unsigned long long* a = nullptr;
+      unsigned int* t = nullptr;
+      FSR_CUDA(cudaMalloc(&a, (size_t)kDetSlots * kDetSlotLen * sizeof(unsigned long long)));
+      FSR_CUDA(cudaMalloc(&t, (size_t)kDetSlots * sizeof(unsigned int)));
+      FSR_CUDA(cudaMemset(a, 0, (size_t)kDetSlots * kDetSlotLen * sizeof(unsigned long long)));
+      FSR_CUDA(cudaMemset(t, 0, (size_t)kDetSlots * sizeof(unsigned int)));
+      FSR_CUDA(cudaDeviceSynchronize());
+      P.tickets = t;
+      P.acc = a;
+    }
+  }
+  if (out) *out = &P;
+  return FSR_OK;
+}
+int det_slot(DetRed* r) {
+  DetPool* P = nullptr;
+  const int rc = det_pool_ensure(&P);
+  if (rc) return rc;
+  const unsigned s = g_det_next.fetch_add(1, std::memory_order_relaxed) % kDetSlots;
+  r->acc = P->acc + (size_t)s * kDetSlotLen;
+  r->ticket = P->tickets + s;
+  return FSR_OK;
+}
+
 int g_halo1 = -1;   // A-operand staging: 0 = 3 column-shifted halo tiles, 1 = single halo tile (see conv3x3_tc.cuh)
 int halo_mode() {
   if (ctx_opt(kOptHalo1) >= 0) return ctx_opt(kOptHalo1);
@@ -752,6 +794,7 @@ const char* fsr_error_string(int code) {
 
 int fsr_pack_conv3x3_weight(const float* w_oihw, const float* bias, void* w_packed, float* bias_packed, int cout,
                             int cin, int cout_pad, int ps_perm, int dtype, void* stream) {
+  { const int rc_pool = det_pool_ensure(); if (rc_pool) return rc_pool; }   // before any stream capture
   if (cout <= 0 || cin <= 0 || cout_pad < cout || (ps_perm && cout % 4)) return FSR_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t total = (size_t)9 * cout_pad * cin;
@@ -766,6 +809,7 @@ int fsr_pack_conv3x3_weight(const float* w_oihw, const float* bias, void* w_pack
 }
 
 int fsr_pack_multi(const FsrPackTask* tasks, int n, int dtype, void* stream) {
+  { const int rc_pool = det_pool_ensure(); if (rc_pool) return rc_pool; }   // before any stream capture
   if (!tasks || n <= 0 || n > kPackMaxTasks) return FSR_ERR_BAD_ARG;
   PackMultiParams p{};
   p.n = n;
@@ -1271,6 +1315,7 @@ int fsr_generator_forward(const FsrGeneratorParams* prm, const void* x, void* y,
 
 int fsr_pack_conv3x3_weight_t(const float* w_oihw, void* w_packed, int cout, int cin, int ps_perm, int flip, int row_pad,
                               const float* row_scale, int dtype, void* stream) {
+  { const int rc_pool = det_pool_ensure(); if (rc_pool) return rc_pool; }   // before any stream capture
   // transposed pack for data-gradient convs (rows = forward input channel, K = forward output channel)
   if (!w_oihw || !w_packed || cout <= 0 || cin <= 0 || row_pad < cin) return FSR_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
@@ -1384,9 +1429,12 @@ int fsr_conv1x1_to1_bwd(const void* x, const float* w, const float* dz, void* dx
   cudaStream_t st = (cudaStream_t)stream;
   int blocks = (npix + 15) / 16;
   if (blocks > num_sms() * 4) blocks = num_sms() * 4;
+  if (C + 1 > kDetSlotLen) return FSR_ERR_BAD_SHAPE;
+  DetRed red;
+  { const int rc = det_slot(&red); if (rc) return rc; }
   LaunchScope scope(FSR_K_NONE - 1, st);
-  FSR_T((PdlLaunch(blocks, 256, 0, st)(conv1x1_to1_bwd_kernel<__half>, (const __half*)x, w, dz, (__half*)dx, dw, db, npix, C)),
-        (PdlLaunch(blocks, 256, 0, st)(conv1x1_to1_bwd_kernel<__nv_bfloat16>, (const __nv_bfloat16*)x, w, dz, (__nv_bfloat16*)dx, dw, db, npix, C)));
+  FSR_T((PdlLaunch(blocks, 256, 0, st)(conv1x1_to1_bwd_kernel<__half>, (const __half*)x, w, dz, (__half*)dx, dw, db, npix, C, red)),
+        (PdlLaunch(blocks, 256, 0, st)(conv1x1_to1_bwd_kernel<__nv_bfloat16>, (const __nv_bfloat16*)x, w, dz, (__nv_bfloat16*)dx, dw, db, npix, C, red)));
   return cuda_rc(cudaGetLastError());
 }
 
@@ -1402,10 +1450,12 @@ int fsr_bce_logits(const float* z, const float* noise, float lab_scale, float la
 int fsr_smooth_l1(const void* a, const void* b, size_t n, float* loss_acc, void* da, float grad_scale, int dtype, void* stream) {
   if (!a || !b || !loss_acc) return FSR_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
+  DetRed red;
+  { const int rc = det_slot(&red); if (rc) return rc; }
   LaunchScope scope(FSR_K_NONE - 1, st);
-  if (dtype == 2) PdlLaunch(ew_blocks(n), 256, 0, st)(smooth_l1_f32_kernel, (const float*)a, (const float*)b, n, loss_acc, (float*)da, grad_scale);
-  else FSR_T((PdlLaunch(ew_blocks(n), 256, 0, st)(smooth_l1_kernel<__half>, (const __half*)a, (const __half*)b, n, loss_acc, (__half*)da, grad_scale)),
-             (PdlLaunch(ew_blocks(n), 256, 0, st)(smooth_l1_kernel<__nv_bfloat16>, (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, n, loss_acc, (__nv_bfloat16*)da, grad_scale)));
+  if (dtype == 2) PdlLaunch(ew_blocks(n), 256, 0, st)(smooth_l1_f32_kernel, (const float*)a, (const float*)b, n, loss_acc, (float*)da, grad_scale, red);
+  else FSR_T((PdlLaunch(ew_blocks(n), 256, 0, st)(smooth_l1_kernel<__half>, (const __half*)a, (const __half*)b, n, loss_acc, (__half*)da, grad_scale, red)),
+             (PdlLaunch(ew_blocks(n), 256, 0, st)(smooth_l1_kernel<__nv_bfloat16>, (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, n, loss_acc, (__nv_bfloat16*)da, grad_scale, red)));
   return cuda_rc(cudaGetLastError());
 }
 
@@ -1419,6 +1469,7 @@ static int instnorm_bwd_impl(const void* raw, const int64_t* stats, const void* 
   if (dy_parity_w && (!fused || (dy_parity_w & 1) || HW % dy_parity_w || ((HW / dy_parity_w) & 1))) return FSR_ERR_BAD_SHAPE;
   if (fused) {
     // training shapes: one launch, the per-(n,c) sums stay inside the block (no `red` scratch, no memset, no atomics)
+    if (act == FSR_ACT_PRELU && dalpha) { const int rc = det_slot(&p.det); if (rc) return rc; }
     LaunchScope scope(FSR_K_NONE - 1, st);
     FSR_T((PdlLaunch(dim3(C / 16, N), 256, 0, st)(instnorm_bwd_fused_kernel<__half>, p)),
           (PdlLaunch(dim3(C / 16, N), 256, 0, st)(instnorm_bwd_fused_kernel<__nv_bfloat16>, p)));
@@ -1459,9 +1510,11 @@ int fsr_act_bwd(const void* y, const void* dy, void* dv, size_t n_elems, const f
   if (!y || !dy || !dv || n_elems % 8) return FSR_ERR_BAD_ARG;
   if (act == FSR_ACT_PRELU && !alpha) return FSR_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
+  DetRed red{nullptr, nullptr};
+  if (act == FSR_ACT_PRELU && dalpha) { const int rc = det_slot(&red); if (rc) return rc; }
   LaunchScope scope(FSR_K_NONE - 1, st);
-  FSR_T((PdlLaunch(ew_blocks(n_elems / 8), 256, 0, st)(act_bwd_kernel<__half>, (const uint4*)y, (const uint4*)dy, (uint4*)dv, n_elems / 8, alpha, slope, act, dalpha)),
-        (PdlLaunch(ew_blocks(n_elems / 8), 256, 0, st)(act_bwd_kernel<__nv_bfloat16>, (const uint4*)y, (const uint4*)dy, (uint4*)dv, n_elems / 8, alpha, slope, act, dalpha)));
+  FSR_T((PdlLaunch(ew_blocks(n_elems / 8), 256, 0, st)(act_bwd_kernel<__half>, (const uint4*)y, (const uint4*)dy, (uint4*)dv, n_elems / 8, alpha, slope, act, dalpha, red)),
+        (PdlLaunch(ew_blocks(n_elems / 8), 256, 0, st)(act_bwd_kernel<__nv_bfloat16>, (const uint4*)y, (const uint4*)dy, (uint4*)dv, n_elems / 8, alpha, slope, act, dalpha, red)));
   return cuda_rc(cudaGetLastError());
 }
 
@@ -1470,9 +1523,11 @@ int fsr_ps_prelu_bwd(const void* U, const void* dU, void* dconv, int N, int H, i
   if (!U || !dU || !dconv || !alpha || F <= 0 || F % 8) return FSR_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t total = (size_t)N * H * W * 4 * (F / 8);
+  DetRed red{nullptr, nullptr};
+  if (dalpha) { const int rc = det_slot(&red); if (rc) return rc; }
   LaunchScope scope(FSR_K_NONE - 1, st);
-  FSR_T((PdlLaunch(ew_blocks(total), 256, 0, st)(ps_prelu_bwd_kernel<__half>, (const __half*)U, (const __half*)dU, (__half*)dconv, N, H, W, F, alpha, dalpha)),
-        (PdlLaunch(ew_blocks(total), 256, 0, st)(ps_prelu_bwd_kernel<__nv_bfloat16>, (const __nv_bfloat16*)U, (const __nv_bfloat16*)dU, (__nv_bfloat16*)dconv, N, H, W, F, alpha, dalpha)));
+  FSR_T((PdlLaunch(ew_blocks(total), 256, 0, st)(ps_prelu_bwd_kernel<__half>, (const __half*)U, (const __half*)dU, (__half*)dconv, N, H, W, F, alpha, dalpha, red)),
+        (PdlLaunch(ew_blocks(total), 256, 0, st)(ps_prelu_bwd_kernel<__nv_bfloat16>, (const __nv_bfloat16*)U, (const __nv_bfloat16*)dU, (__nv_bfloat16*)dconv, N, H, W, F, alpha, dalpha, red)));
   return cuda_rc(cudaGetLastError());
 }
 
@@ -1493,6 +1548,9 @@ int fsr_wgrad_c3(const float* img, const void* act, float* out, int N, int H, in
   if (bx > num_sms() * 4) bx = num_sms() * 4;
   if (bx < 1) bx = 1;
   dim3 grid(bx, C64 / 64);
+  if (27 * C64 > kDetSlotLen) return FSR_ERR_BAD_SHAPE;
+  DetRed red;
+  { const int rc = det_slot(&red); if (rc) return rc; }
   LaunchScope scope(FSR_K_NONE - 1, st);
   if (small_mma_mode()) {
     if (total >= ((size_t)1 << 31) - 16) return FSR_ERR_BAD_SHAPE;
@@ -1500,12 +1558,12 @@ int fsr_wgrad_c3(const float* img, const void* act, float* out, int N, int H, in
     long long mb = (steps + 8 * kWgc3Warps - 1) / (8 * kWgc3Warps);      // >= 8 steps per warp
     if (mb > (long long)num_sms() * 3) mb = (long long)num_sms() * 3;
     dim3 mgrid((unsigned)mb, C64 / 64);
-    FSR_T((PdlLaunch(mgrid, kWgc3Warps * 32, 0, st)(wgrad_c3_mma_kernel<__half>, img, (const __half*)act, out, N, H, W, C64, flip, layout)),
-          (PdlLaunch(mgrid, kWgc3Warps * 32, 0, st)(wgrad_c3_mma_kernel<__nv_bfloat16>, img, (const __nv_bfloat16*)act, out, N, H, W, C64, flip, layout)));
+    FSR_T((PdlLaunch(mgrid, kWgc3Warps * 32, 0, st)(wgrad_c3_mma_kernel<__half>, img, (const __half*)act, out, N, H, W, C64, flip, layout, red)),
+          (PdlLaunch(mgrid, kWgc3Warps * 32, 0, st)(wgrad_c3_mma_kernel<__nv_bfloat16>, img, (const __nv_bfloat16*)act, out, N, H, W, C64, flip, layout, red)));
     return cuda_rc(cudaGetLastError());
   }
-  FSR_T((PdlLaunch(grid, 224, 0, st)(wgrad_c3_kernel<__half>, img, (const __half*)act, out, N, H, W, C64, flip, layout)),
-        (PdlLaunch(grid, 224, 0, st)(wgrad_c3_kernel<__nv_bfloat16>, img, (const __nv_bfloat16*)act, out, N, H, W, C64, flip, layout)));
+  FSR_T((PdlLaunch(grid, 224, 0, st)(wgrad_c3_kernel<__half>, img, (const __half*)act, out, N, H, W, C64, flip, layout, red)),
+        (PdlLaunch(grid, 224, 0, st)(wgrad_c3_kernel<__nv_bfloat16>, img, (const __nv_bfloat16*)act, out, N, H, W, C64, flip, layout, red)));
   return cuda_rc(cudaGetLastError());
 }
 
@@ -1515,10 +1573,13 @@ int fsr_bias_grad(const void* g, float* db, size_t npix, int C, int ps_perm, int
   int blocks = (int)((npix + 255) / 256);
   if (blocks > num_sms() * 4) blocks = num_sms() * 4;
   if (blocks < 1) blocks = 1;
-  const size_t sm = (size_t)C * sizeof(float);
+  const size_t sm = (size_t)C * sizeof(unsigned long long);
+  if (C > kDetSlotLen) return FSR_ERR_BAD_SHAPE;
+  DetRed red;
+  { const int rc = det_slot(&red); if (rc) return rc; }
   LaunchScope scope(FSR_K_NONE - 1, st);
-  FSR_T((PdlLaunch(blocks, 256, sm, st)(bias_grad_kernel<__half>, (const __half*)g, db, npix, C, ps_perm)),
-        (PdlLaunch(blocks, 256, sm, st)(bias_grad_kernel<__nv_bfloat16>, (const __nv_bfloat16*)g, db, npix, C, ps_perm)));
+  FSR_T((PdlLaunch(blocks, 256, sm, st)(bias_grad_kernel<__half>, (const __half*)g, db, npix, C, ps_perm, red)),
+        (PdlLaunch(blocks, 256, sm, st)(bias_grad_kernel<__nv_bfloat16>, (const __nv_bfloat16*)g, db, npix, C, ps_perm, red)));
   return cuda_rc(cudaGetLastError());
 }
 
@@ -1527,8 +1588,11 @@ int fsr_bias_grad_nchw(const float* g, float* db, int N, int C, size_t HW, void*
   cudaStream_t st = (cudaStream_t)stream;
   int bx = (int)((HW + 255) / 256);
   if (bx > 64) bx = 64;
+  if (C > kDetSlotLen) return FSR_ERR_BAD_SHAPE;
+  DetRed red;
+  { const int rc = det_slot(&red); if (rc) return rc; }
   LaunchScope scope(FSR_K_NONE - 1, st);
-  PdlLaunch(dim3(bx, C), 256, 0, st)(bias_grad_nchw_kernel, g, db, N, C, HW);
+  PdlLaunch(dim3(bx, C), 256, 0, st)(bias_grad_nchw_kernel, g, db, N, C, HW, red);
   return cuda_rc(cudaGetLastError());
 }
 

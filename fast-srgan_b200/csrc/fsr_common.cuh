@@ -303,6 +303,49 @@ FSR_DEVINL void stat_mean_rstd(const long long* st, double inv_count, float eps,
   rstd = (float)(1.0 / sqrt(var + (double)eps));
 }
 
+// ---- deterministic cross-block reductions of the backward pass (bias / PReLU-slope / 3-channel weight gradients, loss sums)
+// fp32 atomicAdd makes a sum depend on the order in which blocks arrive; these sums go through 64-bit FIXED-POINT integer
+// atomics instead (associative -> order-independent) into a zeroed slot of the library's pool (capi.cu det_slot()), and the
+// LAST block to arrive converts the totals and adds them to the fp32 outputs, then re-zeroes the slot.  One launch, no
+// caller-visible scratch; with the two-stage weight gradients and the in-block InstanceNorm sums this makes the whole
+// training step bitwise reproducible run to run.
+struct DetRed {
+  unsigned long long* acc;   // [kDetSlotLen], all zero between launches
+  unsigned int* ticket;      // 0 between launches
+};
+constexpr int kDetSlotLen = 16384;
+constexpr float kDetScale = 68719476736.f;          // 2^36: |sum| < 1.3e8, resolution 1.5e-11 per contribution
+FSR_DEVINL unsigned long long det_fix(float v) { return (unsigned long long)__float2ll_rn(v * kDetScale); }
+FSR_DEVINL void det_add(const DetRed& r, int i, float v) { atomicAdd(r.acc + i, det_fix(v)); }
+// det_arrive: called by EVERY thread of EVERY block exactly once, after the block's det_add()s; true (block-uniform) in the
+// last block to arrive, which then det_collect()s the totals (out[i] += total[i0 + i], slot re-zeroed) and det_release()s.
+FSR_DEVINL int det_tid() { return threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z); }
+FSR_DEVINL bool det_arrive(const DetRed& r) {
+  __shared__ unsigned int s_last;
+  __threadfence();
+  __syncthreads();
+  if (det_tid() == 0) s_last = (atomicAdd(r.ticket, 1u) == gridDim.x * gridDim.y * gridDim.z - 1u) ? 1u : 0u;
+  __syncthreads();
+  const bool last = s_last != 0u;
+  if (last) __threadfence();
+  return last;
+}
+FSR_DEVINL void det_collect(const DetRed& r, int i0, int n, float* __restrict__ out) {
+  const int nthreads = blockDim.x * blockDim.y * blockDim.z;
+  for (int i = det_tid(); i < n; i += nthreads) {
+    const long long v = (long long)atomicExch(r.acc + i0 + i, 0ull);
+    if (v != 0) out[i] += __ll2float_rn(v) * (1.0f / kDetScale);
+  }
+}
+FSR_DEVINL void det_release(const DetRed& r) {
+  if (det_tid() == 0) atomicExch(r.ticket, 0u);
+}
+FSR_DEVINL void det_finish(const DetRed& r, float* __restrict__ out, int nout) {
+  if (!det_arrive(r)) return;
+  det_collect(r, 0, nout, out);
+  det_release(r);
+}
+
 FSR_DEVINL float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

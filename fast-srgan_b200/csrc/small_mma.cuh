@@ -197,7 +197,7 @@ constexpr int kWgc3Warps = 4;
 template <typename T>
 __global__ void __launch_bounds__(kWgc3Warps * 32, 3) wgrad_c3_mma_kernel(const float* __restrict__ img, const T* __restrict__ act,
                                                                           float* __restrict__ out, int N, int H, int W, int C64,
-                                                                          int flip, int layout) {
+                                                                          int flip, int layout, DetRed red) {
   pdl_grid_sync();
   __shared__ float s_red[32 * 65];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -336,8 +336,9 @@ __global__ void __launch_bounds__(kWgc3Warps * 32, 3) wgrad_c3_mma_kernel(const 
       idx = (size_t)k * C64 + cbase + c;
     }
     const float vsum = s_red[k * 65 + c];
-    if (vsum != 0.f) atomicAdd(out + idx, vsum);
+    if (vsum != 0.f) det_add(red, (int)idx, vsum);       // fixed-point: the total does not depend on block order
   }
+  det_finish(red, out, 27 * C64);
 }
 
 }  // namespace fsr

@@ -169,7 +169,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) conv1x1_to1_bwd_kernel(const T* __restrict__ x, const float* __restrict__ w,
                                                               const float* __restrict__ dz, T* __restrict__ dx,
                                                               float* __restrict__ dw, float* __restrict__ db,
-                                                              int npix, int C) {
+                                                              int npix, int C, DetRed red) {
   pdl_grid_sync();
   // thread = channel (C <= 1024 handled by stride), block handles a pixel range
   const int per = (npix + gridDim.x - 1) / gridDim.x;
@@ -182,12 +182,17 @@ __global__ void __launch_bounds__(256) conv1x1_to1_bwd_kernel(const T* __restric
       acc = fmaf(g, Cvt<T>::to_f(x[(size_t)p * C + c]), acc);
       if (dx) dx[(size_t)p * C + c] = Cvt<T>::from_f(g * wc);
     }
-    if (dw) atomicAdd(dw + c, acc);
+    if (dw) det_add(red, c, acc);
   }
   if (db && threadIdx.x == 0) {
     float s = 0.f;
     for (int p = p0; p < p1; ++p) s += dz[p];
-    atomicAdd(db, s);
+    det_add(red, C, s);
+  }
+  if ((dw || db) && det_arrive(red)) {            // deterministic cross-block sums (fsr_common.cuh DetRed)
+    if (dw) det_collect(red, 0, C, dw);
+    if (db) det_collect(red, C, 1, db);
+    det_release(red);
   }
 }
 
@@ -213,7 +218,7 @@ __global__ void __launch_bounds__(256) bce_logits_kernel(const float* __restrict
 template <typename T>
 __global__ void __launch_bounds__(256) smooth_l1_kernel(const T* __restrict__ a, const T* __restrict__ b, size_t n,
                                                         float* __restrict__ loss_acc /* += sum */, T* __restrict__ da,
-                                                        float grad_scale /* = weight / n */) {
+                                                        float grad_scale /* = weight / n */, DetRed red) {
   pdl_grid_sync();
   __shared__ float sm[32];
   float acc = 0.f;
@@ -224,11 +229,13 @@ __global__ void __launch_bounds__(256) smooth_l1_kernel(const T* __restrict__ a,
     if (da) da[i] = Cvt<T>::from_f(grad_scale * (ad < 1.f ? d : (d > 0.f ? 1.f : -1.f)));
   }
   acc = block_sum(acc, sm);
-  if (threadIdx.x == 0) atomicAdd(loss_acc, acc);
+  if (threadIdx.x == 0) det_add(red, 0, acc);
+  det_finish(red, loss_acc, 1);
 }
 // same with fp32 NCHW operands (pretrain step, trainer.py:109): a = generator output, b = hr images
 __global__ void __launch_bounds__(256) smooth_l1_f32_kernel(const float* __restrict__ a, const float* __restrict__ b, size_t n,
-                                                            float* __restrict__ loss_acc, float* __restrict__ da, float grad_scale) {
+                                                            float* __restrict__ loss_acc, float* __restrict__ da, float grad_scale,
+                                                            DetRed red) {
   pdl_grid_sync();
   __shared__ float sm[32];
   float acc = 0.f;
@@ -239,7 +246,8 @@ __global__ void __launch_bounds__(256) smooth_l1_f32_kernel(const float* __restr
     if (da) da[i] = grad_scale * (ad < 1.f ? d : (d > 0.f ? 1.f : -1.f));
   }
   acc = block_sum(acc, sm);
-  if (threadIdx.x == 0) atomicAdd(loss_acc, acc);
+  if (threadIdx.x == 0) det_add(red, 0, acc);
+  det_finish(red, loss_acc, 1);
 }
 
 // ------------------------------------------------------------------ InstanceNorm (+activation) backward
@@ -259,6 +267,7 @@ struct InBwdParams {
   float eps;
   int dy_parity_w;       // > 0: `dy` is in the parity-plane layout [N][4][H/2][W/2][C] a stride-2 data gradient writes
                          //      (image width W = dy_parity_w): folds fsr_parity_layout(from parity) into this pass (fused kernel)
+  DetRed det;            // fused kernel: slot for the deterministic PReLU-slope sum
 };
 
 template <typename T, int PASS>
@@ -427,7 +436,7 @@ __global__ void __launch_bounds__(256) instnorm_bwd_fused_kernel(const InBwdPara
   if (threadIdx.x == 32 && p.act == ACT_PRELU && p.dalpha) {
     float t = 0.f;
     for (int i = 0; i < 8; ++i) t += s_da[i];
-    atomicAdd(p.dalpha, t);
+    det_add(p.det, 0, t);
   }
   __syncthreads();
   float m1[8], m2[8];
@@ -450,6 +459,7 @@ __global__ void __launch_bounds__(256) instnorm_bwd_fused_kernel(const InBwdPara
     }
     *reinterpret_cast<uint4*>(draw + (size_t)px * p.C) = make_uint4(ou[0], ou[1], ou[2], ou[3]);
   }
+  if (p.act == ACT_PRELU && p.dalpha) det_finish(p.det, p.dalpha, 1);   // order-independent slope-gradient total
 }
 
 // ------------------------------------------------------------------ plain activation backward (no norm)
@@ -458,7 +468,7 @@ __global__ void __launch_bounds__(256) instnorm_bwd_fused_kernel(const InBwdPara
 template <typename T>
 __global__ void __launch_bounds__(256) act_bwd_kernel(const uint4* __restrict__ y, const uint4* __restrict__ dy,
                                                       uint4* __restrict__ dv, size_t nvec, const float* alpha, float slope_in,
-                                                      int act, float* dalpha) {
+                                                      int act, float* dalpha, DetRed red) {
   pdl_grid_sync();
   const float slope = (act == ACT_PRELU) ? __ldg(alpha) : slope_in;
   const float inv = slope != 0.f ? 1.0f / slope : 0.f;
@@ -479,7 +489,8 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const uint4* __restrict__ 
   }
   if (act == ACT_PRELU && dalpha) {
     da = warp_sum(da);
-    if ((threadIdx.x & 31) == 0) atomicAdd(dalpha, da);
+    if ((threadIdx.x & 31) == 0) det_add(red, 0, da);
+    det_finish(red, dalpha, 1);
   }
 }
 
@@ -491,7 +502,7 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const uint4* __restrict__ 
 template <typename T>
 __global__ void __launch_bounds__(256) ps_prelu_bwd_kernel(const T* __restrict__ U, const T* __restrict__ dU,
                                                            T* __restrict__ dconv, int N, int H, int W, int F,
-                                                           const float* __restrict__ alpha, float* dalpha) {
+                                                           const float* __restrict__ alpha, float* dalpha, DetRed red) {
   pdl_grid_sync();
   const float slope = __ldg(alpha);
   const float inv = slope != 0.f ? 1.0f / slope : 0.f;
@@ -521,7 +532,8 @@ __global__ void __launch_bounds__(256) ps_prelu_bwd_kernel(const T* __restrict__
   }
   if (dalpha) {
     da = warp_sum(da);
-    if ((threadIdx.x & 31) == 0) atomicAdd(dalpha, da);
+    if ((threadIdx.x & 31) == 0) det_add(red, 0, da);
+    det_finish(red, dalpha, 1);
   }
 }
 
@@ -543,12 +555,13 @@ __global__ void __launch_bounds__(256) tanh_bwd_kernel(const float* __restrict__
 template <typename T>
 __global__ void __launch_bounds__(224) wgrad_c3_kernel(const float* __restrict__ img, const T* __restrict__ act,
                                                        float* __restrict__ out, int N, int H, int W, int C64, int flip,
-                                                       int layout /*0: [27][C64]; 1: OIHW [3][C64][9] (head); 2: OIHW [C64][3][9] (neck)*/) {
+                                                       int layout /*0: [27][C64]; 1: OIHW [3][C64][9] (head); 2: OIHW [C64][3][9] (neck)*/,
+                                                       DetRed red) {
   pdl_grid_sync();
   // thread = (k = c3*9 + tap, 8-channel group): one image value + one 16-B activation vector -> 8 FMAs per pixel;
   // a block walks a contiguous pixel range and issues 8 atomics per thread at the end.
   const int k = threadIdx.x >> 3, cg = threadIdx.x & 7;
-  if (k >= 27) return;
+  if (k < 27) {
   const int c3 = k / 9, r = (k % 9) / 3, s = k % 3;
   const int dy = flip ? 1 - r : r - 1, dx = flip ? 1 - s : s - 1;
   const int cbase = blockIdx.y * 64 + cg * 8;
@@ -594,18 +607,22 @@ __global__ void __launch_bounds__(224) wgrad_c3_kernel(const float* __restrict__
     if (layout == 1) idx = ((size_t)c3 * C64 + c64) * 9 + tap;
     else if (layout == 2) idx = ((size_t)c64 * 3 + c3) * 9 + tap;
     else idx = (size_t)k * C64 + c64;
-    atomicAdd(out + idx, acc[j]);
+    det_add(red, (int)idx, acc[j]);
   }
+  }
+  det_finish(red, out, 27 * C64);
 }
 
 // bias gradient: db[c] += sum over pixels of g[pix, c]  (g NHWC T, C channels)
 template <typename T>
 __global__ void __launch_bounds__(256) bias_grad_kernel(const T* __restrict__ g, float* __restrict__ db, size_t npix, int C,
-                                                        int ps_perm /* g columns pixel-shuffle-permuted: col q*C/4+c <-> channel 4c+q */) {
+                                                        int ps_perm /* g columns pixel-shuffle-permuted: col q*C/4+c <-> channel 4c+q */,
+                                                        DetRed red) {
   pdl_grid_sync();
-  // thread = (8-channel vector, pixel lane): 16-B loads, register accumulation, one smem + one global atomic per channel
-  extern __shared__ float s_acc[];           // [C]
-  for (int c = threadIdx.x; c < C; c += blockDim.x) s_acc[c] = 0.f;
+  // thread = (8-channel vector, pixel lane): 16-B loads, register accumulation, one smem + one global FIXED-POINT atomic
+  // per channel (integer adds: the total does not depend on the order of lanes or blocks)
+  extern __shared__ unsigned long long s_acc[];           // [C]
+  for (int c = threadIdx.x; c < C; c += blockDim.x) s_acc[c] = 0ull;
   __syncthreads();
   const int vpp = C / 8;                     // vectors per pixel
   const int lanes = blockDim.x / vpp;        // pixel lanes per block (host guarantees blockDim.x % vpp == 0)
@@ -627,15 +644,16 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(const T* __restrict__ g,
       }
     }
 #pragma unroll
-    for (int k = 0; k < 8; ++k) atomicAdd(&s_acc[cv * 8 + k], acc[k]);
+    for (int k = 0; k < 8; ++k) atomicAdd(&s_acc[cv * 8 + k], det_fix(acc[k]));
   }
   __syncthreads();
   const int cq = C >> 2;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(db + (ps_perm ? 4 * (c % cq) + c / cq : c), s_acc[c]);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(red.acc + (ps_perm ? 4 * (c % cq) + c / cq : c), s_acc[c]);
+  det_finish(red, db, C);
 }
 // fp32 NCHW variant (head bias: g = dpre [N,3,H,W])
 __global__ void __launch_bounds__(256) bias_grad_nchw_kernel(const float* __restrict__ g, float* __restrict__ db, int N, int C,
-                                                             size_t HW) {
+                                                             size_t HW, DetRed red) {
   pdl_grid_sync();
   __shared__ float sm[32];
   const int c = blockIdx.y;
@@ -644,7 +662,8 @@ __global__ void __launch_bounds__(256) bias_grad_nchw_kernel(const float* __rest
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (size_t)gridDim.x * blockDim.x)
       acc += g[((size_t)n * C + c) * HW + i];
   acc = block_sum(acc, sm);
-  if (threadIdx.x == 0) atomicAdd(db + c, acc);
+  if (threadIdx.x == 0) det_add(red, c, acc);
+  det_finish(red, db, C);
 }
 
 // ------------------------------------------------------------------ fused flat AdamW (trainer.py:33-38,181,196)
