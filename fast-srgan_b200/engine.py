@@ -356,10 +356,18 @@ class DiscriminatorNet:
         ctx = dict(img=img, d0=d0, layers=layers, act6=cur) if save else None
         return z, ctx
 
-    def backward(self, ctx, dz: torch.Tensor, wgrad: bool, d_img: Optional[torch.Tensor]):
+    def backward(self, ctx, dz: torch.Tensor, wgrad: bool, d_img: Optional[torch.Tensor], defer: Optional[list] = None):
         """dz fp32 [N,6,6].  wgrad: accumulate parameter gradients (D step).  d_img: fp32 NCHW image-gradient
-        accumulator (G step; the wasted D weight gradients of trainer.py:195 are skipped - never consumed)."""
+        accumulator (G step; the wasted D weight gradients of trainer.py:195 are skipped - never consumed).
+        defer: a list - the weight / bias gradient launches (off the data-gradient chain's critical path) are not issued
+        but appended as closures; the caller runs them later, e.g. on a side stream (GANEngine._seg_d_update)."""
         p, g, P = self.fp.p, self.fp.g, self.P
+
+        def later(fn):
+            if defer is None:
+                fn()
+            else:
+                defer.append(fn)
         dcur = ops.conv1x1_to1_bwd(ctx["act6"], p["stem.7.weight"].view(-1), dz,
                                    g["stem.7.weight"].view(-1) if wgrad else None, g["stem.7.bias"] if wgrad else None)
         dcur_parity = False
@@ -371,7 +379,7 @@ class DiscriminatorNet:
             else:
                 draw = ops.instnorm_bwd(raw, st, dcur, act=L.ACT_LRELU, slope=0.01)
             if wgrad:
-                ops.conv3x3_wgrad(xin, draw, g[f"stem.{i}.conv.weight"], stride=s)
+                later(lambda xin=xin, draw=draw, i=i, s=s: ops.conv3x3_wgrad(xin, draw, g[f"stem.{i}.conv.weight"], stride=s))
             if i == 0 and not (wgrad or d_img is not None):
                 break
             dcur = ops.conv3x3_gen(draw, P[f"t{i}"], self.widths[i][0], stride=s, mode=1)
@@ -380,8 +388,9 @@ class DiscriminatorNet:
                 dcur = ops.parity_layout(dcur, False)
         dv = ops.act_bwd(ctx["d0"], dcur, L.ACT_LRELU, slope=0.2)
         if wgrad:
-            ops.wgrad_c3(ctx["img"], dv, g["neck.0.weight"], flip=False, layout=2)
-            ops.bias_grad(dv, g["neck.0.bias"])
+            img = ctx["img"]
+            later(lambda: ops.wgrad_c3(img, dv, g["neck.0.weight"], flip=False, layout=2))
+            later(lambda: ops.bias_grad(dv, g["neck.0.bias"]))
         if d_img is not None:
             ops.conv3x3_c64_head(dv, P["neck.t"], None, out_u8=3, out=d_img)
 
@@ -510,6 +519,10 @@ class GANEngine:
         self.pg = process_group
         import os
         self.use_graph = os.environ.get("FSR_GRAPH", "1") != "0"
+        self.defer_d_wgrad = os.environ.get("FSR_DEFER_D_WGRAD", "1") != "0"
+        self.adv_on_side = os.environ.get("FSR_ADV_SIDE", "1") != "0"
+        self._d_sr_adv = None
+        self._d_deferred = None
         self.overlap = os.environ.get("FSR_TRAIN_OVERLAP", "1") != "0"
         self._graphs: Dict = {}
         self._side: Optional[torch.cuda.Stream] = None
@@ -584,7 +597,7 @@ class GANEngine:
 
     def _step(self, ins):
         """The whole iteration on the current stream (+ the side stream of the overlap window)."""
-        self._seg_d(ins)
+        self._seg_d(ins, defer=self.overlap and self.defer_d_wgrad)
         main = torch.cuda.current_stream()
         if self.overlap:
             if self._side is None:
@@ -593,12 +606,18 @@ class GANEngine:
             side.wait_stream(main)                                      # D gradients are complete
             with torch.cuda.stream(side):
                 self._seg_d_update()
+                if self.adv_on_side:
+                    self._seg_adv(ins)                                  # D(sr) through the updated D: independent of VGG too
             self._seg_content(ins)                                      # VGG passes: independent of the discriminator
             main.wait_stream(side)                                      # updated + re-packed D before D(sr) at :186
+            self._d_deferred = None                                     # the side stream's operands may be recycled now
+            if not self.adv_on_side:
+                self._seg_adv(ins)
         else:
             self._seg_d_update()
             self._seg_content(ins)
-        self._seg_adv_and_g(ins)
+            self._seg_adv(ins)
+        self._seg_g(ins)
         self._allreduce(self.gp.grad)
         self._seg_opt(ins)
         return self._out
@@ -607,7 +626,7 @@ class GANEngine:
         return self._step(ins)
 
     # ------------------------------------------------------------------ segments
-    def _seg_d(self, ins):
+    def _seg_d(self, ins, defer: bool = False):
         """G(lr) (saved for the generator step) and the discriminator step up to its gradient (trainer.py:171-180)."""
         lr_img, hr_img, n_real, n_fake, _ = ins
         S = self.S
@@ -628,10 +647,16 @@ class GANEngine:
         dz = torch.empty_like(z)
         ops.bce_logits(z[B:], n_real, 0.3, 0.8, losses[0:1], dz[B:], grad_scale=0.5 * S)     # :175,177,179
         ops.bce_logits(z[:B], n_fake, 0.3, 0.0, losses[1:2], dz[:B], grad_scale=0.5 * S)     # :176,178,179
-        self.D.backward(ctx, dz, wgrad=True, d_img=None)                # :180
+        # :180 - the weight gradients are off the data-gradient chain: they are issued in _seg_d_update (side stream of the
+        # overlap window), where they fill the SMs the small VGG layers leave idle
+        self._d_deferred = [] if defer else None
+        self.D.backward(ctx, dz, wgrad=True, d_img=None, defer=self._d_deferred)
 
     def _seg_d_update(self):
-        """gradient exchange + discriminator AdamW (trainer.py:181) + re-pack of its weights (side stream)."""
+        """discriminator weight gradients (deferred from _seg_d) + gradient exchange + discriminator AdamW (trainer.py:181)
+        + re-pack of its weights (side stream)."""
+        for fn in (self._d_deferred or ()):
+            fn()
         self._allreduce(self.dp.grad)
         self.dp.adamw_step(self.lr_d, grad_scale=1.0 / (self.S * self.world))
         self.D.pack(need_bwd=True, force=True)
@@ -652,14 +677,25 @@ class GANEngine:
         self.V.backward(ctx_v, dfeat, self._d_sr)                       # :195 (VGG branch)
         self._nfeat = float(nfeat)
 
-    def _seg_adv_and_g(self, ins):
-        """adversarial loss through the UPDATED discriminator and the generator backward (trainer.py:186-188, :195)."""
+    def _seg_adv(self, ins):
+        """adversarial loss through the UPDATED discriminator and its gradient w.r.t. sr (trainer.py:186-188 and the D branch
+        of :195) into its own buffer: it may run on the side stream while the VGG branch fills self._d_sr."""
         n_g = ins[4]
         S, losses, sr = self.S, self._losses, self._sr
         z, ctx_d = self.D.forward(sr, save=True)                        # :186 (updated D)
         dz = torch.empty_like(z)
         ops.bce_logits(z, n_g, 0.3, 0.7, losses[2:3], dz, grad_scale=0.5 * 0.1 * S)          # :187-188,194
-        self.D.backward(ctx_d, dz, wgrad=False, d_img=self._d_sr)       # :195 (D branch; its wasted wgrad is skipped)
+        self._d_sr_adv = torch.zeros_like(sr)
+        self.D.backward(ctx_d, dz, wgrad=False, d_img=self._d_sr_adv)   # :195 (D branch; its wasted wgrad is skipped)
+
+    def _seg_adv_and_g(self, ins):                                       # diagnostics / tests: both halves on this stream
+        self._seg_adv(ins)
+        self._seg_g(ins)
+
+    def _seg_g(self, ins):
+        """the generator backward from the summed image gradient (trainer.py:195, :194's sum of the two losses)."""
+        losses, sr = self._losses, self._sr
+        self._d_sr.add_(self._d_sr_adv)                                 # VGG branch + D branch (fp32: a + b as before)
         self.G.backward(self._ctx_g, self._d_sr)
         self._out = dict(loss_real=losses[0], loss_fake=losses[1], adv_loss=0.1 * losses[2], content_loss=losses[3] / self._nfeat, sr=sr)
 
