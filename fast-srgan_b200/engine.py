@@ -521,6 +521,7 @@ class GANEngine:
         self.use_graph = os.environ.get("FSR_GRAPH", "1") != "0"
         self.defer_d_wgrad = os.environ.get("FSR_DEFER_D_WGRAD", "1") != "0"
         self.adv_on_side = os.environ.get("FSR_ADV_SIDE", "1") != "0"
+        self.d_on_side = os.environ.get("FSR_D_SIDE", "1") != "0"
         self._d_sr_adv = None
         self._d_deferred = None
         self.overlap = os.environ.get("FSR_TRAIN_OVERLAP", "1") != "0"
@@ -597,14 +598,19 @@ class GANEngine:
 
     def _step(self, ins):
         """The whole iteration on the current stream (+ the side stream of the overlap window)."""
-        self._seg_d(ins, defer=self.overlap and self.defer_d_wgrad)
+        d_side = self.overlap and self.d_on_side
+        self._seg_gfwd(ins)
+        if not d_side:
+            self._seg_dstep(ins, defer=self.overlap and self.defer_d_wgrad)
         main = torch.cuda.current_stream()
         if self.overlap:
             if self._side is None:
                 self._side = torch.cuda.Stream()
             side = self._side
-            side.wait_stream(main)                                      # D gradients are complete
+            side.wait_stream(main)                                      # sr = G(lr) (d_on_side) / the D gradients are complete
             with torch.cuda.stream(side):
+                if d_side:
+                    self._seg_dstep(ins, defer=False)                   # the whole discriminator step beside the VGG passes
                 self._seg_d_update()
                 if self.adv_on_side:
                     self._seg_adv(ins)                                  # D(sr) through the updated D: independent of VGG too
@@ -626,8 +632,12 @@ class GANEngine:
         return self._step(ins)
 
     # ------------------------------------------------------------------ segments
-    def _seg_d(self, ins, defer: bool = False):
-        """G(lr) (saved for the generator step) and the discriminator step up to its gradient (trainer.py:171-180)."""
+    def _seg_d(self, ins, defer: bool = False):                         # diagnostics / tests: both halves on this stream
+        self._seg_gfwd(ins)
+        self._seg_dstep(ins, defer)
+
+    def _seg_gfwd(self, ins):
+        """G(lr) (saved for the generator step) into the first half of the image batch X = [sr; hr] (trainer.py:173 == :185)."""
         lr_img, hr_img, n_real, n_fake, _ = ins
         S = self.S
         self._losses = losses = torch.zeros(4, dtype=torch.float32, device=lr_img.device)   # real, fake, adv bce, content sum
@@ -643,6 +653,12 @@ class GANEngine:
         self._X = X
         self._sr, self._ctx_g = self.G.forward(lr_img, save=True, out=X[:B])      # :173 == :185 (see class docstring)
         X[B:].copy_(hr_img)
+
+    def _seg_dstep(self, ins, defer: bool = False):
+        """the discriminator step up to its gradient (trainer.py:171-180) on X = [sr; hr]."""
+        _, _, n_real, n_fake, _ = ins
+        S, losses, X = self.S, self._losses, self._X
+        B = X.shape[0] // 2
         z, ctx = self.D.forward(X, save=True)                           # :172 (second half) and :174 (first half)
         dz = torch.empty_like(z)
         ops.bce_logits(z[B:], n_real, 0.3, 0.8, losses[0:1], dz[B:], grad_scale=0.5 * S)     # :175,177,179
