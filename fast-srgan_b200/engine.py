@@ -260,18 +260,33 @@ class GeneratorNet:
         ctx = dict(lr=lr_img, a0=a0, xa=xa, blocks=blocks, rawb=rawb, stb=stb, xb=xb, U0=U0, U1=U1, sr=sr) if save else None
         return sr, ctx
 
-    def backward(self, ctx, d_sr: torch.Tensor):
-        """d_sr: fp32 NCHW gradient w.r.t. the generator output; accumulates into fp.g."""
+    def backward(self, ctx, d_sr: torch.Tensor, side: Optional[torch.cuda.Stream] = None):
+        """d_sr: fp32 NCHW gradient w.r.t. the generator output; accumulates into fp.g.
+        side: a stream for the weight / bias gradients.  They are off the data-gradient chain's critical path: each is issued
+        on `side` behind an event recorded where its operands are complete, so it fills the SMs the chain's small launches
+        leave idle; the current stream waits for `side` before returning.  (All weight-gradient launches then share `side`,
+        hence the single partial-sum workspace stays race-free.)"""
         p, g, P, dt, Fm = self.fp.p, self.fp.g, self.P, self.dt, self.F
         Lb = self.L
+        main = torch.cuda.current_stream() if side is not None else None
+        keep = []                                             # operands of side-stream launches stay referenced until the join
+
+        def off(fn, *operands):
+            if side is None:
+                fn()
+                return
+            keep.append(operands)
+            side.wait_event(main.record_event())
+            with torch.cuda.stream(side):
+                fn()
         dpre = ops.tanh_bwd(ctx["sr"], d_sr)                                           # model.py:109
-        ops.wgrad_c3(dpre, ctx["U1"], g["head.0.weight"], flip=True, layout=1)
-        ops.bias_grad_nchw(dpre, g["head.0.bias"])
+        off(lambda: (ops.wgrad_c3(dpre, ctx["U1"], g["head.0.weight"], flip=True, layout=1),
+                     ops.bias_grad_nchw(dpre, g["head.0.bias"])), dpre)
         dU = ops.neck_conv3x3(dpre, P["head.t"], None, dt, act=L.ACT_NONE)              # dgrad of model.py:103-108
         for i, (U, xin) in ((1, (ctx["U1"], ctx["U0"])), (0, (ctx["U0"], ctx["xb"]))):   # model.py:39-40
             dconv = ops.ps_prelu_bwd(U, dU, p[f"upsampling.{i}.relu.weight"], g[f"upsampling.{i}.relu.weight"])
-            ops.conv3x3_wgrad(xin, dconv, g[f"upsampling.{i}.conv.weight"], ps_perm=True)
-            ops.bias_grad(dconv, g[f"upsampling.{i}.conv.bias"], ps_perm=True)
+            off(lambda xin=xin, dconv=dconv, i=i: (ops.conv3x3_wgrad(xin, dconv, g[f"upsampling.{i}.conv.weight"], ps_perm=True),
+                                                   ops.bias_grad(dconv, g[f"upsampling.{i}.conv.bias"], ps_perm=True)), xin, dconv)
             dU = ops.conv3x3_gen(dconv, P[f"up{i}.t"], Fm, mode=1)
         dxb = dU
         # output gradients of the 2L+1 F->F convs, same slot order as the input arena of forward()
@@ -279,6 +294,16 @@ class GeneratorNet:
         da = torch.empty_like(xa)
         ops.instnorm_bwd(ctx["rawb"], ctx["stb"], dxb, out=da[2 * Lb])                  # model.py:94
         dcur = self._dgrad(da[2 * Lb], "bottleneck.0.weight")
+        # all 2L+1 weight gradients of the residual chain: grouped tcgen05 launches (<= 148 (group, cin, cout) pairs each);
+        # with a side stream the upper half of the chain is launched as soon as its output gradients exist
+        names = self._convs64()
+        per = max(1, 148 // ((Fm // 64) ** 2))
+
+        def wgrad_slots(k0, k1):
+            for a in range(k0, k1, per):
+                b = min(a + per, k1)
+                ops.conv3x3_wgrad_grouped(xa[a:b], da[a:b], [g[n] for n in names[a:b]])
+        half = Lb // 2 if side is not None else 0                                       # blocks >= half: slots 2*half .. 2L
         for i in reversed(range(Lb)):                                                   # model.py:67-69
             raw1, st1, raw2, st2 = ctx["blocks"][i]
             ops.instnorm_bwd(raw2, st2, dcur, out=da[2 * i + 1])
@@ -287,15 +312,16 @@ class GeneratorNet:
                              dalpha=g[f"stem.{i}.relu1.weight"], out=da[2 * i])
             din = self._dgrad(da[2 * i], f"stem.{i}.conv1.weight")
             dcur = ops.add(din, dcur)                                                   # + skip (model.py:69)
-        # all 2L+1 weight gradients of the residual chain: grouped tcgen05 launches (<= 148 (group, cin, cout) pairs each)
-        names = self._convs64()
-        per = max(1, 148 // ((Fm // 64) ** 2))
-        for k0 in range(0, len(names), per):
-            ops.conv3x3_wgrad_grouped(xa[k0:k0 + per], da[k0:k0 + per], [g[n] for n in names[k0:k0 + per]])
+            if i == half and half > 0:
+                off(lambda: wgrad_slots(2 * half, 2 * Lb + 1))
+        off(lambda: wgrad_slots(0, 2 * half if half > 0 else 2 * Lb + 1))
         da0 = ops.add(dcur, dxb)                                                        # + long skip (model.py:115)
         dv = ops.act_bwd(ctx["a0"], da0, L.ACT_PRELU, alpha=p["neck.1.weight"], dalpha=g["neck.1.weight"])
-        ops.wgrad_c3(ctx["lr"], dv, g["neck.0.weight"], flip=False, layout=2)           # model.py:76
-        ops.bias_grad(dv, g["neck.0.bias"])
+        off(lambda: (ops.wgrad_c3(ctx["lr"], dv, g["neck.0.weight"], flip=False, layout=2),           # model.py:76
+                     ops.bias_grad(dv, g["neck.0.bias"])), dv)
+        if side is not None:
+            main.wait_stream(side)
+        keep.clear()
 
 
 # ====================================================================================== Discriminator
@@ -522,6 +548,7 @@ class GANEngine:
         self.defer_d_wgrad = os.environ.get("FSR_DEFER_D_WGRAD", "1") != "0"
         self.adv_on_side = os.environ.get("FSR_ADV_SIDE", "1") != "0"
         self.d_on_side = os.environ.get("FSR_D_SIDE", "1") != "0"
+        self.g_wgrad_side = os.environ.get("FSR_G_WGRAD_SIDE", "1") != "0"
         self._d_sr_adv = None
         self._d_deferred = None
         self.overlap = os.environ.get("FSR_TRAIN_OVERLAP", "1") != "0"
@@ -712,7 +739,7 @@ class GANEngine:
         """the generator backward from the summed image gradient (trainer.py:195, :194's sum of the two losses)."""
         losses, sr = self._losses, self._sr
         self._d_sr.add_(self._d_sr_adv)                                 # VGG branch + D branch (fp32: a + b as before)
-        self.G.backward(self._ctx_g, self._d_sr)
+        self.G.backward(self._ctx_g, self._d_sr, side=self._side if (self.overlap and self.g_wgrad_side) else None)
         self._out = dict(loss_real=losses[0], loss_fake=losses[1], adv_loss=0.1 * losses[2], content_loss=losses[3] / self._nfeat, sr=sr)
 
     def _seg_opt(self, ins):
