@@ -1471,8 +1471,14 @@ static int instnorm_bwd_impl(const void* raw, const int64_t* stats, const void* 
     // training shapes: one launch, the per-(n,c) sums stay inside the block (no `red` scratch, no memset, no atomics)
     if (act == FSR_ACT_PRELU && dalpha) { const int rc = det_slot(&p.det); if (rc) return rc; }
     LaunchScope scope(FSR_K_NONE - 1, st);
-    FSR_T((PdlLaunch(dim3(C / 16, N), 256, 0, st)(instnorm_bwd_fused_kernel<__half>, p)),
-          (PdlLaunch(dim3(C / 16, N), 256, 0, st)(instnorm_bwd_fused_kernel<__nv_bfloat16>, p)));
+    static const int res_on = [] { const char* e = getenv("FSR_IN_BWD_RES"); return (e && e[0] == '1') ? 1 : 0; }();
+    if (res_on && HW <= 128 * 5) {           // register-resident variant (see the kernel): measured SLOWER (6.21 -> 6.28 ms step), opt-in
+      FSR_T((PdlLaunch(dim3(C / 16, N), 256, 0, st)(instnorm_bwd_fused_kernel<__half, 5>, p)),
+            (PdlLaunch(dim3(C / 16, N), 256, 0, st)(instnorm_bwd_fused_kernel<__nv_bfloat16, 5>, p)));
+    } else {
+      FSR_T((PdlLaunch(dim3(C / 16, N), 256, 0, st)(instnorm_bwd_fused_kernel<__half, 0>, p)),
+            (PdlLaunch(dim3(C / 16, N), 256, 0, st)(instnorm_bwd_fused_kernel<__nv_bfloat16, 0>, p)));
+    }
     return cuda_rc(cudaGetLastError());
   }
   if (!red) return FSR_ERR_BAD_ARG;

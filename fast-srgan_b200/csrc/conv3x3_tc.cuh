@@ -331,9 +331,17 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
         const int x0 = tx * TW, y0 = ty * TH;
         if (n != cur_n) {
+          // the four lanes that share channel group g (lane & 7) decode two channels each (fp64 divide + sqrt: ~0.4 us
+          // apiece, serial) and exchange them - the small training planes change image every other tile
+          float m2[2], r2[2];
 #pragma unroll
-          for (int k = 0; k < 8; ++k)
-            stat_mean_rstd(p.in_stats + ((size_t)n * 64 + 8 * g + k) * 2, inv_hw, p.in_eps, mean[k], rstd[k]);
+          for (int j = 0; j < 2; ++j)
+            stat_mean_rstd(p.in_stats + ((size_t)n * 64 + 8 * g + 2 * (lane >> 3) + j) * 2, inv_hw, p.in_eps, m2[j], r2[j]);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            mean[k] = __shfl_sync(0xffffffffu, m2[k & 1], (k >> 1) * 8 + g);
+            rstd[k] = __shfl_sync(0xffffffffu, r2[k & 1], (k >> 1) * 8 + g);
+          }
           cur_n = n;
         }
         const bool inside = (y0 >= 1) && (x0 >= 1) && (y0 + TH + 1 <= p.H) && (x0 + TW + 1 <= p.W);   // whole halo box in the image
@@ -394,9 +402,17 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
         const int x0 = tx * TW, y0 = ty * TH;
         if (n != cur_n) {
+          // the four lanes that share channel group g (lane & 7) decode two channels each (fp64 divide + sqrt: ~0.4 us
+          // apiece, serial) and exchange them - the small training planes change image every other tile
+          float m2[2], r2[2];
 #pragma unroll
-          for (int k = 0; k < 8; ++k)
-            stat_mean_rstd(p.in_stats + ((size_t)n * 64 + 8 * g + k) * 2, inv_hw, p.in_eps, mean[k], rstd[k]);
+          for (int j = 0; j < 2; ++j)
+            stat_mean_rstd(p.in_stats + ((size_t)n * 64 + 8 * g + 2 * (lane >> 3) + j) * 2, inv_hw, p.in_eps, m2[j], r2[j]);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            mean[k] = __shfl_sync(0xffffffffu, m2[k & 1], (k >> 1) * 8 + g);
+            rstd[k] = __shfl_sync(0xffffffffu, r2[k & 1], (k >> 1) * 8 + g);
+          }
           cur_n = n;
         }
         constexpr int kRows = Geo::kBoxW * Geo::kBoxH;                    // 180

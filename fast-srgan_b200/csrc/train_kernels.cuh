@@ -360,24 +360,23 @@ __global__ void __launch_bounds__(256) instnorm_bwd_kernel(const InBwdParams p) 
 }
 
 // Single-launch form for the small planes of the training shapes (HW <= 4096): one block owns one sample's 16-channel
-// group (a full 32-byte sector per pixel), sweeps the plane twice (the second sweep hits L1/L2) - pass 1 sums, pass 2
-// writes dRaw.  Replaces 2 launches + 1 memset per call and keeps the per-(n,c) sums inside the block (fixed-order
-// reduction, no atomics): the InstanceNorm backward is bitwise reproducible.
-template <typename T>
+// group (a full 32-byte sector per pixel) - pass 1 sums, pass 2 writes dRaw.  Replaces 2 launches + 1 memset per call and
+// keeps the per-(n,c) sums inside the block (fixed-order reduction, no atomics): the InstanceNorm backward is bitwise
+// reproducible.  RES > 0 (HW <= 128 * RES, the 24x24 / 12x12 / 6x6 planes): every thread's pixels are loaded ONCE, all
+// loads in flight together before the statistics are even decoded, and both passes run from registers - these launches
+// sit on the critical path of the backward chains and were latency-bound (two dependent sweeps of 4-5 serial loads).
+// RES = 0: two streaming sweeps (the second hits L1/L2).  Same arithmetic in the same order either way.
+template <typename T, int RES>
 __global__ void __launch_bounds__(256) instnorm_bwd_fused_kernel(const InBwdParams p) {
   pdl_grid_sync();
   __shared__ float s_red[8][2][16];                  // [warp][vector of the pixel][a1 0..7, a2 0..7]
   __shared__ float s_m[2][16];                       // mean(g), mean(g*xhat) per (vector, channel)
+  __shared__ float s_mr[2][16];                      // mean, rstd of the block's 16 channels
   __shared__ float s_da[8];
   const int n = blockIdx.y, cg = blockIdx.x;          // sample, 16-channel group
   const int vec = threadIdx.x & 1, pl = threadIdx.x >> 1;   // 128 pixel lanes x 2 vectors of 8 channels
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c0 = cg * 16 + vec * 8;
-  float mean[8], rstd[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) stat_mean_rstd(p.stats + ((size_t)n * p.C + c0 + k) * 2, 1.0 / (double)p.HW, p.eps, mean[k], rstd[k]);
-  const float slope = (p.act == ACT_PRELU) ? __ldg(p.alpha) : p.slope;
-  const bool has_act = (p.act == ACT_PRELU || p.act == ACT_LRELU);
   const size_t base = ((size_t)n * p.HW) * p.C + c0;
   const T* raw = reinterpret_cast<const T*>(p.raw) + base;
   const T* dy = reinterpret_cast<const T*>(p.dy) + base;
@@ -389,11 +388,30 @@ __global__ void __launch_bounds__(256) instnorm_bwd_fused_kernel(const InBwdPara
     const int y = px / pw, x = px - y * pw;
     return (size_t)(((y & 1) * 2 + (x & 1)) * ph2 + (y >> 1)) * pw2 + (x >> 1);
   };
+  constexpr int NR = RES > 0 ? RES : 1;
+  uint4 rr[NR], gg[NR];
+  if constexpr (RES > 0) {
+#pragma unroll
+    for (int u = 0; u < RES; ++u) {
+      const int px = pl + u * 128;
+      const bool ok = px < p.HW;
+      rr[u] = ok ? *reinterpret_cast<const uint4*>(raw + (size_t)px * p.C) : make_uint4(0, 0, 0, 0);
+      gg[u] = ok ? *reinterpret_cast<const uint4*>(dy + dy_px(px) * p.C) : make_uint4(0, 0, 0, 0);
+    }
+  }
+  if (threadIdx.x < 16)                               // one fp64 decode per channel of the block instead of 8 per thread
+    stat_mean_rstd(p.stats + ((size_t)n * p.C + cg * 16 + threadIdx.x) * 2, 1.0 / (double)p.HW, p.eps, s_mr[0][threadIdx.x],
+                   s_mr[1][threadIdx.x]);
+  __syncthreads();
+  float mean[8], rstd[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { mean[k] = s_mr[0][vec * 8 + k]; rstd[k] = s_mr[1][vec * 8 + k]; }
+  const float slope = (p.act == ACT_PRELU) ? __ldg(p.alpha) : p.slope;
+  const bool has_act = (p.act == ACT_PRELU || p.act == ACT_LRELU);
   float a1[8], a2[8], da = 0.f;
 #pragma unroll
   for (int k = 0; k < 8; ++k) { a1[k] = 0.f; a2[k] = 0.f; }
-  for (int px = pl; px < p.HW; px += 128) {
-    const uint4 r = *reinterpret_cast<const uint4*>(raw + (size_t)px * p.C), g4 = *reinterpret_cast<const uint4*>(dy + dy_px(px) * p.C);
+  auto accum = [&](const uint4& r, const uint4& g4) {
     const uint32_t ru[4] = {r.x, r.y, r.z, r.w}, gu[4] = {g4.x, g4.y, g4.z, g4.w};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -407,6 +425,14 @@ __global__ void __launch_bounds__(256) instnorm_bwd_fused_kernel(const InBwdPara
       a1[2 * k] += g0; a2[2 * k] = fmaf(g0, xh0, a2[2 * k]);
       a1[2 * k + 1] += g1; a2[2 * k + 1] = fmaf(g1, xh1, a2[2 * k + 1]);
     }
+  };
+  if constexpr (RES > 0) {
+#pragma unroll
+    for (int u = 0; u < RES; ++u)
+      if (pl + u * 128 < p.HW) accum(rr[u], gg[u]);
+  } else {
+    for (int px = pl; px < p.HW; px += 128)
+      accum(*reinterpret_cast<const uint4*>(raw + (size_t)px * p.C), *reinterpret_cast<const uint4*>(dy + dy_px(px) * p.C));
   }
   // warp: lanes of equal parity hold the same channel vector -> butterfly over lane bits 1..4, then 8 warps through smem
 #pragma unroll
@@ -442,8 +468,7 @@ __global__ void __launch_bounds__(256) instnorm_bwd_fused_kernel(const InBwdPara
   float m1[8], m2[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) { m1[k] = s_m[vec][k]; m2[k] = s_m[vec][8 + k]; }
-  for (int px = pl; px < p.HW; px += 128) {
-    const uint4 r = *reinterpret_cast<const uint4*>(raw + (size_t)px * p.C), g4 = *reinterpret_cast<const uint4*>(dy + dy_px(px) * p.C);
+  auto emit = [&](const uint4& r, const uint4& g4, int px) {
     const uint32_t ru[4] = {r.x, r.y, r.z, r.w}, gu[4] = {g4.x, g4.y, g4.z, g4.w};
     uint32_t ou[4];
 #pragma unroll
@@ -458,6 +483,14 @@ __global__ void __launch_bounds__(256) instnorm_bwd_fused_kernel(const InBwdPara
       ou[k] = Cvt<T>::pack2(rstd[2 * k] * (g0 - m1[2 * k] - xh0 * m2[2 * k]), rstd[2 * k + 1] * (g1 - m1[2 * k + 1] - xh1 * m2[2 * k + 1]));
     }
     *reinterpret_cast<uint4*>(draw + (size_t)px * p.C) = make_uint4(ou[0], ou[1], ou[2], ou[3]);
+  };
+  if constexpr (RES > 0) {
+#pragma unroll
+    for (int u = 0; u < RES; ++u)
+      if (pl + u * 128 < p.HW) emit(rr[u], gg[u], pl + u * 128);
+  } else {
+    for (int px = pl; px < p.HW; px += 128)
+      emit(*reinterpret_cast<const uint4*>(raw + (size_t)px * p.C), *reinterpret_cast<const uint4*>(dy + dy_px(px) * p.C), px);
   }
   if (p.act == ACT_PRELU && p.dalpha) det_finish(p.det, p.dalpha, 1);   // order-independent slope-gradient total
 }
