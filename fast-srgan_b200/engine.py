@@ -525,10 +525,14 @@ class GANEngine:
         at :185; between the two only the discriminator is updated, the forward is deterministic and InstanceNorm keeps
         no running statistics, so both evaluations are the same tensor bit for bit (asserted in
         tests/test_train_step_gpu.py::test_generator_forward_is_identical_before_and_after_the_d_step).
-      * the discriminator's gradient exchange (all-reduce over ranks), its AdamW step and the re-pack of its weights
-        run on a SIDE stream while the main stream runs the two VGG19 passes, the content loss and the VGG data
-        gradient - none of which touch the discriminator (SURVEY.md 8e "legal overlap windows"); D(sr) at :186 waits
-        for the side stream.
+      * two streams.  After G(lr) the SIDE stream takes everything that touches the discriminator - D([sr; hr]) forward
+        and backward with its weight gradients (:172-180), the gradient exchange (all-reduce over ranks), AdamW (:181),
+        the re-pack of its weights, then D(sr) through the UPDATED discriminator and its data gradient (:186-188) -
+        while the MAIN stream runs the two VGG19 passes, the content loss and the VGG data gradient (:190-192), none of
+        which touch the discriminator (SURVEY.md 8e "legal overlap windows").  They join before the generator's
+        backward (:195), whose weight / bias gradients are again issued on the side stream behind per-operand events
+        while the main stream walks the data-gradient chain.  Same arithmetic as one stream, bit for bit
+        (FSR_TRAIN_OVERLAP=0 / FSR_D_SIDE / FSR_ADV_SIDE / FSR_G_WGRAD_SIDE are the A/B switches).
       * the whole step - collectives included, issued through libfsr_b200's fsr_nccl_* - is captured into ONE CUDA graph
         per input shape after two eager warm-up steps."""
 
