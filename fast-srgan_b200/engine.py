@@ -531,8 +531,10 @@ class GANEngine:
         while the MAIN stream runs the two VGG19 passes, the content loss and the VGG data gradient (:190-192), none of
         which touch the discriminator (SURVEY.md 8e "legal overlap windows").  They join before the generator's
         backward (:195), whose weight / bias gradients are again issued on the side stream behind per-operand events
-        while the main stream walks the data-gradient chain.  Same arithmetic as one stream, bit for bit
-        (FSR_TRAIN_OVERLAP=0 / FSR_D_SIDE / FSR_ADV_SIDE / FSR_G_WGRAD_SIDE are the A/B switches).
+        while the main stream walks the data-gradient chain.  Same arithmetic as one stream: results are bit-identical
+        to the single-stream order except that the residual chain's grouped weight gradient is launched in two halves
+        (a different, still fixed, split of one sum).  A/B switches: FSR_TRAIN_OVERLAP, FSR_D_SIDE, FSR_ADV_SIDE,
+        FSR_G_WGRAD_SIDE.
       * the whole step - collectives included, issued through libfsr_b200's fsr_nccl_* - is captured into ONE CUDA graph
         per input shape after two eager warm-up steps."""
 
