@@ -3,7 +3,7 @@
 import torch
 import torch.nn.functional as F
 
-from fast_srgan_b200.pairs import _expand_up, expand_pair
+from fast_srgan_b200.pairs import _expand_up, _pad32, expand_pair
 
 
 def to_pairs(x):                      # NCHW [N,C,H,W] -> pair grid NCHW [N,2C,H,W/2], slot (parity, c)
@@ -44,3 +44,25 @@ def test_expand_up_matches_pixel_shuffle():
             out[:, i::2, j::2, :] = z[:, (2 * i + j) * 64:(2 * i + j + 1) * 64].permute(0, 2, 3, 1)
     got = out.reshape(N, 2 * H, 4 * Wp, 32).permute(0, 3, 1, 2)                   # pairs -> 32-channel pixels
     assert torch.allclose(got, ref, atol=1e-12)
+
+
+def test_narrow_networks_pad_to_32_channels_exactly():
+    """n_filters = 16: the upsampling conv [4F, F] padded to [128, 32] keeps reference channel 4c + q at its index, so the
+    pixel-shuffled output is the true 16 channels followed by 16 exact zeros (pairs.PairGenerator._pack)."""
+    g = torch.Generator().manual_seed(9)
+    Fn = 16
+    x = torch.randn((1, Fn, 4, 6), generator=g, dtype=torch.float64)
+    w = torch.randn((4 * Fn, Fn, 3, 3), generator=g, dtype=torch.float64)
+    b = torch.randn(4 * Fn, generator=g, dtype=torch.float64)
+    ref = F.pixel_shuffle(F.conv2d(x, w, b, padding=1), 2)                        # [1,16,8,12]
+    w2, b2 = _expand_up(_pad32(w, 128, 32).double(), _pad32(b, 128).double())
+    xp = torch.zeros((1, 32, 4, 6), dtype=torch.float64)
+    xp[:, :Fn] = x
+    z = F.conv2d(to_pairs(xp), w2, b2, padding=1)
+    N, _, H, Wp = z.shape
+    out = torch.zeros((N, 2 * H, 2 * Wp, 64), dtype=torch.float64)
+    for i in (0, 1):
+        for j in (0, 1):
+            out[:, i::2, j::2, :] = z[:, (2 * i + j) * 64:(2 * i + j + 1) * 64].permute(0, 2, 3, 1)
+    got = out.reshape(N, 2 * H, 4 * Wp, 32).permute(0, 3, 1, 2)
+    assert torch.allclose(got[:, :Fn], ref, atol=1e-6) and got[:, Fn:].abs().max().item() == 0.0
